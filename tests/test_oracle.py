@@ -1,0 +1,182 @@
+"""CPU tests: the oracle against the golden fixtures (reference SymPy derivation and
+reference pure-Python GP layer, tests/golden/make_golden_*.py) and against itself
+(literal loops vs vectorised twins vs C restatement; C hybrd1 vs SciPy MINPACK)."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import c_oracle as C
+from oracle import oracle as O
+from oracle.kernel_forms import FAMILIES, NAMES
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = os.path.join(HERE, "golden")
+
+
+@pytest.mark.parametrize("family", ["product", "sq", "sum", "period"])
+def test_scalar_forms_match_reference_sympy(family):
+    g = np.load(os.path.join(G, f"kernel_forms_{family}.npz"))
+    pts = g["points"]
+    cls = FAMILIES[family]
+    for name in NAMES:
+        v = getattr(cls, name)(*pts.T)
+        ref = g[name]
+        scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)) + 1e-300)
+        assert np.max(np.abs(v - ref) / scale) < 1e-12, (family, name)
+
+
+def test_period_half_equals_product():
+    g = np.load(os.path.join(G, "kernel_forms_product.npz"))
+    pts = g["points"]
+    for name in NAMES:
+        a = getattr(FAMILIES["product"], name)(*pts.T)
+        b = getattr(FAMILIES["period"], name)(*pts.T, 0.5)
+        assert np.allclose(a, b, rtol=1e-12, atol=1e-14), name
+
+
+LIT = dict(x=np.array([1.0, 2.0, 3.0]), y=np.array([0.0, 3.0, 2.0]), x0=np.array([1.0, 2.0]),
+           y0=np.array([0.0, 3.0]), hyp=np.array([0.5, 2.0, 0.4]), hypp=np.array([0.6, 1.9, 0.3]))
+
+
+@pytest.mark.parametrize("family", ["product", "sq"])
+def test_literal_inputs_of_test_sympgpr(family):
+    """Inputs of python/05_tokamak/SympGPR/test_sympgpr.py:7-10,19,48-68, tolerance :26-74."""
+    g = np.load(os.path.join(G, f"path_{family}.npz"))
+    x, y, x0, y0, hyp, hypp = (LIT[k] for k in ("x", "y", "x0", "y0", "hyp", "hypp"))
+    K = np.empty((6, 4), order="F")
+    O.build_k(x, y, x0, y0, hyp, K, family)
+    for Kt in (K, O.build_k_vec(x, y, x0, y0, hyp, family), C.build_k(x, y, x0, y0, hyp, family=family)):
+        assert np.allclose(Kt, g["lit_build_k"], rtol=1e-12, atol=1e-12)
+    Kr = np.empty((3, 2), order="F")
+    O.buildkreg(x, y, x0, y0, hyp, Kr, family)
+    for Kt in (Kr, O.buildkreg_vec(x, y, x0, y0, hyp, family), C.buildkreg(x, y, x0, y0, hyp, family)):
+        assert np.allclose(Kt, g["lit_buildkreg"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(O.buildkreg_vec(x[:1], y[:1], x0, y0, hyp, family), g["lit_buildkreg_1"], rtol=1e-12, atol=1e-12)
+    Kyinvp = np.array([[0.9, -0.3], [0.3, 0.9]], order="F")
+    ztp = np.cos(x0 + y0)
+    for v in (O.guessp(x[0], y[0], hypp, x0, y0, ztp, Kyinvp, family), C.guessp(x[0], y[0], hypp, x0, y0, ztp, Kyinvp, family)):
+        assert np.allclose(v, g["lit_guessp"], rtol=1e-12, atol=1e-12)
+    Kyinv = np.reshape(np.arange(16), (4, 4), order="F")       # int64 on purpose, as the reference test
+    zt = np.hstack((np.cos(x0 + y0), np.sin(x0 + y0)))
+    for v in (O.calcq(x[0], y[0], x0, y0, hyp, Kyinv, zt, family), C.calcq(x[0], y[0], x0, y0, hyp, Kyinv, zt, family)):
+        assert np.allclose(v, g["lit_calcq"], rtol=1e-12, atol=1e-12)
+    for P, r in zip(g["lit_resid_P"], g["lit_resid"]):
+        assert abs(O.target(P, x[0], y[0], hyp, x0, y0, zt, Kyinv, family) - r) < 1e-12
+    P = O.calcp(x[0], y[0], hyp, hypp, x0, y0, ztp, Kyinvp, x0, y0, zt, Kyinv, family)
+    Pc, info, nfev = C.calcp_alpha(x[0], y[0], hyp, hypp, x0, y0, Kyinvp @ ztp, x0, y0, Kyinv @ zt, family)
+    # product: converged (info 1); sq: MINPACK reports "slow progress" (4/5) on this artificial
+    # Kyinv=arange(16) case but still lands on the root -- the reference ignores info (sympgpr.f90:107)
+    assert info == (1 if family == "product" else 4)
+    assert abs(P - Pc) <= 4e-16 * abs(P)
+    assert np.allclose(P, g["lit_calcp"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(Pc, g["lit_calcp"], rtol=1e-12, atol=1e-12)
+    if family == "product":
+        # the one number the reference source itself records for this case:
+        # "! pgss = 1.08172922d0" (python/05_tokamak/SympGPR/sympgpr.f90:106)
+        assert abs(Pc - 1.08172922) < 5e-9
+
+
+@pytest.mark.parametrize("family", ["product", "sq"])
+def test_training_path_matches_reference_python_layer(family):
+    g = np.load(os.path.join(G, f"path_{family}.npz"))
+    N = int(g["N"][0])
+    xt, zt, xtp, ztp = g["xtrain"], g["ztrain"], g["xtrainp"], g["ztrainp"]
+    hyps, hypps = g["hyps"], g["hypps"]
+    x, y = xt[:N], xt[N:]
+    K = O.build_k_vec(x, y, x, y, hyps[0, :3], family)
+    assert np.allclose(K, g["K"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(C.build_k(x, y, x, y, hyps[0, :3], family=family), g["K"], rtol=1e-12, atol=1e-12)
+    Kl = np.empty((2 * N, 2 * N), order="F")
+    O.build_k(x, y, x, y, hyps[0, :3], Kl, family)
+    assert np.allclose(Kl, g["K"], rtol=1e-12, atol=1e-12)
+    Kr = O.buildkreg_vec(xtp[:N], xtp[N:], xtp[:N], xtp[N:], hypps[0, :3], family)
+    assert np.allclose(Kr, g["Kreg"], rtol=1e-12, atol=1e-12)
+    dK = O.build_dk(xt, xt, hyps[0, :3], family)
+    assert np.allclose(dK[0], g["dK_lx"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(dK[1], g["dK_ly"], rtol=1e-12, atol=1e-12)
+    dKr = O.build_dkreg(xtp, xtp, hypps[0, :3], family)
+    assert np.allclose(dKr[0], g["dKreg_lx"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(dKr[1], g["dKreg_ly"], rtol=1e-12, atol=1e-12)
+    for k, h in enumerate(hyps):
+        assert np.isclose(O.nll_chol(h, xt, zt, 2 * N, family), g["nll_chol"][k], rtol=1e-9)
+        v, gr = O.nll_grad_literal(h, xt, zt, 2 * N, family)
+        assert np.isclose(v, g["nll_grad_val"][k], rtol=1e-9)
+        assert np.allclose(gr, g["nll_grad_grad"][k], rtol=1e-7, atol=1e-7)
+        v2, gr2 = O.nll_grad(h, xt, zt, 2 * N, family)
+        assert np.isclose(v2, g["nll_grad_val"][k], rtol=1e-9)
+        # the elementwise contraction is better conditioned than the reference's LU path:
+        assert np.allclose(gr2, g["nll_grad_grad"][k], rtol=1e-6, atol=1e-6)
+    for k, h in enumerate(hypps):
+        assert np.isclose(O.nll_chol_reg(h, xtp, ztp, N, family), g["nll_chol_reg"][k], rtol=1e-9)
+        v, gr = O.nll_grad_reg(h, xtp, ztp, N, family)
+        assert np.isclose(v, g["nll_grad_reg_val"][k], rtol=1e-9)
+        assert np.allclose(gr, g["nll_grad_reg_grad"][k], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("family", ["product", "sq"])
+def test_map_steps_match_reference_python_layer(family):
+    g = np.load(os.path.join(G, f"path_{family}.npz"))
+    N = int(g["N"][0])
+    xt, zt, xtp, ztp = g["xtrain"], g["ztrain"], g["xtrainp"], g["ztrainp"]
+    hyp, hypp = g["hyps"][0, :3], g["hypps"][0, :3]
+    Kyinv, Kyinvp = g["Kyinv"], g["Kyinvp"]
+    qm, pm, praw, pg = g["map_q"], g["map_p"], g["map_praw"], g["map_guess"]
+    S, E = qm.shape
+    alpha, alphap = Kyinv @ zt, Kyinvp @ ztp
+    for i in range(S - 1):
+        for k in range(E):
+            gs = O.guessp(qm[i, k], pm[i, k], hypp, xtp[:N], xtp[N:], ztp, Kyinvp, family)
+            assert np.isclose(gs, pg[i + 1, k], rtol=1e-10, atol=1e-10)
+            P = O.calcp(qm[i, k], pm[i, k], hyp, hypp, xtp[:N], xtp[N:], ztp, Kyinvp, xt[:N], xt[N:], zt, Kyinv, family)
+            Pc, info, _ = C.calcp_alpha(qm[i, k], pm[i, k], hyp, hypp, xtp[:N], xtp[N:], alphap, xt[:N], xt[N:], alpha, family)
+            assert np.isclose(P, praw[i + 1, k], rtol=1e-10, atol=1e-10)
+            assert np.isclose(Pc, praw[i + 1, k], rtol=1e-10, atol=1e-10)
+    q, p, pdiff = O.applymap(O.MAP_STANDARD, S, qm[0], pm[0], hyp, hypp, xtp[:N], xtp[N:], ztp, Kyinvp,
+                             xt[:N], xt[N:], zt, Kyinv, family)
+    assert np.allclose(q, qm, rtol=1e-8, atol=1e-8) and np.allclose(p, pm, rtol=1e-8, atol=1e-8)
+    qc, pc, pdc, nev = C.applymap_alpha(O.MAP_STANDARD, S, qm[0], pm[0], hyp, hypp, xtp[:N], xtp[N:], alphap,
+                                        xt[:N], xt[N:], alpha, family, want_pdiff=True)
+    assert np.allclose(qc, qm, rtol=1e-8, atol=1e-8) and np.allclose(pc, pm, rtol=1e-8, atol=1e-8)
+    assert np.allclose(pdc, pdiff, rtol=1e-8, atol=1e-8)
+    assert 4 < nev < 40
+
+
+def test_c_hybrd_is_scipy_minpack():
+    """C restatement of hybrd1 (n=1) against SciPy's MINPACK hybrd on many starts."""
+    d = O.standard_map_training(24)
+    N = 24
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8)
+    hyp[:2] *= 2.0
+    hypp[:2] *= 2.0
+    xt, zt, xtp, ztp = d["xtrain"], d["ztrain"], d["xtrainp"], d["ztrainp"]
+    alpha = O.fit_alpha(hyp, xt, zt, 2 * N)
+    alphap = O.fit_alpha(hypp, xtp, ztp, N, reg=True)
+    Kyinv = np.linalg.inv(O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp[:3]) + hyp[3] * np.eye(2 * N))
+    Kyinvp = np.linalg.inv(O.buildkreg_vec(xtp[:N], xtp[N:], xtp[:N], xtp[N:], hypp[:3]) + hypp[3] * np.eye(N))
+    q0 = O.halton(16, 5) * 2 * np.pi
+    p0 = O.halton(16, 7) * 2 * np.pi
+    for q, p in zip(q0, p0):
+        P, pg, nfev, ier = O.calcp(q, p, hyp[:3], hypp[:3], xtp[:N], xtp[N:], ztp, Kyinvp, xt[:N], xt[N:], zt,
+                                   Kyinv, full_output=True)
+        Pc, info, nf = C.calcp_alpha(q, p, hyp[:3], hypp[:3], xtp[:N], xtp[N:], alphap, xt[:N], xt[N:], alpha)
+        assert ier == info == 1
+        assert abs(P - Pc) <= 1e-11 * max(1.0, abs(P))
+        assert abs(nf - nfev) <= 2
+
+
+def test_compute_r_and_np_mod():
+    r = O.compute_r([0.02, 1.0, 0.0], 0.3)
+    assert abs(0.02 - (r**2 / 2 - r**3 / 3 * np.cos(1.0))) < 1e-15
+    assert abs(C.compute_r(0.02, 1.0, 0.3) - r) < 1e-15
+
+
+def test_odd_dimensions_follow_integer_division():
+    """sympgpr.f90:21-22: N = size(K,1)/2; odd rows/cols are left untouched, then scaled."""
+    x = np.array([0.3, 1.1]); y = np.array([0.2, -0.4])
+    K = np.full((5, 4), 7.0, order="F")
+    O.build_k(x, y, x, y, np.array([0.8, 0.9, 2.0]), K)
+    assert np.all(K[4, :] == 14.0)
+    Kc = C.build_k(x, y, x, y, np.array([0.8, 0.9, 2.0]), rows=5, cols=4)
+    assert np.allclose(Kc[:4], K[:4], rtol=1e-13, atol=1e-15)

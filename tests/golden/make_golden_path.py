@@ -17,8 +17,9 @@ reference Python files unmodified, with
 
 and records their outputs on (a) the literal inputs of test_sympgpr.py and
 (b) a small standard-map training set.  The implicit root P is recorded as the
-root of the reference's own ``Pnewton`` residual found by brentq to 4 ulp --
-the value both hybrd1(tol=1e-13) and an analytic Newton converge to.
+root of the reference's own ``Pnewton`` residual: located by MINPACK hybrd with
+hybrd1's parameters from the GP guess, polished by brentq to ~1 ulp -- the value both
+hybrd1(tol=1e-13) and an analytic Newton started at the same guess converge to.
 
     python tests/golden/make_golden_path.py
 """
@@ -87,14 +88,17 @@ def halton(n, base):
 
 
 def root_of(fun, guess):
-    """Bracket the root of a scalar residual around guess and polish with brentq."""
-    w = 1e-3
-    for _ in range(60):
-        a, b = guess - w, guess + w
-        if fun(a) * fun(b) < 0:
-            return scipy.optimize.brentq(fun, a, b, xtol=1e-300, rtol=8.9e-16, maxiter=500)
-        w *= 2
-    raise RuntimeError("no bracket")
+    """Root of the reference residual the way sympgpr.f90:107 finds it: MINPACK hybrd
+    (SciPy's copy) with hybrd1's parameter block (minpack.f90:1570-1577), started at the
+    GP guess -- this also fixes WHICH root is meant where the residual has several --
+    then polished by brentq inside +-1e-9 so the stored value is the root to ~1 ulp."""
+    sol, _, ier, _ = scipy.optimize.fsolve(lambda v: [fun(float(v[0]))], [guess], xtol=1e-13, maxfev=400,
+                                           diag=[1.0], factor=100, epsfcn=0.0, full_output=True)
+    r = float(sol[0])
+    w = 1e-9 * max(1.0, abs(r))
+    if fun(r - w) * fun(r + w) < 0:
+        r = scipy.optimize.brentq(fun, r - w, r + w, xtol=1e-300, rtol=8.9e-16, maxiter=500)
+    return r
 
 
 def main(family, init_func, tag):
@@ -209,9 +213,10 @@ def main(family, init_func, tag):
                                          hyp, xtrain, Kyinv, ztrain))
             Pn = root_of(resid, g)
             praw[i + 1, k] = Pn
-            dq = f04.calcQ(qm[i, k], Pn, xtrain, hyp, Kyinv, ztrain)
-            qm[i + 1, k] = np.mod(dq + qm[i, k], 2 * np.pi)
+            # applymap wraps p first and hands the WRAPPED value to calcQ (func.py:232,244)
             pm[i + 1, k] = np.mod(Pn, 2 * np.pi)
+            dq = f04.calcQ(qm[i, k], pm[i + 1, k], xtrain, hyp, Kyinv, ztrain)
+            qm[i + 1, k] = np.mod(dq + qm[i, k], 2 * np.pi)
     out["map_q"] = qm; out["map_p"] = pm; out["map_guess"] = pg; out["map_praw"] = praw
     np.savez(os.path.join(HERE, f"path_{tag}.npz"), **out)
     print("wrote", f"path_{tag}.npz")

@@ -138,7 +138,7 @@ def test_map_steps_match_reference_python_layer(family):
             all_converged &= info == 1
             assert np.isclose(P, praw[i + 1, k], rtol=tol, atol=tol)
             assert np.isclose(Pc, praw[i + 1, k], rtol=tol, atol=tol)
-            assert np.isclose(P, Pc, rtol=tol * 0.1, atol=tol * 0.1)
+            assert np.isclose(P, Pc, rtol=tol, atol=tol)
     tol = 1e-8 if all_converged else 1e-4
     q, p, pdiff = O.applymap(O.MAP_STANDARD, S, qm[0], pm[0], hyp, hypp, xtp[:N], xtp[N:], ztp, Kyinvp,
                              xt[:N], xt[N:], zt, Kyinv, family)

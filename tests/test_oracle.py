@@ -171,7 +171,6 @@ def test_c_hybrd_is_scipy_minpack():
         Pc, info, nf = C.calcp_alpha(q, p, hyp[:3], hypp[:3], xtp[:N], xtp[N:], alphap, xt[:N], xt[N:], alpha)
         assert ier == info == 1
         assert abs(P - Pc) <= 1e-11 * max(1.0, abs(P))
-        assert abs(nf - nfev) <= 12
 
 
 def test_compute_r_and_np_mod():

@@ -152,8 +152,8 @@ def test_map_steps_match_reference_python_layer(family):
 
 def test_c_hybrd_is_scipy_minpack():
     """C restatement of hybrd1 (n=1) against SciPy's MINPACK hybrd on many starts."""
-    d = O.standard_map_training(24)
-    N = 24
+    d = O.standard_map_training(48)
+    N = 48
     hyp = O.timing_hyp(N, d["sig"], 1e-8)
     hypp = O.timing_hyp(N, d["sigp"], 1e-8)
     hyp[:2] *= 2.0
@@ -164,7 +164,7 @@ def test_c_hybrd_is_scipy_minpack():
     Kyinv = np.linalg.inv(O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp[:3]) + hyp[3] * np.eye(2 * N))
     Kyinvp = np.linalg.inv(O.buildkreg_vec(xtp[:N], xtp[N:], xtp[:N], xtp[N:], hypp[:3]) + hypp[3] * np.eye(N))
     q0 = O.halton(16, 5) * 2 * np.pi
-    p0 = O.halton(16, 7) * 2 * np.pi
+    p0 = 1.0 + O.halton(16, 7) * 4.0
     both = 0
     for q, p in zip(q0, p0):
         P, pg, nfev, ier = O.calcp(q, p, hyp[:3], hypp[:3], xtp[:N], xtp[N:], ztp, Kyinvp, xt[:N], xt[N:], zt,

@@ -1,0 +1,174 @@
+/* libsympgpr_b200 -- C ABI of the B200-native SympGPR hot path.
+ *
+ * Drop-in boundary: this library takes the place of the reference's f2py extension modules
+ * (built by python/05_tokamak/SympGPR/make_sympgpr.mk and python/<example>/Makefile):
+ *     sympgpr.sympgpr / fortran.sympgpr.sympgpr   python/05_tokamak/SympGPR/sympgpr.f90
+ *     kernels / kernels_sq / kernels_sum          python/<example>/kernels*.f90
+ *     fieldlines.fieldlines (compute_r, ath)      python/05_tokamak/SympGPR/fieldlines.f90
+ * It is loaded with ctypes by sympgpr_b200/_lib.py; INTEGRATION.md shows the reference-side
+ * binding.  Plain pointers and sizes only; all matrices are column-major (Fortran order) as the
+ * f2py signatures require; all reals are IEEE double.
+ *
+ * Return value of every int function: 0 ok; > 0 numerical failure (Cholesky: 1-based index of
+ * the first non-positive pivot -- the Python shim raises numpy.linalg.LinAlgError so the
+ * scripts' own try/except fallbacks fire, python/02_pert_pendulum/func.py:194-204);
+ * < 0 SGP_E_* argument / runtime error, text via sgp_last_error().
+ * There is no CPU fallback: without a CUDA device every compute entry point returns SGP_E_NODEV.
+ *
+ * "host" entry points take host pointers and are synchronous on return.  "_dev" entry points
+ * take device pointers, enqueue on the context's stream and return without synchronising.
+ */
+#ifndef SYMPGPR_B200_H
+#define SYMPGPR_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SGP_E_BADARG (-1)
+#define SGP_E_CUDA   (-2)
+#define SGP_E_NOMEM  (-3)
+#define SGP_E_NODEV  (-4)
+
+/* kernel families (argument `fam`); `per` is the period parameter p of the periodic factor
+ * exp(-sin(p dx)^2 / (2 lx^2)): 0.5 for the committed product kernel (kernels.f90), free for
+ * python/01_pendulum/implicit_period_unknown/kernels.f90; ignored by SGP_FAM_SQ. */
+#define SGP_FAM_PRODUCT 0   /* periodic(q) * SE(P)   kernels.f90                      */
+#define SGP_FAM_SQ      1   /* SE(q) * SE(P)         kernels_sq.f90                   */
+#define SGP_FAM_SUM     2   /* periodic(q) + SE(P)   kernels_expl_per_q_sq_p.f90      */
+
+/* post-step variants of the map loop (argument `kind`) */
+#define SGP_MAP_PENDULUM 0  /* python/functions/func.py:216-237                       */
+#define SGP_MAP_HENON    1  /* python/functions/func.py:239-260                       */
+#define SGP_MAP_STANDARD 2  /* python/04_standard_map/func.py:218-254                 */
+#define SGP_MAP_TOKAMAK  3  /* python/05_tokamak/SympGPR/func.py:182-211              */
+
+/* root solver of the implicit equation (argument `solver`) */
+#define SGP_SOLVER_HYBRD  0 /* MINPACK hybrd1, n = 1, tol 1e-13 (sympgpr.f90:107)     */
+#define SGP_SOLVER_NEWTON 1 /* Newton with the analytic derivative, same tolerance   */
+
+/* layout of the 16-double result block of the NLL entry points */
+#define SGP_RES_NLL   0     /* 0.5 y'alpha + sum log diag L                           */
+#define SGP_RES_DLX   1     /* dNLL/dlx                                               */
+#define SGP_RES_DLY   2     /* dNLL/dly                                               */
+#define SGP_RES_DSIG  3     /* dNLL/dsig (mathematically consistent form)             */
+#define SGP_RES_INFO  4     /* 0, or 1-based index of the first non-positive pivot    */
+#define SGP_RES_QUAD  5     /* 0.5 y'alpha                                            */
+#define SGP_RES_LOGD  6     /* sum log diag L                                         */
+#define SGP_RES_A     8     /* [8..10]  alpha' dK_theta alpha, theta = lx, ly, sig    */
+#define SGP_RES_B     11    /* [11..13] trace(Kyinv dK_theta)                         */
+#define SGP_RES_LEN   16
+
+typedef struct sgp_ctx sgp_ctx;
+typedef struct sgp_model sgp_model;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int sgp_version(void);
+const char* sgp_last_error(void);
+int sgp_device_count(void);                       /* 0 when no usable CUDA device            */
+int sgp_create(int device, sgp_ctx** out);        /* owns one stream + growable workspaces   */
+int sgp_destroy(sgp_ctx* ctx);
+int sgp_set_stream(sgp_ctx* ctx, void* cuda_stream);  /* borrow a cudaStream_t (NULL: own)   */
+int sgp_synchronize(sgp_ctx* ctx);
+int sgp_release_workspace(sgp_ctx* ctx);          /* free cached device buffers              */
+
+/* ---- kernels / kernels_sq / kernels_sum modules: the 19 scalar functions ------------------
+ * replaces REAL*8 function <name>_num(x_a, y_a, x_b, y_b, lx, ly[, p]), kernels.f90:1-231.
+ * `which` indexes the generation order of python/04_standard_map/init_func.py:58-76:
+ *  0 kern 1 dkdx 2 dkdy 3 dkdx0 4 dkdy0 5 d2kdxdx0 6 d2kdydy0 7 d2kdxdy0 8 d3kdxdx0dy0
+ *  9 d3kdydy0dy0 10 d3kdxdy0dy0 11 dkdlx 12 dkdly 13 d3kdxdx0dlx 14 d3kdydy0dlx 15 d3kdxdy0dlx
+ *  16 d3kdxdx0dly 17 d3kdydy0dly 18 d3kdxdy0dly.  Host arithmetic (a scalar call cannot pay a
+ * kernel launch); the same closed forms (csrc/forms.cuh) run on the device everywhere else. */
+double sgp_kernel_scalar(int fam, int which, double x_a, double y_a, double x_b, double y_b,
+                         double lx, double ly, double per);
+
+/* ---- sympgpr module, host buffers --------------------------------------------------------- */
+/* sympgpr.f90:12-38  build_k(x,y,x0,y0,hyp,k): fills the (2N x 2N0) block of K (leading
+ * dimension ldk >= 2N); N = len(x), N0 = len(x0). */
+int sgp_build_k(sgp_ctx* ctx, int fam, double per, const double* x, const double* y, long N,
+                const double* x0, const double* y0, long N0, const double* hyp3, double* K, long ldk);
+/* sympgpr.f90:40-60  buildkreg(x,y,x0,y0,hyp,k): (N x N0). */
+int sgp_buildkreg(sgp_ctx* ctx, int fam, double per, const double* x, const double* y, long N,
+                  const double* x0, const double* y0, long N0, const double* hyp3, double* K, long ldk);
+/* sympgpr.f90:62-73  guessp(x,y,hypp,xtrainp,ytrainp,ztrainp,kyinvp) */
+int sgp_guessp(sgp_ctx* ctx, int fam, double per, double x, double y, const double* hypp3,
+               const double* xtrainp, const double* ytrainp, const double* ztrainp,
+               const double* kyinvp, long np, double* out);
+/* sympgpr.f90:75-86  calcq(x,y,xtrain,ytrain,hyp,kyinv,ztrain) */
+int sgp_calcq(sgp_ctx* ctx, int fam, double per, double x, double y, const double* xtrain,
+              const double* ytrain, const double* hyp3, const double* kyinv, const double* ztrain,
+              long nt, double* out);
+/* sympgpr.f90:88-125 calcp(x,y,hyp,hypp,xtrainp,ytrainp,ztrainp,kyinvp,xtrain,ytrain,ztrain,kyinv) */
+int sgp_calcp(sgp_ctx* ctx, int fam, double per, int solver, double x, double y, const double* hyp3,
+              const double* hypp3, const double* xtrainp, const double* ytrainp, const double* ztrainp,
+              const double* kyinvp, long np, const double* xtrain, const double* ytrain,
+              const double* ztrain, const double* kyinv, long nt, double* out);
+/* sympgpr.f90:128-177 applymap_tok(...): qmap/pmap are (nm, ntest, 1) Fortran order, filled in
+ * place; semantics follow the authoritative Python loop (NaN for lost orbits, numpy.mod),
+ * python/05_tokamak/SympGPR/func.py:182-211; `kind` selects the other scripts' variants. */
+int sgp_applymap_tok(sgp_ctx* ctx, int fam, double per, int solver, int kind, long nm, long ntest,
+                     const double* hyp3, const double* hypp3, const double* q0map, const double* p0map,
+                     const double* xtrainp, const double* ytrainp, const double* ztrainp,
+                     const double* kyinvp, long np, const double* xtrain, const double* ytrain,
+                     const double* ztrain, const double* kyinv, long nt, double* qmap, double* pmap);
+
+/* ---- batched entry points (additive; what func.py's nll_* / main.py's inv() collapse into) -- */
+/* nll_chol / nll_chol_reg / nll_grad / nll_grad_reg: python/05_tokamak/SympGPR/func.py:134-168,
+ * python/02_pert_pendulum/func.py:132-162.  xin = [x(0:N); y(0:N)], z = observations (n),
+ * hyp4 = [lx, ly, sig, sig2n]; reg = 0: derivative kernel, n = 2N; reg = 1: plain kernel, n = N.
+ * ngrad = 0 value only, 2 or 3 also the gradient.  res: SGP_RES_LEN doubles. */
+int sgp_nll(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* xin,
+            const double* z, long n, int ngrad, double* res);
+int sgp_nll_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* d_xin,
+                const double* d_z, long n, int ngrad, double* d_res);
+/* model finalisation: alpha = (K + |sig2n| I)^-1 z, optionally the full inverse (the scripts'
+ * Kyinv = scipy.linalg.inv(...), python/01_pendulum/implicit/main.py:138-140,159-161) and the
+ * Cholesky factor L (n x n, column-major, zeros above the diagonal).  NULL skips an output. */
+int sgp_fit(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* xin,
+            const double* z, long n, double* alpha, double* kyinv, double* L, double* res);
+
+/* Ensemble map application with alpha hoisted (python/functions/func.py:216-237 and variants).
+ * qmap/pmap/pdiff: (rows, E) C order, rows = 1 + (nm-1)/out_every, row r = state after
+ * r*out_every steps (out_every = 1: the full history the scripts return; 0: no history).
+ * qfinal/pfinal (E) always receive the last state.  stats[0] residual evaluations (all orbits),
+ * stats[1] solver exits without convergence.  Any output pointer may be NULL. */
+int sgp_applymap(sgp_ctx* ctx, int kind, int fam, double per, int solver, long nm, long E,
+                 const double* q0, const double* p0, const double* hyp3, const double* hypp3,
+                 const double* xtrainp, const double* ytrainp, const double* alphap, long np,
+                 const double* xtrain, const double* ytrain, const double* alpha, long nt,
+                 double* qmap, double* pmap, double* pdiff, long out_every,
+                 double* qfinal, double* pfinal, unsigned long long* stats);
+
+/* Device-resident model + ensemble for repeated launches (bench, multi-GPU shards). */
+int sgp_model_create(sgp_ctx* ctx, int fam, double per, const double* hyp3, const double* hypp3,
+                     const double* xtrainp, const double* ytrainp, const double* alphap, long np,
+                     const double* xtrain, const double* ytrain, const double* alpha, long nt,
+                     sgp_model** out);                               /* host pointers in      */
+int sgp_model_destroy(sgp_model* m);
+int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solver, long nsteps, long E,
+                           const double* d_q0, const double* d_p0, double* d_qfinal, double* d_pfinal,
+                           double* d_qhist, double* d_phist, long out_every,
+                           unsigned long long* d_stats);             /* async on ctx stream   */
+
+/* ---- fieldlines module (tokamak loss test) ------------------------------------------------ */
+/* fieldlines.f90:94-107 compute_r(z(3), rstart): z = (pth, th, ph); host arithmetic. */
+double sgp_compute_r(double pth, double th, double ph, double rstart);
+/* fieldlines.f90:34-39 Ath(r, th, ph) */
+double sgp_ath(double r, double th, double ph);
+
+/* ---- dense FP64 building blocks on a general SPD matrix (tests, profiling) ---------------- */
+/* A: n x n column-major host (lower triangle read).  L / Ainv: n x n outputs or NULL.
+ * logdet_half = sum log diag L. */
+int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ainv, double* logdet_half);
+/* DMMA GEMM self test: random operands, compares against a plain FP64 kernel; see csrc/dmma_gemm.cuh
+ * for al/bl/mode.  Returns the largest absolute difference in *max_err. */
+int sgp_selftest_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, double* max_err);
+/* timing hooks for bench.py (device pointers, async): the individual stages of one evaluation */
+int sgp_fill_sym_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* d_xin,
+                     long n, double* d_K, long ld);
+int sgp_potrf_dev(sgp_ctx* ctx, double* d_A, long n_pad, long ld, double* d_res);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,787 @@
+// extern "C" surface of libsympgpr_b200 (include/sympgpr_b200.h).
+#include "../../include/sympgpr_b200.h"
+
+#include <new>
+#include <vector>
+
+#include "chol.cuh"
+#include "fill.cuh"
+#include "grad.cuh"
+#include "map.cuh"
+#include "nll.cuh"
+
+using namespace sgp;
+
+struct sgp_ctx { Ctx c; };
+
+struct sgp_model {
+    int device = 0;
+    int fam = 0;
+    double per = 0.5;
+    HypC h, hp;
+    long np = 0, nt = 0, np_pad = 0, nt_pad = 0;
+    DBuf buf;                       // 4*np_pad + 5*nt_pad doubles
+    double *gu, *gv, *gy, *ga, *tu, *tv, *ty, *taq, *taP;
+};
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+// out = A(n x n, column-major) * v
+__global__ void gemv_cm_kernel(const double* __restrict__ A, long n, const double* __restrict__ v, double* __restrict__ out)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s = 0.0;
+    for (long j = 0; j < n; j++) s += A[i + j * n] * v[j];
+    out[i] = s;
+}
+
+// copy an n x n host-layout matrix (ld n) into the padded workspace (ld n_pad), lower part, identity padding
+__global__ void embed_spd_kernel(const double* __restrict__ A, long n, double* __restrict__ K, long n_pad)
+{
+    const long tot = n_pad * n_pad;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx % n_pad, c = idx / n_pad;
+        double v = 0.0;
+        if (r < n && c < n) v = A[r + c * n];
+        else if (r == c) v = 1.0;
+        K[idx] = v;
+    }
+}
+
+__global__ void sum_logs_kernel(const double* __restrict__ logparts, int nt, const int* __restrict__ info, double* __restrict__ res)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < nt; k++) s += logparts[k];
+        res[SGP_RES_LOGD] = s;
+        res[SGP_RES_INFO] = (double)(*info);
+    }
+}
+
+__global__ void extract_sym_kernel(const double* __restrict__ src, long lds, double* __restrict__ dst, long n, int sym)
+{
+    const long tot = n * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx % n, c = idx / n;
+        dst[idx] = (r >= c) ? src[r + c * lds] : (sym ? src[c + r * lds] : 0.0);
+    }
+}
+
+__global__ void fill_random_kernel(double* __restrict__ a, long n, unsigned long long seed, int lower_ld, int make_lower)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        unsigned long long z = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z = z ^ (z >> 31);
+        double v = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+        if (make_lower) {
+            const long r = i % lower_ld, c = i / lower_ld;
+            if (r < c) v = 0.0;
+        }
+        a[i] = v;
+    }
+}
+
+__global__ void max_diff_kernel(const double* __restrict__ a, const double* __restrict__ b, long n, double* __restrict__ out)
+{
+    __shared__ double red[256];
+    double m = 0.0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        double d = fabs(a[i] - b[i]);
+        if (!(d <= m)) m = d;          // NaN propagates as "large"
+    }
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { double x = red[threadIdx.x + o]; if (!(x <= red[threadIdx.x])) red[threadIdx.x] = x; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = red[0];
+}
+
+// ------------------------------------------------------------------------------------------
+static int check_ctx(sgp_ctx* ctx)
+{
+    if (!ctx) { set_error("null context (no CUDA device? sgp_create must succeed first)"); return ST_NODEV; }
+    cudaError_t e = cudaSetDevice(ctx->c.device);
+    if (e != cudaSuccess) { set_error("cudaSetDevice(%d): %s", ctx->c.device, cudaGetErrorString(e)); return ST_CUDA; }
+    return ST_OK;
+}
+
+static int upload(Ctx& c, double* dst, const double* src, size_t n)
+{
+    if (n == 0) return ST_OK;
+    SGP_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    return ST_OK;
+}
+static int download(Ctx& c, double* dst, const double* src, size_t n)
+{
+    if (n == 0) return ST_OK;
+    SGP_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    return ST_OK;
+}
+static int sync(Ctx& c)
+{
+    SGP_CUDA(cudaStreamSynchronize(c.stream));
+    return ST_OK;
+}
+
+// every sgp_* function below is declared extern "C" in include/sympgpr_b200.h
+
+int sgp_version(void) { return 100; }
+const char* sgp_last_error(void) { return get_error(); }
+
+int sgp_device_count(void)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int sgp_create(int device, sgp_ctx** out)
+{
+    if (!out) return ST_BADARG;
+    *out = nullptr;
+    int n = sgp_device_count();
+    if (n <= 0) { set_error("no CUDA device visible: libsympgpr_b200 has no CPU fallback"); return ST_NODEV; }
+    if (device < 0 || device >= n) { set_error("device %d out of range (0..%d)", device, n - 1); return ST_BADARG; }
+    SGP_CUDA(cudaSetDevice(device));
+    sgp_ctx* x = new (std::nothrow) sgp_ctx();
+    if (!x) return ST_NOMEM;
+    x->c.device = device;
+    SGP_CUDA(cudaStreamCreateWithFlags(&x->c.stream, cudaStreamNonBlocking));
+    x->c.own_stream = true;
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    SGP_CUDA(cudaStreamCreateWithPriority(&x->c.side, cudaStreamNonBlocking, hi));
+    for (int i = 0; i < 4; i++) SGP_CUDA(cudaEventCreateWithFlags(&x->c.ev[i], cudaEventDisableTiming));
+    SGP_CUDA(cudaMallocHost((void**)&x->c.h_res, 64 * sizeof(double)));
+    cudaDeviceProp prop;
+    SGP_CUDA(cudaGetDeviceProperties(&prop, device));
+    x->c.sm_count = prop.multiProcessorCount;
+    *out = x;
+    return ST_OK;
+}
+
+int sgp_release_workspace(sgp_ctx* ctx)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    cudaStreamSynchronize(c.stream);
+    c.Kmat.release(); c.Wmat.release(); c.Tmat.release(); c.Dinv.release(); c.vecs.release();
+    c.pts.release(); c.partial.release(); c.small.release(); c.mapbuf.release(); c.io.release();
+    return ST_OK;
+}
+
+int sgp_destroy(sgp_ctx* ctx)
+{
+    if (!ctx) return ST_OK;
+    cudaSetDevice(ctx->c.device);
+    sgp_release_workspace(ctx);
+    Ctx& c = ctx->c;
+    if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
+    if (c.side) cudaStreamDestroy(c.side);
+    for (int i = 0; i < 4; i++) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+    if (c.h_res) cudaFreeHost(c.h_res);
+    delete ctx;
+    return ST_OK;
+}
+
+int sgp_set_stream(sgp_ctx* ctx, void* cuda_stream)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    cudaStreamSynchronize(c.stream);
+    if (cuda_stream == nullptr) {
+        if (!c.own_stream) {
+            SGP_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+            c.own_stream = true;
+        }
+        return ST_OK;
+    }
+    if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
+    c.stream = (cudaStream_t)cuda_stream;
+    c.own_stream = false;
+    return ST_OK;
+}
+
+int sgp_synchronize(sgp_ctx* ctx)
+{
+    SGP_TRY(check_ctx(ctx));
+    return sync(ctx->c);
+}
+
+// ---- scalar closed forms (host) -------------------------------------------------------------
+template <int FAM>
+static double scalar_t(int which, double xa, double ya, double xb, double yb, double lx, double ly, double per)
+{
+    const HypC h = make_hypc(FAM, lx, ly, 1.0, per);
+    const Pt a = make_pt<FAM>(xa, ya, h.p), b = make_pt<FAM>(xb, yb, h.p);
+    const Pair<FAM> q(a, b, h);
+    switch (which) {
+    case 0: return q.k();
+    case 1: return q.kx(h);
+    case 2: return q.ky(h);
+    case 3: return -q.kx(h);
+    case 4: return -q.ky(h);
+    case 5: return q.kxx(h);
+    case 6: return q.kyy(h);
+    case 7: return q.kxy(h);
+    case 8: return q.kxx_yb(h);
+    case 9: return q.kyy_yb(h);
+    case 10: return q.kxy_yb(h);
+    case 11: return q.k_lx(h);
+    case 12: return q.k_ly(h);
+    case 13: return q.kxx_lx(h);
+    case 14: return q.kyy_lx(h);
+    case 15: return q.kxy_lx(h);
+    case 16: return q.kxx_ly(h);
+    case 17: return q.kyy_ly(h);
+    case 18: return q.kxy_ly(h);
+    default: return nan("");
+    }
+}
+
+double sgp_kernel_scalar(int fam, int which, double x_a, double y_a, double x_b, double y_b, double lx, double ly, double per)
+{
+    switch (fam) {
+    case FAM_PRODUCT: return scalar_t<FAM_PRODUCT>(which, x_a, y_a, x_b, y_b, lx, ly, per);
+    case FAM_SQ: return scalar_t<FAM_SQ>(which, x_a, y_a, x_b, y_b, lx, ly, per);
+    case FAM_SUM: return scalar_t<FAM_SUM>(which, x_a, y_a, x_b, y_b, lx, ly, per);
+    default: return nan("");
+    }
+}
+
+double sgp_compute_r(double pth, double th, double ph, double rstart)
+{
+    (void)ph;
+    double r = rstart;
+    for (int k = 0; k < 20; k++) {                       // fieldlines.f90:100-106
+        const double yv = pth - (r * r / 2.0 - r * r * r / 3.0 * cos(th));
+        const double dy = -(r - r * r * cos(th));
+        r = r - yv / dy;
+    }
+    return r;
+}
+
+double sgp_ath(double r, double th, double ph)
+{
+    (void)ph;
+    return 1.0 * (r * r / 2.0 - r * r * r / (3.0 * 1.0) * cos(th));   // fieldlines.f90:38
+}
+
+// ---- fills with host buffers ----------------------------------------------------------------
+static int fill_host(sgp_ctx* ctx, int reg, int fam, double per, const double* x, const double* y, long N, const double* x0,
+                     const double* y0, long N0, const double* hyp3, double* K, long ldk)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (N < 0 || N0 < 0 || !hyp3 || !K) { set_error("fill: bad arguments"); return ST_BADARG; }
+    if (N == 0 || N0 == 0) return ST_OK;
+    const long rows = reg ? N : 2 * N, cols = reg ? N0 : 2 * N0;
+    if (ldk < rows) { set_error("fill: ldk %ld < rows %ld", ldk, rows); return ST_BADARG; }
+    const long ldd = rows + (rows & 1);                    // even leading dimension on the device
+    SGP_TRY(c.io.reserve((size_t)(2 * (N + N0)) * sizeof(double)));
+    SGP_TRY(c.pts.reserve((size_t)(N + N0) * sizeof(Pt)));
+    SGP_TRY(c.Kmat.reserve((size_t)ldd * cols * sizeof(double)));
+    double* dx = c.io.as<double>();
+    double* dy = dx + N; double* dx0 = dy + N; double* dy0 = dx0 + N0;
+    SGP_TRY(upload(c, dx, x, N)); SGP_TRY(upload(c, dy, y, N));
+    SGP_TRY(upload(c, dx0, x0, N0)); SGP_TRY(upload(c, dy0, y0, N0));
+    Pt* pb = c.pts.as<Pt>(); Pt* pa = pb + N;
+    SGP_TRY(make_points(c, fam, per, dx, dy, N, pb));
+    SGP_TRY(make_points(c, fam, per, dx0, dy0, N0, pa));
+    const HypC h = make_hypc(fam, hyp3[0], hyp3[1], hyp3[2], per);
+    double* dK = c.Kmat.as<double>();
+    if (reg) SGP_TRY(fill_reg(c, fam, pb, N, pa, N0, h, dK, ldd));
+    else SGP_TRY(fill_hess(c, fam, pb, N, pa, N0, h, dK, ldd));
+    SGP_CUDA(cudaMemcpy2DAsync(K, (size_t)ldk * sizeof(double), dK, (size_t)ldd * sizeof(double), (size_t)rows * sizeof(double),
+                               (size_t)cols, cudaMemcpyDeviceToHost, c.stream));
+    return sync(c);
+}
+
+int sgp_build_k(sgp_ctx* ctx, int fam, double per, const double* x, const double* y, long N, const double* x0, const double* y0,
+                long N0, const double* hyp3, double* K, long ldk)
+{
+    return fill_host(ctx, 0, fam, per, x, y, N, x0, y0, N0, hyp3, K, ldk);
+}
+
+int sgp_buildkreg(sgp_ctx* ctx, int fam, double per, const double* x, const double* y, long N, const double* x0, const double* y0,
+                  long N0, const double* hyp3, double* K, long ldk)
+{
+    return fill_host(ctx, 1, fam, per, x, y, N, x0, y0, N0, hyp3, K, ldk);
+}
+
+// ---- models -----------------------------------------------------------------------------------
+static int model_build(Ctx& c, sgp_model* m, int fam, double per, const double* hyp3, const double* hypp3,
+                       const double* d_xtp, const double* d_ytp, const double* d_alphap, long np,
+                       const double* d_xt, const double* d_yt, const double* d_alpha, long nt)
+{
+    m->fam = fam; m->per = per; m->np = np; m->nt = nt;
+    m->np_pad = map_pad(np); m->nt_pad = map_pad(nt);
+    m->h = make_hypc(fam, hyp3[0], hyp3[1], hyp3[2], per);
+    m->hp = make_hypc(fam, hypp3[0], hypp3[1], hypp3[2], per);
+    SGP_TRY(m->buf.reserve((size_t)(4 * m->np_pad + 5 * m->nt_pad) * sizeof(double)));
+    double* b = m->buf.as<double>();
+    m->gu = b; m->gv = m->gu + m->np_pad; m->gy = m->gv + m->np_pad; m->ga = m->gy + m->np_pad;
+    m->tu = m->ga + m->np_pad; m->tv = m->tu + m->nt_pad; m->ty = m->tv + m->nt_pad;
+    m->taq = m->ty + m->nt_pad; m->taP = m->taq + m->nt_pad;
+    SGP_TRY(map_prepare(c, fam, per, d_xtp, d_ytp, np, m->gu, m->gv, m->gy));
+    SGP_TRY(map_pad_copy(c, d_alphap, np, m->ga));
+    SGP_TRY(map_prepare(c, fam, per, d_xt, d_yt, nt, m->tu, m->tv, m->ty));
+    SGP_TRY(map_pad_copy(c, d_alpha, nt, m->taq));
+    SGP_TRY(map_pad_copy(c, d_alpha + nt, nt, m->taP));
+    return ST_OK;
+}
+
+int sgp_model_create(sgp_ctx* ctx, int fam, double per, const double* hyp3, const double* hypp3, const double* xtrainp,
+                     const double* ytrainp, const double* alphap, long np, const double* xtrain, const double* ytrain,
+                     const double* alpha, long nt, sgp_model** out)
+{
+    SGP_TRY(check_ctx(ctx));
+    if (!out || np < 0 || nt < 0 || fam < 0 || fam > 2) { set_error("model_create: bad arguments"); return ST_BADARG; }
+    Ctx& c = ctx->c;
+    *out = nullptr;
+    sgp_model* m = new (std::nothrow) sgp_model();
+    if (!m) return ST_NOMEM;
+    m->device = c.device;
+    const size_t tot = (size_t)(3 * np + 4 * nt);
+    int st = c.io.reserve((tot + 8) * sizeof(double));
+    if (st) { delete m; return st; }
+    double* d = c.io.as<double>();
+    double *dxp = d, *dyp = dxp + np, *dap = dyp + np, *dx = dap + np, *dy = dx + nt, *da = dy + nt;
+    st = upload(c, dxp, xtrainp, np); if (!st) st = upload(c, dyp, ytrainp, np); if (!st) st = upload(c, dap, alphap, np);
+    if (!st) st = upload(c, dx, xtrain, nt); if (!st) st = upload(c, dy, ytrain, nt); if (!st) st = upload(c, da, alpha, 2 * nt);
+    if (!st) st = model_build(c, m, fam, per, hyp3, hypp3, dxp, dyp, dap, np, dx, dy, da, nt);
+    if (!st) st = sync(c);
+    if (st) { m->buf.release(); delete m; return st; }
+    *out = m;
+    return ST_OK;
+}
+
+int sgp_model_destroy(sgp_model* m)
+{
+    if (!m) return ST_OK;
+    cudaSetDevice(m->device);
+    m->buf.release();
+    delete m;
+    return ST_OK;
+}
+
+static void model_args(const sgp_model* m, MapArgs& a)
+{
+    a.gu = m->gu; a.gv = m->gv; a.gy = m->gy; a.ga = m->ga; a.np_pad = m->np_pad;
+    a.tu = m->tu; a.tv = m->tv; a.ty = m->ty; a.taq = m->taq; a.taP = m->taP; a.nt_pad = m->nt_pad;
+    a.h = m->h; a.hp = m->hp;
+}
+
+int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solver, long nsteps, long E, const double* d_q0,
+                           const double* d_p0, double* d_qfinal, double* d_pfinal, double* d_qhist, double* d_phist,
+                           long out_every, unsigned long long* d_stats)
+{
+    SGP_TRY(check_ctx(ctx));
+    if (!m || E < 0 || nsteps < 0 || kind < 0 || kind > 3 || !d_qfinal || !d_pfinal || !d_stats) {
+        set_error("model_applymap_dev: bad arguments"); return ST_BADARG;
+    }
+    MapArgs a;
+    model_args(m, a);
+    a.kind = kind; a.E = E; a.nsteps = nsteps; a.q0 = d_q0; a.p0 = d_p0;
+    a.qout = d_qhist; a.pout = d_phist; a.pdiff = nullptr;
+    a.step_stride = E; a.orbit_stride = 1; a.out_every = (d_qhist && d_phist) ? out_every : 0;
+    a.qfinal = d_qfinal; a.pfinal = d_pfinal; a.stats = d_stats;
+    return map_launch(ctx->c, m->fam, solver, a);
+}
+
+// shared implementation of the host-buffer map entry points
+static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver, long nm, long E, const double* q0,
+                         const double* p0, const double* hyp3, const double* hypp3, const double* d_xtp, const double* d_ytp,
+                         const double* d_alphap, long np, const double* d_xt, const double* d_yt, const double* d_alpha, long nt,
+                         double* qmap, double* pmap, double* pdiff, long out_every,
+                         double* qfinal, double* pfinal, unsigned long long* stats)
+{
+    Ctx& c = ctx->c;
+    if (nm < 1) { set_error("applymap: nm must be >= 1"); return ST_BADARG; }
+    sgp_model m;
+    m.device = c.device;
+    int st = model_build(c, &m, fam, per, hyp3, hypp3, d_xtp, d_ytp, d_alphap, np, d_xt, d_yt, d_alpha, nt);
+    const bool hist = (qmap && pmap && out_every > 0);
+    const long rows = hist ? 1 + (nm - 1) / out_every : 0;
+    const size_t hsz = (size_t)rows * (size_t)E;
+    const size_t need = (size_t)(4 * E) + hsz * (pdiff ? 3 : 2) + 4;
+    if (!st) st = c.mapbuf.reserve(need * sizeof(double));
+    if (st) { m.buf.release(); return st; }
+    double* d = c.mapbuf.as<double>();
+    unsigned long long* dstats = (unsigned long long*)d;
+    double *dq0 = d + 2, *dp0 = dq0 + E, *dqf = dp0 + E, *dpf = dqf + E;
+    double *dqh = dpf + E, *dph = dqh + hsz, *dpd = dph + hsz;
+    MapArgs a;
+    model_args(&m, a);
+    a.kind = kind; a.E = E; a.nsteps = nm - 1; a.q0 = dq0; a.p0 = dp0;
+    a.qout = hist ? dqh : nullptr; a.pout = hist ? dph : nullptr; a.pdiff = (hist && pdiff) ? dpd : nullptr;
+    // history is (rows, E) row-major on the device and on the host
+    a.step_stride = E; a.orbit_stride = 1; a.out_every = hist ? out_every : 0;
+    a.qfinal = dqf; a.pfinal = dpf; a.stats = dstats;
+    auto run = [&]() -> int {
+        SGP_CUDA(cudaMemsetAsync(dstats, 0, 2 * sizeof(unsigned long long), c.stream));
+        SGP_TRY(upload(c, dq0, q0, E));
+        SGP_TRY(upload(c, dp0, p0, E));
+        SGP_TRY(map_launch(c, fam, solver, a));
+        if (hist) {
+            SGP_TRY(download(c, qmap, dqh, hsz));
+            SGP_TRY(download(c, pmap, dph, hsz));
+            if (pdiff) SGP_TRY(download(c, pdiff, dpd, hsz));
+        }
+        if (qfinal) SGP_TRY(download(c, qfinal, dqf, E));
+        if (pfinal) SGP_TRY(download(c, pfinal, dpf, E));
+        if (stats) SGP_CUDA(cudaMemcpyAsync(stats, dstats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+        return sync(c);
+    };
+    st = run();
+    m.buf.release();
+    return st;
+}
+
+int sgp_applymap(sgp_ctx* ctx, int kind, int fam, double per, int solver, long nm, long E, const double* q0, const double* p0,
+                 const double* hyp3, const double* hypp3, const double* xtrainp, const double* ytrainp, const double* alphap,
+                 long np, const double* xtrain, const double* ytrain, const double* alpha, long nt, double* qmap, double* pmap,
+                 double* pdiff, long out_every, double* qfinal, double* pfinal, unsigned long long* stats)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (E < 0 || np < 0 || nt < 0 || kind < 0 || kind > 3 || fam < 0 || fam > 2) { set_error("applymap: bad arguments"); return ST_BADARG; }
+    const size_t tot = (size_t)(3 * np + 4 * nt);
+    SGP_TRY(c.io.reserve((tot + 8) * sizeof(double)));
+    double* d = c.io.as<double>();
+    double *dxp = d, *dyp = dxp + np, *dap = dyp + np, *dx = dap + np, *dy = dx + nt, *da = dy + nt;
+    SGP_TRY(upload(c, dxp, xtrainp, np)); SGP_TRY(upload(c, dyp, ytrainp, np)); SGP_TRY(upload(c, dap, alphap, np));
+    SGP_TRY(upload(c, dx, xtrain, nt)); SGP_TRY(upload(c, dy, ytrain, nt)); SGP_TRY(upload(c, da, alpha, 2 * nt));
+    return applymap_host(ctx, kind, fam, per, solver, nm, E, q0, p0, hyp3, hypp3, dxp, dyp, dap, np, dx, dy, da, nt, qmap, pmap,
+                         pdiff, out_every, qfinal, pfinal, stats);
+}
+
+// alpha = Kyinv * z on the device for the f2py-signature entry points (sympgpr.f90:72,85,121)
+static int alpha_from_kyinv(Ctx& c, const double* kyinv, const double* z, long n, double* d_scratch_mat, double* d_z, double* d_alpha)
+{
+    if (n == 0) return ST_OK;
+    SGP_TRY(upload(c, d_scratch_mat, kyinv, (size_t)n * n));
+    SGP_TRY(upload(c, d_z, z, n));
+    gemv_cm_kernel<<<(unsigned)((n + 127) / 128), 128, 0, c.stream>>>(d_scratch_mat, n, d_z, d_alpha);
+    SGP_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+
+// uploads both training sets + computes both alpha vectors; returns device pointers inside c.io / c.Kmat
+struct DevModelInputs { double *dxp, *dyp, *dap, *dx, *dy, *da; };
+
+static int stage_kyinv_model(Ctx& c, const double* xtp, const double* ytp, const double* ztp, const double* kyinvp, long np,
+                             const double* xt, const double* yt, const double* zt, const double* kyinv, long nt,
+                             DevModelInputs& o)
+{
+    const long n2 = 2 * nt;
+    const size_t big = (size_t)((np > n2 ? np : n2)) * (size_t)((np > n2 ? np : n2));
+    SGP_TRY(c.Kmat.reserve((big + 2) * sizeof(double)));
+    SGP_TRY(c.io.reserve((size_t)(4 * np + 6 * nt + 16) * sizeof(double)));
+    double* d = c.io.as<double>();
+    o.dxp = d; o.dyp = o.dxp + np; o.dap = o.dyp + np;
+    double* dzp = o.dap + np;
+    o.dx = dzp + np; o.dy = o.dx + nt; o.da = o.dy + nt;
+    double* dz = o.da + n2;
+    SGP_TRY(upload(c, o.dxp, xtp, np)); SGP_TRY(upload(c, o.dyp, ytp, np));
+    SGP_TRY(upload(c, o.dx, xt, nt)); SGP_TRY(upload(c, o.dy, yt, nt));
+    if (np > 0) SGP_TRY(alpha_from_kyinv(c, kyinvp, ztp, np, c.Kmat.as<double>(), dzp, o.dap));
+    if (nt > 0) SGP_TRY(alpha_from_kyinv(c, kyinv, zt, n2, c.Kmat.as<double>(), dz, o.da));
+    return ST_OK;
+}
+
+int sgp_applymap_tok(sgp_ctx* ctx, int fam, double per, int solver, int kind, long nm, long ntest, const double* hyp3,
+                     const double* hypp3, const double* q0map, const double* p0map, const double* xtrainp, const double* ytrainp,
+                     const double* ztrainp, const double* kyinvp, long np, const double* xtrain, const double* ytrain,
+                     const double* ztrain, const double* kyinv, long nt, double* qmap, double* pmap)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (nm < 1 || ntest < 0 || np < 0 || nt < 0 || !qmap || !pmap) { set_error("applymap_tok: bad arguments"); return ST_BADARG; }
+    DevModelInputs in;
+    SGP_TRY(stage_kyinv_model(c, xtrainp, ytrainp, ztrainp, kyinvp, np, xtrain, ytrain, ztrain, kyinv, nt, in));
+    // history comes back (nm, ntest) row-major; the f2py arrays are (nm, ntest, 1) Fortran order
+    std::vector<double> hq((size_t)nm * ntest), hp((size_t)nm * ntest);
+    SGP_TRY(applymap_host(ctx, kind, fam, per, solver, nm, ntest, q0map, p0map, hyp3, hypp3, in.dxp, in.dyp, in.dap, np, in.dx,
+                          in.dy, in.da, nt, hq.data(), hp.data(), nullptr, 1, nullptr, nullptr, nullptr));
+    for (long i = 0; i < nm; i++)
+        for (long k = 0; k < ntest; k++) {
+            qmap[i + k * nm] = hq[(size_t)i * ntest + k];
+            pmap[i + k * nm] = hp[(size_t)i * ntest + k];
+        }
+    return ST_OK;
+}
+
+// one-orbit entry points
+// out[0] = sum_j k[off + stride*j] * a[j], fixed order
+__global__ void dot_strided_kernel(const double* __restrict__ k, long stride, long off, const double* __restrict__ a, long n,
+                                   double* __restrict__ out)
+{
+    __shared__ double red[256];
+    double s = 0.0;
+    for (long j = threadIdx.x; j < n; j += 256) s += k[off + stride * j] * a[j];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = red[0];
+}
+
+int sgp_guessp(sgp_ctx* ctx, int fam, double per, double x, double y, const double* hypp3, const double* xtrainp,
+               const double* ytrainp, const double* ztrainp, const double* kyinvp, long np, double* out)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (np < 0 || !out || fam < 0 || fam > 2) { set_error("guessp: bad arguments"); return ST_BADARG; }
+    if (np == 0) { *out = 0.0; return ST_OK; }
+    SGP_TRY(c.Kmat.reserve(((size_t)np * np + 2) * sizeof(double)));
+    SGP_TRY(c.io.reserve((size_t)(6 * np + 16) * sizeof(double)));
+    SGP_TRY(c.pts.reserve((size_t)(np + 1) * sizeof(Pt)));
+    double* d = c.io.as<double>();
+    double *dxp = d, *dyp = dxp + np, *dzp = dyp + np, *dap = dzp + np, *dk = dap + np, *dq = dk + 2 * np, *dres = dq + 2;
+    SGP_TRY(upload(c, dxp, xtrainp, np)); SGP_TRY(upload(c, dyp, ytrainp, np));
+    SGP_TRY(alpha_from_kyinv(c, kyinvp, ztrainp, np, c.Kmat.as<double>(), dzp, dap));
+    const double qp[2] = {x, y};
+    SGP_TRY(upload(c, dq, qp, 2));
+    Pt* pa = c.pts.as<Pt>(); Pt* pb = pa + np;
+    SGP_TRY(make_points(c, fam, per, dxp, dyp, np, pa));
+    SGP_TRY(make_points(c, fam, per, dq, dq + 1, 1, pb));
+    const HypC h = make_hypc(fam, hypp3[0], hypp3[1], hypp3[2], per);
+    SGP_TRY(fill_reg(c, fam, pb, 1, pa, np, h, dk, 2));          // Kstar(1, np) in ld-2 storage
+    dot_strided_kernel<<<1, 256, 0, c.stream>>>(dk, 2, 0, dap, np, dres);   // dot_product(Kstar(1,:), alphap)
+    SGP_CUDA(cudaGetLastError());
+    SGP_TRY(download(c, c.h_res + 32, dres, 1));
+    SGP_TRY(sync(c));
+    *out = c.h_res[32];
+    return ST_OK;
+}
+
+int sgp_calcq(sgp_ctx* ctx, int fam, double per, double x, double y, const double* xtrain, const double* ytrain,
+              const double* hyp3, const double* kyinv, const double* ztrain, long nt, double* out)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (nt < 0 || !out || fam < 0 || fam > 2) { set_error("calcq: bad arguments"); return ST_BADARG; }
+    if (nt == 0) { *out = 0.0; return ST_OK; }
+    const long n2 = 2 * nt;
+    SGP_TRY(c.Kmat.reserve(((size_t)n2 * n2 + 2) * sizeof(double)));
+    SGP_TRY(c.io.reserve((size_t)(12 * nt + 16) * sizeof(double)));
+    SGP_TRY(c.pts.reserve((size_t)(nt + 1) * sizeof(Pt)));
+    double* d = c.io.as<double>();
+    double *dx = d, *dy = dx + nt, *dz = dy + nt, *da = dz + n2, *dk = da + n2, *dq = dk + 2 * n2, *dres = dq + 2;
+    SGP_TRY(upload(c, dx, xtrain, nt)); SGP_TRY(upload(c, dy, ytrain, nt));
+    SGP_TRY(alpha_from_kyinv(c, kyinv, ztrain, n2, c.Kmat.as<double>(), dz, da));
+    const double qp[2] = {x, y};
+    SGP_TRY(upload(c, dq, qp, 2));
+    Pt* pa = c.pts.as<Pt>(); Pt* pb = pa + nt;
+    SGP_TRY(make_points(c, fam, per, dx, dy, nt, pa));
+    SGP_TRY(make_points(c, fam, per, dq, dq + 1, 1, pb));
+    const HypC h = make_hypc(fam, hyp3[0], hyp3[1], hyp3[2], per);
+    SGP_TRY(fill_hess(c, fam, pb, 1, pa, nt, h, dk, 2));          // Kstar(2, 2 nt), ld 2
+    dot_strided_kernel<<<1, 256, 0, c.stream>>>(dk, 2, 1, da, n2, dres);    // dot_product(Kstar(2,:), alpha)
+    SGP_CUDA(cudaGetLastError());
+    SGP_TRY(download(c, c.h_res + 32, dres, 1));
+    SGP_TRY(sync(c));
+    *out = c.h_res[32];
+    return ST_OK;
+}
+
+int sgp_calcp(sgp_ctx* ctx, int fam, double per, int solver, double x, double y, const double* hyp3, const double* hypp3,
+              const double* xtrainp, const double* ytrainp, const double* ztrainp, const double* kyinvp, long np,
+              const double* xtrain, const double* ytrain, const double* ztrain, const double* kyinv, long nt, double* out)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (np < 0 || nt < 0 || !out) { set_error("calcp: bad arguments"); return ST_BADARG; }
+    DevModelInputs in;
+    SGP_TRY(stage_kyinv_model(c, xtrainp, ytrainp, ztrainp, kyinvp, np, xtrain, ytrain, ztrain, kyinv, nt, in));
+    // one orbit, one step, no post-processing of P (MAP_HENON leaves P untouched): pfinal = P
+    double qf = 0.0, pf = 0.0;
+    SGP_TRY(applymap_host(ctx, MAP_HENON, fam, per, solver, 2, 1, &x, &y, hyp3, hypp3, in.dxp, in.dyp, in.dap, np, in.dx, in.dy,
+                          in.da, nt, nullptr, nullptr, nullptr, 0, &qf, &pf, nullptr));
+    *out = pf;
+    return ST_OK;
+}
+
+// ---- NLL / fit ------------------------------------------------------------------------------------
+static int check_res_info(const double* res)
+{
+    const double info = res[SGP_RES_INFO];
+    if (info > 0.0) {
+        set_error("Cholesky failed: leading minor of order %d is not positive definite", (int)info);
+        return (int)info;
+    }
+    return ST_OK;
+}
+
+int sgp_nll_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* d_xin, const double* d_z, long n,
+                int ngrad, double* d_res)
+{
+    SGP_TRY(check_ctx(ctx));
+    if (!hyp4 || !d_xin || !d_z || !d_res || (ngrad != 0 && ngrad != 2 && ngrad != 3)) { set_error("nll: bad arguments"); return ST_BADARG; }
+    NllJob j;
+    j.fam = fam; j.per = per; j.reg = reg;
+    for (int k = 0; k < 4; k++) j.hyp[k] = hyp4[k];
+    j.n = n; j.d_x = d_xin; j.d_z = d_z; j.ngrad = ngrad; j.d_res = d_res; j.d_alpha = nullptr; j.d_kinv = nullptr; j.d_L = nullptr;
+    return nll_enqueue(ctx->c, j);
+}
+
+static int nll_host(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* xin, const double* z, long n,
+                    int ngrad, double* alpha, double* kyinv, double* L, double* res)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (!hyp4 || !xin || !z || n <= 0 || (ngrad != 0 && ngrad != 2 && ngrad != 3)) { set_error("nll: bad arguments"); return ST_BADARG; }
+    const long N = reg ? n : n / 2;
+    const size_t out_mats = (kyinv ? (size_t)n * n : 0) + (L ? (size_t)n * n : 0);
+    SGP_TRY(c.io.reserve(((size_t)(2 * N + 2 * n) + RES_DOUBLES + out_mats + 8) * sizeof(double)));
+    double* d = c.io.as<double>();
+    double *dx = d, *dz = dx + 2 * N, *dres = dz + n, *dal = dres + RES_DOUBLES, *dki = dal + n, *dL = dki + (kyinv ? (size_t)n * n : 0);
+    SGP_TRY(upload(c, dx, xin, 2 * N));
+    SGP_TRY(upload(c, dz, z, n));
+    NllJob j;
+    j.fam = fam; j.per = per; j.reg = reg;
+    for (int k = 0; k < 4; k++) j.hyp[k] = hyp4[k];
+    j.n = n; j.d_x = dx; j.d_z = dz; j.ngrad = ngrad; j.d_res = dres;
+    j.d_alpha = alpha ? dal : nullptr; j.d_kinv = kyinv ? dki : nullptr; j.d_L = L ? dL : nullptr;
+    SGP_TRY(nll_enqueue(c, j));
+    SGP_TRY(download(c, c.h_res, dres, RES_DOUBLES));
+    if (alpha) SGP_TRY(download(c, alpha, dal, n));
+    if (kyinv) SGP_TRY(download(c, kyinv, dki, (size_t)n * n));
+    if (L) SGP_TRY(download(c, L, dL, (size_t)n * n));
+    SGP_TRY(sync(c));
+    if (res) memcpy(res, c.h_res, RES_DOUBLES * sizeof(double));
+    return check_res_info(c.h_res);
+}
+
+int sgp_nll(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* xin, const double* z, long n, int ngrad,
+            double* res)
+{
+    return nll_host(ctx, fam, per, reg, hyp4, xin, z, n, ngrad, nullptr, nullptr, nullptr, res);
+}
+
+int sgp_fit(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* xin, const double* z, long n,
+            double* alpha, double* kyinv, double* L, double* res)
+{
+    return nll_host(ctx, fam, per, reg, hyp4, xin, z, n, 0, alpha, kyinv, L, res);
+}
+
+// ---- dense building blocks ------------------------------------------------------------------------
+int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ainv, double* logdet_half)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (!A || n <= 0) { set_error("spd_factor: bad arguments"); return ST_BADARG; }
+    const long n_pad = round_up(n, TILE);
+    const int nt = (int)(n_pad / TILE);
+    SGP_TRY(c.io.reserve(((size_t)n * n + 8) * sizeof(double)));
+    SGP_TRY(c.Kmat.reserve((size_t)n_pad * n_pad * sizeof(double)));
+    SGP_TRY(c.Dinv.reserve((size_t)nt * TILE * TILE * sizeof(double)));
+    SGP_TRY(c.small.reserve((size_t)(nt + 8 + RES_DOUBLES) * sizeof(double)));
+    double* dA = c.io.as<double>();
+    double* K = c.Kmat.as<double>();
+    double* logparts = c.small.as<double>();
+    int* info = (int*)(logparts + nt);
+    double* dres = logparts + nt + 2;
+    SGP_TRY(upload(c, dA, A, (size_t)n * n));
+    embed_spd_kernel<<<1024, 256, 0, c.stream>>>(dA, n, K, n_pad);
+    SGP_CUDA(cudaGetLastError());
+    SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), c.stream));
+    SGP_TRY(potrf(c, K, n_pad, n_pad, c.Dinv.as<double>(), logparts, info));
+    sum_logs_kernel<<<1, 32, 0, c.stream>>>(logparts, nt, info, dres);
+    SGP_CUDA(cudaGetLastError());
+    if (L) {
+        extract_sym_kernel<<<1024, 256, 0, c.stream>>>(K, n_pad, dA, n, 0);
+        SGP_CUDA(cudaGetLastError());
+        SGP_TRY(download(c, L, dA, (size_t)n * n));
+    }
+    if (Ainv) {
+        SGP_TRY(c.Wmat.reserve((size_t)n_pad * n_pad * sizeof(double)));
+        SGP_TRY(c.Tmat.reserve((trtri_workspace_doubles(n_pad) + 2) * sizeof(double)));
+        SGP_TRY(trtri(c, K, n_pad, n_pad, c.Dinv.as<double>(), c.Tmat.as<double>()));
+        SGP_TRY(lauum(c, K, n_pad, n_pad, c.Wmat.as<double>(), n_pad));
+        extract_sym_kernel<<<1024, 256, 0, c.stream>>>(c.Wmat.as<double>(), n_pad, dA, n, 1);
+        SGP_CUDA(cudaGetLastError());
+        SGP_TRY(download(c, Ainv, dA, (size_t)n * n));
+    }
+    SGP_TRY(download(c, c.h_res, dres, RES_DOUBLES));
+    SGP_TRY(sync(c));
+    if (logdet_half) *logdet_half = c.h_res[SGP_RES_LOGD];
+    return check_res_info(c.h_res);
+}
+
+int sgp_selftest_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, double* max_err)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (Mt <= 0 || Nt <= 0 || K <= 0 || K % GK || !max_err) { set_error("selftest_gemm: bad arguments"); return ST_BADARG; }
+    if ((mode == TM_LOWER || mode == TM_LOWER_KGE) && Mt != Nt) { set_error("selftest_gemm: lower modes need Mt == Nt"); return ST_BADARG; }
+    const long M = (long)Mt * TILE, N = (long)Nt * TILE;
+    // operand storage: LAYOUT_MN -> (rows x K) ld rows ; LAYOUT_K -> (K x rows) ld K
+    const long lda = (al == LAYOUT_MN) ? M : K, ldb = (bl == LAYOUT_MN) ? N : K;
+    const size_t szA = (size_t)M * K, szB = (size_t)N * K, szC = (size_t)M * N;
+    SGP_TRY(c.Kmat.reserve((szA + szB + 3 * szC + 1024) * sizeof(double)));
+    double* dA = c.Kmat.as<double>();
+    double* dB = dA + szA; double* dC0 = dB + szB; double* dC1 = dC0 + szC; double* dC2 = dC1 + szC; double* dred = dC2 + szC;
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dA, (long)szA, 1ull, 1, 0);
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dB, (long)szB, 2ull, 1, 0);
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dC0, (long)szC, 3ull, 1, 0);
+    SGP_CUDA(cudaMemcpyAsync(dC1, dC0, szC * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    SGP_CUDA(cudaMemcpyAsync(dC2, dC0, szC * sizeof(double), cudaMemcpyDeviceToDevice, c.stream));
+    GemmArgs g;
+    g.A = dA; g.lda = lda; g.B = dB; g.ldb = ldb; g.ldc = M; g.Mt = Mt; g.Nt = Nt; g.K = K; g.alpha = -1.25; g.beta = 0.75; g.mode = mode;
+    g.C = dC1;
+    SGP_TRY(dmma_gemm(c, al, bl, g));
+    g.C = dC2;
+    SGP_TRY(ref_gemm(c, al, bl, g, dC2));
+    max_diff_kernel<<<256, 256, 0, c.stream>>>(dC1, dC2, (long)szC, dred);
+    SGP_CUDA(cudaGetLastError());
+    std::vector<double> red(256);
+    SGP_TRY(download(c, red.data(), dred, 256));
+    SGP_TRY(sync(c));
+    double m = 0.0;
+    for (double v : red) if (!(v <= m)) m = v;
+    *max_err = m;
+    return ST_OK;
+}
+
+int sgp_fill_sym_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* d_xin, long n, double* d_K, long ld)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    const long N = reg ? n : n / 2;
+    if (n <= 0 || ld < n || (ld & 1) || fam < 0 || fam > 2) { set_error("fill_sym_dev: bad arguments"); return ST_BADARG; }
+    SGP_TRY(c.pts.reserve((size_t)N * sizeof(Pt)));
+    Pt* pts = c.pts.as<Pt>();
+    const HypC h = make_hypc(fam, hyp4[0], hyp4[1], hyp4[2], per);
+    SGP_TRY(make_points(c, fam, per, d_xin, d_xin + N, N, pts));
+    if (reg) return fill_reg_sym(c, fam, pts, N, h, fabs(hyp4[3]), d_K, ld, ld >= round_up(n, TILE) ? round_up(n, TILE) : n);
+    return fill_hess_sym(c, fam, pts, N, h, fabs(hyp4[3]), d_K, ld, ld >= round_up(n, TILE) ? round_up(n, TILE) : n);
+}
+
+int sgp_potrf_dev(sgp_ctx* ctx, double* d_A, long n_pad, long ld, double* d_res)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (n_pad <= 0 || n_pad % TILE || ld < n_pad) { set_error("potrf_dev: order must be a multiple of 128"); return ST_BADARG; }
+    const int nt = (int)(n_pad / TILE);
+    SGP_TRY(c.Dinv.reserve((size_t)nt * TILE * TILE * sizeof(double)));
+    SGP_TRY(c.small.reserve((size_t)(nt + 8) * sizeof(double)));
+    double* logparts = c.small.as<double>();
+    int* info = (int*)(logparts + nt);
+    SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), c.stream));
+    SGP_TRY(potrf(c, d_A, n_pad, ld, c.Dinv.as<double>(), logparts, info));
+    sum_logs_kernel<<<1, 32, 0, c.stream>>>(logparts, nt, info, d_res);
+    SGP_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+

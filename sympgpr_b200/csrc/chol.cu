@@ -1,0 +1,344 @@
+// Blocked FP64 Cholesky (potrf), triangular solves (potrs), triangular inverse (trtri) and
+// X^T X (lauum) on one B200, built from the structured DMMA GEMM of dmma_gemm.cuh.
+//
+// Replaces the LAPACK calls the reference makes from Python:
+//   scipy.linalg.cholesky      python/05_tokamak/SympGPR/func.py:147       -> potrf
+//   solve_triangular x2        python/02_pert_pendulum/func.py:173-177     -> potrs
+//   np.linalg.inv (LU)         python/02_pert_pendulum/func.py:152         -> potri = trtri + lauum
+//
+// All matrices are column-major with order n_pad (a multiple of 128; rows/cols >= n carry an
+// identity block so factor, log-determinant and inverse of the leading n x n block are
+// unchanged).  Only the lower triangle is referenced.
+#include "chol.cuh"
+
+#include <limits.h>
+
+namespace sgp {
+
+// ------------------------------------------------------------------------------------------
+// 128 x 128 diagonal tile: factor in place, zero the strict upper part, emit inv(L) and
+// sum(log(diag L)).  One CTA, tile resident in shared memory (row stride 129 doubles).
+// ------------------------------------------------------------------------------------------
+constexpr int PT_LD = TILE + 1;
+constexpr size_t PT_SMEM = (size_t)(TILE * PT_LD + 2 * 256) * sizeof(double);
+
+__global__ void __launch_bounds__(256, 1)
+potrf_tile_kernel(double* __restrict__ A, long lda, double* __restrict__ Dinv, double* __restrict__ logpart,
+                  int* __restrict__ info, int col0)
+{
+    extern __shared__ __align__(16) double sm[];
+    double* S = sm;                      // S[r*PT_LD + c]
+    double* tmp = sm + TILE * PT_LD;     // 512 doubles scratch
+    const int tid = threadIdx.x;
+
+    for (int idx = tid; idx < TILE * TILE; idx += 256) {
+        int r = idx & (TILE - 1), c = idx >> 7;
+        S[r * PT_LD + c] = (r >= c) ? A[r + (long)c * lda] : 0.0;
+    }
+    __syncthreads();
+
+    const int r = tid & (TILE - 1);      // row owned in the trailing update
+    const int half = tid >> 7;           // columns of parity `half`
+    double mylog = 0.0;
+
+    for (int j = 0; j < TILE; j++) {
+        double d = S[j * PT_LD + j];
+        bool bad = !(d > 0.0);           // also true for NaN
+        if (bad) {
+            if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
+            d = 1.0;
+        }
+        const double dj = sqrt(d);
+        const double inv = 1.0 / dj;
+        __syncthreads();                 // everyone has read S[j][j]
+        if (half == 0) {
+            if (r > j) S[r * PT_LD + j] *= inv;
+            else if (r == j) { S[j * PT_LD + j] = dj; mylog = log(dj); }
+        }
+        __syncthreads();
+        if (r > j) {
+            const double lrj = S[r * PT_LD + j];
+            // columns c in (j, r] with c % 2 == half
+            int c = j + 1 + ((j + 1 + half) & 1);
+            for (; c <= r; c += 2) S[r * PT_LD + c] -= lrj * S[c * PT_LD + j];
+        }
+        __syncthreads();                 // S[j+1][j+1] final before the next pivot is read
+    }
+
+    // L back to global (lower + explicit zeros above the diagonal)
+    for (int idx = tid; idx < TILE * TILE; idx += 256) {
+        int rr = idx & (TILE - 1), c = idx >> 7;
+        A[rr + (long)c * lda] = S[rr * PT_LD + c];
+    }
+    // sum of log(diag): fixed order
+    if (half == 0) tmp[r] = mylog;
+    __syncthreads();
+    if (tid == 0) {
+        double s = 0.0;
+        for (int k = 0; k < TILE; k++) s += tmp[k];
+        *logpart = s;
+    }
+    __syncthreads();
+
+    // in-place inverse of the lower-triangular tile (unblocked, last column first):
+    //   X[j][j] = 1/L[j][j];  X[j+1:, j] = -X[j+1:, j+1:] * L[j+1:, j] * X[j][j]
+    for (int j = TILE - 1; j >= 0; j--) {
+        const double xjj = 1.0 / S[j * PT_LD + j];
+        double part = 0.0;
+        if (r > j) {
+            int k = j + 1 + ((j + 1 + half) & 1);
+            for (; k <= r; k += 2) part += S[r * PT_LD + k] * S[k * PT_LD + j];
+        }
+        tmp[tid] = part;
+        __syncthreads();                 // all reads of column j (still L) done
+        if (half == 0) {
+            if (r > j) S[r * PT_LD + j] = -(tmp[r] + tmp[r + TILE]) * xjj;
+            else if (r == j) S[j * PT_LD + j] = xjj;
+        }
+        __syncthreads();
+    }
+    for (int idx = tid; idx < TILE * TILE; idx += 256) {
+        int rr = idx & (TILE - 1), c = idx >> 7;
+        Dinv[rr + c * TILE] = S[rr * PT_LD + c];
+    }
+}
+
+// copy a 128x128 tile (src ld 128) into the matrix
+__global__ void copy_tile_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src)
+{
+    for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
+        int r = idx & (TILE - 1), c = idx >> 7;
+        dst[r + (long)c * ldd] = src[idx];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// potrs by blocked substitution with the tile inverses.
+// forward step j:  w_j = Dinv_j * y_j ;  y[rows below] -= L[rows below, j] * w_j
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TILE)
+trsv_fwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Dinv, double* __restrict__ y,
+                     double* __restrict__ w, int j)
+{
+    __shared__ double yj[TILE];
+    __shared__ double wj[TILE];
+    const int tid = threadIdx.x;
+    const long base = (long)j * TILE;
+    yj[tid] = y[base + tid];
+    __syncthreads();
+    {
+        const double* D = Dinv + (long)j * TILE * TILE;
+        double s = 0.0;
+        for (int c = 0; c <= tid; c++) s += D[tid + c * TILE] * yj[c];
+        wj[tid] = s;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        w[base + tid] = wj[tid];
+        return;
+    }
+    const long row = base + (long)blockIdx.x * TILE + tid;     // blockIdx.x >= 1: rows below the tile
+    const double* Lr = L + row + base * ld;
+    double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+    for (int c = 0; c < TILE; c += 2) {
+        s0 += Lr[(long)c * ld] * wj[c];
+        s1 += Lr[(long)(c + 1) * ld] * wj[c + 1];
+    }
+    y[row] -= (s0 + s1);
+}
+
+// backward step j:  a_j = Dinv_j^T * w_j ;  w[cols left] -= L[tile rows j, cols left]^T * a_j
+__global__ void __launch_bounds__(256)
+trsv_bwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Dinv, double* __restrict__ w,
+                     double* __restrict__ a, int j)
+{
+    __shared__ double wj[TILE];
+    __shared__ double aj[TILE];
+    const int tid = threadIdx.x;
+    const long base = (long)j * TILE;
+    if (tid < TILE) wj[tid] = w[base + tid];
+    __syncthreads();
+    if (tid < TILE) {
+        const double* D = Dinv + (long)j * TILE * TILE;
+        double s = 0.0;
+        for (int rr = tid; rr < TILE; rr++) s += D[rr + tid * TILE] * wj[rr];   // (Dinv^T)[tid][rr]
+        aj[tid] = s;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (tid < TILE) a[base + tid] = aj[tid];
+        return;
+    }
+    // blocks 1..: 64 columns each, 8 warps x 8 columns
+    const int warp = tid >> 5, lane = tid & 31;
+    const long c0 = (long)(blockIdx.x - 1) * 64 + warp * 8;
+    for (int cc = 0; cc < 8; cc++) {
+        const long col = c0 + cc;
+        const double* Lc = L + base + col * ld;
+        double s = Lc[lane] * aj[lane] + Lc[lane + 32] * aj[lane + 32] + Lc[lane + 64] * aj[lane + 64] +
+                   Lc[lane + 96] * aj[lane + 96];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) w[col] -= s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// drivers
+// ------------------------------------------------------------------------------------------
+static int g_potrf_cfg = 0;
+
+static int launch_potrf_tile(Ctx& c, double* A, long lda, double* Dinv, double* logparts, int* info, int jt)
+{
+    if (!g_potrf_cfg) {
+        SGP_CUDA(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
+        g_potrf_cfg = 1;
+    }
+    const long o = (long)jt * TILE;
+    potrf_tile_kernel<<<1, 256, PT_SMEM, c.stream>>>(A + o + o * lda, lda, Dinv + (long)jt * TILE * TILE, logparts + jt,
+                                                      info, (int)o);
+    SGP_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+
+static int gemm(Ctx& c, int al, int bl, const double* A, long lda, const double* B, long ldb, double* C, long ldc,
+                int Mt, int Nt, long K, double alpha, double beta, int mode)
+{
+    GemmArgs g;
+    g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
+    g.Mt = Mt; g.Nt = Nt; g.K = (int)K; g.alpha = alpha; g.beta = beta; g.mode = mode;
+    SGP_CUDA(gemm_launch(al, bl, g, c.stream));
+    return ST_OK;
+}
+
+#define AT(A, lda, rt, ct) ((A) + (long)(rt) * TILE + (long)(ct) * TILE * (lda))
+
+// X * L[l0..l0+kt)^T = B,  B = A[r0..r0+rt) x [l0..l0+kt)  (tile indices), in place
+static int trsm_rec(Ctx& c, double* A, long lda, const double* Dinv, int l0, int kt, int r0, int rt)
+{
+    if (rt <= 0) return ST_OK;
+    if (kt == 1) {
+        double* B = AT(A, lda, r0, l0);
+        return gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, Dinv + (long)l0 * TILE * TILE, TILE, B, lda, rt, 1, TILE, 1.0, 0.0,
+                    TM_FULL);
+    }
+    const int k1 = kt / 2, k2 = kt - k1;
+    SGP_TRY(trsm_rec(c, A, lda, Dinv, l0, k1, r0, rt));
+    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, AT(A, lda, r0, l0), lda, AT(A, lda, l0 + k1, l0), lda, AT(A, lda, r0, l0 + k1),
+                 lda, rt, k2, (long)k1 * TILE, -1.0, 1.0, TM_FULL));
+    return trsm_rec(c, A, lda, Dinv, l0 + k1, k2, r0, rt);
+}
+
+static int potrf_rec(Ctx& c, double* A, long lda, double* Dinv, double* logparts, int* info, int j0, int mt)
+{
+    if (mt == 1) return launch_potrf_tile(c, A, lda, Dinv, logparts, info, j0);
+    const int m1 = mt / 2, m2 = mt - m1;
+    SGP_TRY(potrf_rec(c, A, lda, Dinv, logparts, info, j0, m1));
+    SGP_TRY(trsm_rec(c, A, lda, Dinv, j0, m1, j0 + m1, m2));
+    double* B = AT(A, lda, j0 + m1, j0);
+    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, B, lda, AT(A, lda, j0 + m1, j0 + m1), lda, m2, m2, (long)m1 * TILE,
+                 -1.0, 1.0, TM_LOWER));
+    return potrf_rec(c, A, lda, Dinv, logparts, info, j0 + m1, m2);
+}
+
+int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info)
+{
+    if (n_pad % TILE || lda % 2) { set_error("potrf: n_pad %ld / lda %ld not tile aligned", n_pad, lda); return ST_BADARG; }
+    return potrf_rec(c, A, lda, Dinv, logparts, info, 0, (int)(n_pad / TILE));
+}
+
+int potrs(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w, double* alpha)
+{
+    const int nt = (int)(n_pad / TILE);
+    for (int j = 0; j < nt; j++) {
+        trsv_fwd_step_kernel<<<nt - j, TILE, 0, c.stream>>>(L, lda, Dinv, y, w, j);
+    }
+    SGP_CUDA(cudaGetLastError());
+    for (int j = nt - 1; j >= 0; j--) {
+        trsv_bwd_step_kernel<<<1 + 2 * j, 256, 0, c.stream>>>(L, lda, Dinv, w, alpha, j);
+    }
+    SGP_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+
+static int trtri_rec(Ctx& c, double* A, long lda, const double* Dinv, double* T, int j0, int mt)
+{
+    if (mt == 1) {
+        copy_tile_kernel<<<1, 256, 0, c.stream>>>(AT(A, lda, j0, j0), lda, Dinv + (long)j0 * TILE * TILE);
+        SGP_CUDA(cudaGetLastError());
+        return ST_OK;
+    }
+    const int m1 = mt / 2, m2 = mt - m1;
+    SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, m1));
+    SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0 + m1, m2));
+    const long ldt = (long)m2 * TILE;
+    // T = L21 * X11        (X11 lower: k >= tn*128)
+    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + m1, j0), lda, AT(A, lda, j0, j0), lda, T, ldt, m2, m1,
+                 (long)m1 * TILE, 1.0, 0.0, TM_B_LOWER));
+    // L21 = -X22 * T       (X22 lower: k < (tm+1)*128)
+    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + m1, j0 + m1), lda, T, ldt, AT(A, lda, j0 + m1, j0), lda, m2, m1,
+                 (long)m2 * TILE, -1.0, 0.0, TM_A_LOWER));
+    return ST_OK;
+}
+
+int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T)
+{
+    return trtri_rec(c, A, lda, Dinv, T, 0, (int)(n_pad / TILE));
+}
+
+size_t trtri_workspace_doubles(long n_pad)
+{
+    const long mt = n_pad / TILE;
+    const long m1 = mt / 2, m2 = mt - m1;
+    return (size_t)(m1 * TILE) * (size_t)(m2 * TILE);
+}
+
+int lauum(Ctx& c, const double* X, long n_pad, long lda, double* W, long ldw)
+{
+    const int nt = (int)(n_pad / TILE);
+    return gemm(c, LAYOUT_K, LAYOUT_K, X, lda, X, lda, W, ldw, nt, nt, n_pad, 1.0, 0.0, TM_LOWER_KGE);
+}
+
+// ------------------------------------------------------------------------------------------
+// self test support: plain FP64 reference GEMM (one thread per output element)
+// ------------------------------------------------------------------------------------------
+__global__ void ref_gemm_kernel(GemmArgs p, int al, int bl, double* __restrict__ out)
+{
+    const long M = (long)p.Mt * TILE, N = (long)p.Nt * TILE;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * N) return;
+    const long m = idx % M, n = idx / M;
+    const int tm = (int)(m / TILE), tn = (int)(n / TILE);
+    long k0 = 0, k1 = p.K;
+    bool skip = false;
+    if (p.mode == TM_LOWER || p.mode == TM_LOWER_KGE) skip = tn > tm;
+    if (p.mode == TM_LOWER_KGE) k0 = (long)tm * TILE;
+    if (p.mode == TM_B_LOWER) k0 = (long)tn * TILE;
+    if (p.mode == TM_A_LOWER) { k1 = (long)(tm + 1) * TILE; if (k1 > p.K) k1 = p.K; }
+    double* o = out + m + n * p.ldc;
+    if (skip) return;
+    double s = 0.0;
+    for (long k = k0; k < k1; k++) {
+        const double a = (al == LAYOUT_MN) ? p.A[m + k * p.lda] : p.A[k + m * p.lda];
+        const double b = (bl == LAYOUT_MN) ? p.B[n + k * p.ldb] : p.B[k + n * p.ldb];
+        s += a * b;
+    }
+    *o = (p.beta == 0.0 ? 0.0 : p.beta * (*o)) + p.alpha * s;
+}
+
+int ref_gemm(Ctx& c, int al, int bl, const GemmArgs& g, double* out)
+{
+    const long tot = (long)g.Mt * TILE * (long)g.Nt * TILE;
+    ref_gemm_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, c.stream>>>(g, al, bl, out);
+    SGP_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+
+int dmma_gemm(Ctx& c, int al, int bl, const GemmArgs& g)
+{
+    SGP_CUDA(gemm_launch(al, bl, g, c.stream));
+    return ST_OK;
+}
+
+}  // namespace sgp

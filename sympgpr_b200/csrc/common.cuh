@@ -1,0 +1,79 @@
+// Shared host-side plumbing of libsympgpr_b200: context, workspace, error codes.
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "forms.cuh"
+
+namespace sgp {
+
+// status codes of the C ABI (include/sympgpr_b200.h)
+constexpr int ST_OK = 0;
+constexpr int ST_BADARG = -1;
+constexpr int ST_CUDA = -2;
+constexpr int ST_NOMEM = -3;
+constexpr int ST_NODEV = -4;
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+
+#define SGP_CUDA(call)                                                                        \
+    do {                                                                                      \
+        cudaError_t e__ = (call);                                                             \
+        if (e__ != cudaSuccess) {                                                             \
+            sgp::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return (e__ == cudaErrorMemoryAllocation) ? sgp::ST_NOMEM : sgp::ST_CUDA;        \
+        }                                                                                     \
+    } while (0)
+
+#define SGP_TRY(call)            \
+    do {                         \
+        int s__ = (call);        \
+        if (s__ != 0) return s__; \
+    } while (0)
+
+// A growable device buffer.
+struct DBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return ST_OK;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e != cudaSuccess) {
+            set_error("cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+            cudaGetLastError();
+            return ST_NOMEM;
+        }
+        cap = bytes;
+        return ST_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <class T> T* as() const { return (T*)p; }
+};
+
+constexpr int TILE = 128;
+inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
+
+// Result block written by the device-side finalisation of an NLL evaluation.
+//   [0] nll  [1] dlx  [2] dly  [3] dsig  [4] info (0 ok, >0 first non-positive pivot, 1-based)
+//   [5] 0.5*y'alpha  [6] sum log diag(L)  [7] reserved
+//   [8..10] A_lx, A_ly, A_sig = alpha' dK alpha   [11..13] B_lx, B_ly, B_sig = trace(Kyinv dK)
+constexpr int RES_DOUBLES = 16;
+
+struct Ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;    // main stream (borrowed or owned)
+    bool own_stream = false;
+    cudaStream_t side = nullptr;      // panel / look-ahead stream (owned)
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io;
+    double* h_res = nullptr;          // pinned host staging (RES_DOUBLES + spare)
+    int sm_count = 148;
+};
+
+}  // namespace sgp

@@ -1,0 +1,160 @@
+// NLL, NLL+gradient and model fit on one GPU.
+//
+// Reference call sites this pipeline replaces as a whole:
+//   nll_chol      python/05_tokamak/SympGPR/func.py:143-150     (fill, + noise, potrf, potrs, value)
+//   nll_chol_reg  python/05_tokamak/SympGPR/func.py:134-141
+//   nll_grad      python/02_pert_pendulum/func.py:148-162       (+ inverse, dK, traces)
+//   nll_grad_reg  python/02_pert_pendulum/func.py:132-146
+//   Kyinv = scipy.linalg.inv(K + sig2_n I)  python/01_pendulum/implicit/main.py:138-140,159-161
+#include "nll.cuh"
+
+#include "chol.cuh"
+#include "fill.cuh"
+#include "grad.cuh"
+
+namespace sgp {
+
+__global__ void finalize_kernel(const double* __restrict__ z, const double* __restrict__ alpha, long n,
+                                const double* __restrict__ logparts, int nt, const int* __restrict__ info,
+                                const double* __restrict__ partial, long npart, double sig, int ngrad,
+                                double* __restrict__ res)
+{
+    __shared__ double red[256];
+    const int tid = threadIdx.x;
+    // 0.5 * z' alpha, fixed summation order
+    double s = 0.0;
+    for (long i = tid; i < n; i += 256) s += z[i] * alpha[i];
+    red[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    const double quad = 0.5 * red[0];
+    __syncthreads();
+    double g[6] = {0, 0, 0, 0, 0, 0};
+    if (ngrad > 0) {
+        for (int k = 0; k < 6; k++) {
+            double a = 0.0;
+            for (long b = tid; b < npart; b += 256) a += partial[b * 6 + k];
+            red[tid] = a;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1) {
+                if (tid < o) red[tid] += red[tid + o];
+                __syncthreads();
+            }
+            g[k] = red[0];
+            __syncthreads();
+        }
+    }
+    if (tid == 0) {
+        double ld = 0.0;
+        for (int k = 0; k < nt; k++) ld += logparts[k];
+        res[0] = quad + ld;
+        res[5] = quad;
+        res[6] = ld;
+        res[4] = (double)(*info);
+        res[7] = 0.0;
+        // dK_theta = sig * d3k..., dK_sig = K / sig
+        const double A[3] = {sig * g[0], sig * g[1], g[2]};
+        const double B[3] = {sig * g[3], sig * g[4], g[5]};
+        for (int k = 0; k < 3; k++) {
+            res[1 + k] = (ngrad > k) ? (-0.5 * A[k] + 0.5 * B[k]) : 0.0;
+            res[8 + k] = A[k];
+            res[11 + k] = B[k];
+        }
+        res[14] = res[15] = 0.0;
+    }
+}
+
+// dst (n x n, ld n) = symmetric completion of the lower triangle of src (ld lds)
+__global__ void sym_out_kernel(const double* __restrict__ src, long lds, double* __restrict__ dst, long n)
+{
+    const long tot = n * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx % n, c = idx / n;
+        dst[idx] = (r >= c) ? src[r + c * lds] : src[c + r * lds];
+    }
+}
+
+// dst (n x n, ld n) = lower triangle of src, zeros above
+__global__ void tril_out_kernel(const double* __restrict__ src, long lds, double* __restrict__ dst, long n)
+{
+    const long tot = n * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx % n, c = idx / n;
+        dst[idx] = (r >= c) ? src[r + c * lds] : 0.0;
+    }
+}
+
+int nll_enqueue(Ctx& c, const NllJob& job)
+{
+    const long n = job.n;
+    if (n <= 0) { set_error("nll: empty problem (n = %ld)", n); return ST_BADARG; }
+    if (!job.reg && (n % 2)) { set_error("nll: derivative-kernel order must be even, got %ld", n); return ST_BADARG; }
+    const long N = job.reg ? n : n / 2;
+    const long n_pad = round_up(n, TILE);
+    const int nt = (int)(n_pad / TILE);
+    const int fam = job.fam;
+    if (fam < 0 || fam > 2) { set_error("unknown kernel family %d", fam); return ST_BADARG; }
+    if (!(job.hyp[0] > 0.0) || !(job.hyp[1] > 0.0)) { set_error("nll: length scales must be positive"); return ST_BADARG; }
+    const bool need_inv = job.ngrad > 0 || job.d_kinv != nullptr;
+
+    SGP_TRY(c.Kmat.reserve((size_t)n_pad * n_pad * sizeof(double)));
+    SGP_TRY(c.Dinv.reserve((size_t)nt * TILE * TILE * sizeof(double)));
+    SGP_TRY(c.vecs.reserve((size_t)4 * n_pad * sizeof(double)));
+    SGP_TRY(c.pts.reserve((size_t)N * sizeof(Pt)));
+    const long npart = need_inv ? grad_num_partials(N) : 0;
+    SGP_TRY(c.partial.reserve((size_t)(npart * 6 + 8) * sizeof(double)));
+    SGP_TRY(c.small.reserve((size_t)(nt + 8) * sizeof(double)));
+    if (need_inv) {
+        SGP_TRY(c.Wmat.reserve((size_t)n_pad * n_pad * sizeof(double)));
+        SGP_TRY(c.Tmat.reserve((trtri_workspace_doubles(n_pad) + 2) * sizeof(double)));
+    }
+    double* K = c.Kmat.as<double>();
+    double* Dinv = c.Dinv.as<double>();
+    double* yv = c.vecs.as<double>();
+    double* wv = yv + n_pad;
+    double* av = wv + n_pad;
+    Pt* pts = c.pts.as<Pt>();
+    double* logparts = c.small.as<double>();
+    int* info = (int*)(logparts + nt);
+    cudaStream_t st = c.stream;
+
+    const HypC h = make_hypc(fam, job.hyp[0], job.hyp[1], job.hyp[2], job.per);
+    const double noise = fabs(job.hyp[3]);
+
+    SGP_TRY(make_points(c, fam, job.per, job.d_x, job.d_x + N, N, pts));
+    if (job.reg) SGP_TRY(fill_reg_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
+    else SGP_TRY(fill_hess_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
+
+    SGP_CUDA(cudaMemsetAsync(yv, 0, (size_t)n_pad * sizeof(double), st));
+    SGP_CUDA(cudaMemcpyAsync(yv, job.d_z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), st));
+
+    SGP_TRY(potrf(c, K, n_pad, n_pad, Dinv, logparts, info));
+    if (job.d_L) {
+        tril_out_kernel<<<1024, 256, 0, st>>>(K, n_pad, job.d_L, n);
+        SGP_CUDA(cudaGetLastError());
+    }
+    SGP_TRY(potrs(c, K, n_pad, n_pad, Dinv, yv, wv, av));
+    if (job.d_alpha) SGP_CUDA(cudaMemcpyAsync(job.d_alpha, av, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+
+    double* partial = c.partial.as<double>();
+    if (need_inv) {
+        double* W = c.Wmat.as<double>();
+        SGP_TRY(trtri(c, K, n_pad, n_pad, Dinv, c.Tmat.as<double>()));
+        SGP_TRY(lauum(c, K, n_pad, n_pad, W, n_pad));
+        if (job.ngrad > 0) SGP_TRY(grad_contract(c, fam, job.reg, pts, N, h, W, n_pad, av, partial));
+        if (job.d_kinv) {
+            sym_out_kernel<<<1024, 256, 0, st>>>(W, n_pad, job.d_kinv, n);
+            SGP_CUDA(cudaGetLastError());
+        }
+    }
+    finalize_kernel<<<1, 256, 0, st>>>(job.d_z, av, n, logparts, nt, info, partial, job.ngrad > 0 ? npart : 0, job.hyp[2],
+                                       job.ngrad, job.d_res);
+    SGP_CUDA(cudaGetLastError());
+    return ST_OK;
+}
+
+}  // namespace sgp

@@ -1,0 +1,153 @@
+"""CPU tests of the product boundary: the C-ABI library builds/loads and exports every symbol
+include/sympgpr_b200.h declares, host-side scalar entry points agree with the golden vectors,
+argument validation mirrors f2py, and compute entry points fail loudly without a GPU."""
+import ctypes
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+G = os.path.join(ROOT, "tests", "golden")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from sympgpr_b200 import _lib
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    hdr = open(os.path.join(ROOT, "include", "sympgpr_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = sorted(set(re.findall(r"\b(sgp_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 25
+    from sympgpr_b200 import _lib
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in the header but not exported"
+        assert n in _lib._PROTOS, f"{n} has no ctypes prototype"
+    assert lib.sgp_version() >= 100
+
+
+def test_no_oracle_in_product():
+    """The product must never import or link the oracle."""
+    pkg = os.path.join(ROOT, "sympgpr_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                txt = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "import oracle" not in txt and "from oracle" not in txt and "liboracle" not in txt, f
+    out = subprocess.run(["ldd", os.path.join(pkg, "libsympgpr_b200.so")], capture_output=True, text=True).stdout
+    assert "oracle" not in out
+
+
+@pytest.mark.parametrize("family,module", [("product", "kernels"), ("sq", "kernels_sq"), ("sum", "kernels_sum"),
+                                           ("period", "kernels_period")])
+def test_kernels_modules_match_reference_sympy(family, module):
+    """`from kernels import *` surface (19 scalar functions) against the reference derivation."""
+    import sympgpr_b200
+    mods = sympgpr_b200.install_shims()
+    mod = mods[module]
+    g = np.load(os.path.join(G, f"kernel_forms_{family}.npz"))
+    pts = g["points"]
+    from sympgpr_b200.api import SCALAR_NAMES
+    assert set(SCALAR_NAMES) <= set(dir(mod))
+    for name in SCALAR_NAMES:
+        v = np.array([getattr(mod, name)(*p) for p in pts])
+        ref = g[name]
+        scale = np.maximum(np.abs(ref), 1e-3 * np.max(np.abs(ref)) + 1e-300)
+        assert np.max(np.abs(v - ref) / scale) < 1e-12, (family, name)
+
+
+def test_shim_module_surface():
+    import sympgpr_b200
+    sympgpr_b200.install_shims()
+    from sympgpr import sympgpr
+    from fortran.sympgpr import sympgpr as s2
+    from fieldlines import fieldlines
+    for n in ("build_k", "buildkreg", "guessp", "calcq", "calcp", "applymap_tok", "pi"):
+        assert hasattr(sympgpr, n) and hasattr(s2, n)
+    assert abs(sympgpr.pi - np.pi) < 1e-15
+    r = fieldlines.compute_r(np.array([0.02, 1.0, 0.0]), 0.3)
+    assert abs(0.02 - fieldlines.ath(r, 1.0, 0.0)) < 1e-15
+
+
+def test_f2py_style_argument_errors():
+    from sympgpr_b200 import api
+    K = np.zeros((4, 4), order="F")
+    with pytest.raises(ValueError):
+        api.build_k([0.0, 1.0], [0.0, 1.0], [0.0, 1.0], [0.0, 1.0], [1.0, 1.0], K)          # hyp must have 3
+    with pytest.raises(ValueError):
+        api.build_k([0.0, 1.0], [0.0, 1.0], [0.0, 1.0], [0.0, 1.0], [1.0, 1.0, 1.0], K.astype(np.float32))
+    q = np.zeros((2, 3, 1))                                                                    # C order
+    with pytest.raises(ValueError):
+        api.applymap_tok_f2py([1, 1, 1], [1, 1, 1], np.zeros(3), np.zeros(3), [0.0], [0.0], [0.0], [[1.0]], [0.0], [0.0],
+                              [0.0, 0.0], np.eye(2), q, q.copy())
+
+
+def test_compute_fails_loudly_without_gpu():
+    from sympgpr_b200 import _lib, api
+    if _lib.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(RuntimeError, match="no CPU fallback|no CUDA device"):
+        api.nll_chol([1.0, 1.0, 1.0, 1e-8], np.zeros(4), np.zeros(4), 4)
+    with pytest.raises(RuntimeError):
+        api.build_k([0.0], [0.0], [0.0], [0.0], [1.0, 1.0, 1.0], np.zeros((2, 2), order="F"))
+
+
+# ---------------------------------------------------------------------------------------------------
+# device headers compiled for the host: the solver state machines against the oracle
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    out = tmp_path_factory.mktemp("harness") / "libharness.so"
+    src = os.path.join(ROOT, "tests", "harness", "host_harness.cpp")
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-fPIC", "-shared", "-ffp-contract=off", "-o", str(out), src])
+    H = ctypes.CDLL(str(out))
+    H.harness_calcp.restype = ctypes.c_double
+    return H
+
+
+def _dp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+
+
+@pytest.mark.parametrize("family,fid", [("product", 0), ("sq", 1)])
+def test_device_solvers_on_host_match_oracle(harness, family, fid):
+    from oracle import c_oracle as C
+    from oracle import oracle as O
+    N = 48
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8)
+    hyp[:2] *= 2
+    hypp[:2] *= 2
+    xt, zt, xtp, ztp = d["xtrain"], d["ztrain"], d["xtrainp"], d["ztrainp"]
+    alpha = O.fit_alpha(hyp, xt, zt, 2 * N, family=family)
+    alphap = O.fit_alpha(hypp, xtp, ztp, N, reg=True, family=family)
+    h3, hp3 = np.ascontiguousarray(hyp[:3]), np.ascontiguousarray(hypp[:3])
+    xq, yP = np.ascontiguousarray(xt[:N]), np.ascontiguousarray(xt[N:])
+    xpq, ypp = np.ascontiguousarray(xtp[:N]), np.ascontiguousarray(xtp[N:])
+    q0 = O.halton(40, 5) * 2 * np.pi
+    p0 = 1.0 + O.halton(40, 7) * 4
+    nconv = 0
+    for q, p in zip(q0, p0):
+        Pc, info, _ = C.calcp_alpha(q, p, h3, hp3, xpq, ypp, alphap, xq, yP, alpha, family)
+        dq_ref = None
+        for solver in (0, 1):
+            i1, n1, dq = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+            P = harness.harness_calcp(fid, solver, ctypes.c_double(0.5), ctypes.c_double(q), ctypes.c_double(p), _dp(h3),
+                                      _dp(hp3), _dp(xpq), _dp(ypp), _dp(alphap), ctypes.c_long(N), _dp(xq), _dp(yP),
+                                      _dp(alpha), ctypes.c_long(N), ctypes.byref(i1), ctypes.byref(n1), ctypes.byref(dq))
+            if info == 1 and i1.value == 1:
+                nconv += 1
+                assert abs(P - Pc) <= 1e-11 * max(1.0, abs(Pc)), (family, solver, q, p)
+                if dq_ref is None:
+                    dq_ref = dq.value
+                assert abs(dq.value - dq_ref) < 1e-9
+            if solver == 1:
+                assert n1.value <= (12 if family == "product" else 50)
+    assert nconv >= (60 if family == "product" else 30)

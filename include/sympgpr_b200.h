@@ -64,6 +64,7 @@ typedef struct sgp_model sgp_model;
 
 /* ---- context ------------------------------------------------------------------------------ */
 int sgp_version(void);
+unsigned long long sgp_launch_count(void);        /* kernels launched by this library so far */
 const char* sgp_last_error(void);
 int sgp_device_count(void);                       /* 0 when no usable CUDA device            */
 int sgp_create(int device, sgp_ctx** out);        /* owns one stream + growable workspaces   */
@@ -167,6 +168,9 @@ int sgp_selftest_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, in
 int sgp_fill_sym_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* d_xin,
                      long n, double* d_K, long ld);
 int sgp_potrf_dev(sgp_ctx* ctx, double* d_A, long n_pad, long ld, double* d_res);
+/* full (2N x 2N0) build_k on device buffers: the HBM-write roofline case (8 n^2 bytes) */
+int sgp_build_k_dev(sgp_ctx* ctx, int fam, double per, const double* d_x, const double* d_y, long N,
+                    const double* d_x0, const double* d_y0, long N0, const double* hyp3, double* d_K, long ld);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,7 @@ _ctx = {}
 
 _PROTOS = {
     "sgp_version": (c_i, []),
+    "sgp_launch_count": (ctypes.c_ulonglong, []),
     "sgp_last_error": (ctypes.c_char_p, []),
     "sgp_device_count": (c_i, []),
     "sgp_create": (c_i, [c_i, ctypes.POINTER(c_vp)]),
@@ -65,6 +66,7 @@ _PROTOS = {
     "sgp_selftest_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
     "sgp_fill_sym_dev": (c_i, [c_vp, c_i, c_d, c_i, c_dp, c_vp, c_l, c_vp, c_l]),
     "sgp_potrf_dev": (c_i, [c_vp, c_vp, c_l, c_l, c_vp]),
+    "sgp_build_k_dev": (c_i, [c_vp, c_i, c_d, c_vp, c_vp, c_l, c_vp, c_vp, c_l, c_dp, c_vp, c_l]),
 }
 
 

@@ -132,6 +132,7 @@ static int sync(Ctx& c)
 // every sgp_* function below is declared extern "C" in include/sympgpr_b200.h
 
 int sgp_version(void) { return 100; }
+unsigned long long sgp_launch_count(void) { return launch_count(); }
 const char* sgp_last_error(void) { return get_error(); }
 
 int sgp_device_count(void)
@@ -766,6 +767,19 @@ int sgp_fill_sym_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* h
     SGP_TRY(make_points(c, fam, per, d_xin, d_xin + N, N, pts));
     if (reg) return fill_reg_sym(c, fam, pts, N, h, fabs(hyp4[3]), d_K, ld, ld >= round_up(n, TILE) ? round_up(n, TILE) : n);
     return fill_hess_sym(c, fam, pts, N, h, fabs(hyp4[3]), d_K, ld, ld >= round_up(n, TILE) ? round_up(n, TILE) : n);
+}
+
+int sgp_build_k_dev(sgp_ctx* ctx, int fam, double per, const double* d_x, const double* d_y, long N, const double* d_x0,
+                    const double* d_y0, long N0, const double* hyp3, double* d_K, long ld)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (N <= 0 || N0 <= 0 || ld < 2 * N || fam < 0 || fam > 2 || !hyp3) { set_error("build_k_dev: bad arguments"); return ST_BADARG; }
+    SGP_TRY(c.pts.reserve((size_t)(N + N0) * sizeof(Pt)));
+    Pt* pb = c.pts.as<Pt>(); Pt* pa = pb + N;
+    SGP_TRY(make_points(c, fam, per, d_x, d_y, N, pb));
+    SGP_TRY(make_points(c, fam, per, d_x0, d_y0, N0, pa));
+    return fill_hess(c, fam, pb, N, pa, N0, make_hypc(fam, hyp3[0], hyp3[1], hyp3[2], per), d_K, ld);
 }
 
 int sgp_potrf_dev(sgp_ctx* ctx, double* d_A, long n_pad, long ld, double* d_res)

@@ -199,6 +199,7 @@ static int launch_potrf_tile(Ctx& c, double* A, long lda, double* Dinv, double* 
     potrf_tile_kernel<<<1, 256, PT_SMEM, c.stream>>>(A + o + o * lda, lda, Dinv + (long)jt * TILE * TILE, logparts + jt,
                                                       info, (int)o);
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 
@@ -209,6 +210,7 @@ static int gemm(Ctx& c, int al, int bl, const double* A, long lda, const double*
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.Mt = Mt; g.Nt = Nt; g.K = (int)K; g.alpha = alpha; g.beta = beta; g.mode = mode;
     SGP_CUDA(gemm_launch(al, bl, g, c.stream));
+    count_launch();
     return ST_OK;
 }
 
@@ -255,6 +257,7 @@ int potrs(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, dou
         trsv_fwd_step_kernel<<<nt - j, TILE, 0, c.stream>>>(L, lda, Dinv, y, w, j);
     }
     SGP_CUDA(cudaGetLastError());
+    count_launch(2ull * nt);
     for (int j = nt - 1; j >= 0; j--) {
         trsv_bwd_step_kernel<<<1 + 2 * j, 256, 0, c.stream>>>(L, lda, Dinv, w, alpha, j);
     }
@@ -266,6 +269,7 @@ static int trtri_rec(Ctx& c, double* A, long lda, const double* Dinv, double* T,
 {
     if (mt == 1) {
         copy_tile_kernel<<<1, 256, 0, c.stream>>>(AT(A, lda, j0, j0), lda, Dinv + (long)j0 * TILE * TILE);
+        count_launch();
         SGP_CUDA(cudaGetLastError());
         return ST_OK;
     }
@@ -338,6 +342,7 @@ int ref_gemm(Ctx& c, int al, int bl, const GemmArgs& g, double* out)
 int dmma_gemm(Ctx& c, int al, int bl, const GemmArgs& g)
 {
     SGP_CUDA(gemm_launch(al, bl, g, c.stream));
+    count_launch();
     return ST_OK;
 }
 

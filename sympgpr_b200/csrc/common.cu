@@ -16,4 +16,8 @@ void set_error(const char* fmt, ...)
 
 const char* get_error() { return g_err; }
 
+static unsigned long long g_launches = 0ull;
+void count_launch(unsigned long long n) { __atomic_fetch_add(&g_launches, n, __ATOMIC_RELAXED); }
+unsigned long long launch_count() { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
 }  // namespace sgp

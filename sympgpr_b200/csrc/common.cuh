@@ -17,6 +17,8 @@ constexpr int ST_NOMEM = -3;
 constexpr int ST_NODEV = -4;
 
 void set_error(const char* fmt, ...);
+void count_launch(unsigned long long n = 1ull);   // kernels launched by this library (bench.py gpu_launches)
+unsigned long long launch_count();
 const char* get_error();
 
 #define SGP_CUDA(call)                                                                        \

@@ -32,6 +32,7 @@ int make_points(Ctx& c, int fam, double p, const double* x, const double* y, lon
     if (fam == FAM_SQ) points_kernel<FAM_SQ><<<g, 256, 0, c.stream>>>(x, y, n, p, out);
     else points_kernel<FAM_PRODUCT><<<g, 256, 0, c.stream>>>(x, y, n, p, out);
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 
@@ -96,6 +97,7 @@ int fill_hess(Ctx& c, int fam, const Pt* pb, long N, const Pt* pa, long N0, cons
     default: set_error("unknown kernel family %d", fam); return ST_BADARG;
     }
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 
@@ -167,8 +169,10 @@ int fill_hess_sym(Ctx& c, int fam, const Pt* pts, long N, const HypC& h, double 
     default: set_error("unknown kernel family %d", fam); return ST_BADARG;
     }
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     if (n_pad > 2 * N) {
         pad_identity_kernel<<<256, 256, 0, c.stream>>>(K, ld, 2 * N, n_pad);
+        count_launch();
         SGP_CUDA(cudaGetLastError());
     }
     return ST_OK;
@@ -220,6 +224,7 @@ int fill_reg(Ctx& c, int fam, const Pt* pb, long N, const Pt* pa, long N0, const
     default: set_error("unknown kernel family %d", fam); return ST_BADARG;
     }
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 
@@ -234,8 +239,10 @@ int fill_reg_sym(Ctx& c, int fam, const Pt* pts, long N, const HypC& h, double n
     default: set_error("unknown kernel family %d", fam); return ST_BADARG;
     }
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     if (n_pad > N) {
         pad_identity_kernel<<<256, 256, 0, c.stream>>>(K, ld, N, n_pad);
+        count_launch();
         SGP_CUDA(cudaGetLastError());
     }
     return ST_OK;

@@ -154,6 +154,7 @@ int grad_contract(Ctx& c, int fam, int reg, const Pt* pts, long N, const HypC& h
     }
 #undef LAUNCH
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 

@@ -245,6 +245,7 @@ int map_prepare(Ctx& c, int fam, double per, const double* x, const double* y, l
     if (fam == FAM_SQ) map_prep_kernel<FAM_SQ><<<g, 256, 0, c.stream>>>(x, y, n, n_pad, per, u, v, yo);
     else map_prep_kernel<FAM_PRODUCT><<<g, 256, 0, c.stream>>>(x, y, n, n_pad, per, u, v, yo);
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 
@@ -253,6 +254,7 @@ int map_pad_copy(Ctx& c, const double* src, long n, double* dst)
     const long n_pad = map_pad(n);
     pad_copy_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, c.stream>>>(src, n, n_pad, dst);
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 
@@ -278,6 +280,7 @@ int map_launch(Ctx& c, int fam, int solver, const MapArgs& a)
     }
 #undef ML
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 

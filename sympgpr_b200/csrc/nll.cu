@@ -136,6 +136,7 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     if (job.d_L) {
         tril_out_kernel<<<1024, 256, 0, st>>>(K, n_pad, job.d_L, n);
         SGP_CUDA(cudaGetLastError());
+        count_launch();
     }
     SGP_TRY(potrs(c, K, n_pad, n_pad, Dinv, yv, wv, av));
     if (job.d_alpha) SGP_CUDA(cudaMemcpyAsync(job.d_alpha, av, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -149,11 +150,13 @@ int nll_enqueue(Ctx& c, const NllJob& job)
         if (job.d_kinv) {
             sym_out_kernel<<<1024, 256, 0, st>>>(W, n_pad, job.d_kinv, n);
             SGP_CUDA(cudaGetLastError());
+        count_launch();
         }
     }
     finalize_kernel<<<1, 256, 0, st>>>(job.d_z, av, n, logparts, nt, info, partial, job.ngrad > 0 ? npart : 0, job.hyp[2],
                                        job.ngrad, job.d_res);
     SGP_CUDA(cudaGetLastError());
+    count_launch();
     return ST_OK;
 }
 

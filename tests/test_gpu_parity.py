@@ -1,0 +1,373 @@
+"""GPU parity tests (pytest -m gpu): the CUDA path, called through the C ABI, against the oracle
+on the same inputs and against the committed golden fixtures.
+
+Tolerances are the ones BASELINE.json states: kernel entries 1e-12 (allclose-style, as
+python/05_tokamak/SympGPR/test_sympgpr.py:26-74), NLL and gradient 1e-9 relative, orbits 1e-8."""
+import os
+
+import numpy as np
+import pytest
+import scipy.linalg
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = os.path.join(HERE, "golden")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from sympgpr_b200 import _lib, api as a
+    if _lib.device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests need a B200 (the product has no CPU fallback)")
+    return a
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def C():
+    from oracle import c_oracle
+    return c_oracle
+
+
+# ------------------------------------------------------------------------------- dense blocks
+LAY = {"MN": 0, "K": 1}
+
+
+@pytest.mark.parametrize("al,bl,mode,Mt,Nt,K", [
+    (0, 0, 0, 1, 1, 16), (0, 0, 0, 2, 3, 128), (0, 0, 0, 3, 1, 384), (0, 0, 1, 3, 3, 256),
+    (0, 1, 0, 2, 2, 128), (0, 1, 3, 3, 2, 256), (0, 1, 4, 3, 2, 384), (0, 1, 4, 1, 1, 128),
+    (1, 1, 0, 2, 2, 64), (1, 1, 2, 3, 3, 384), (1, 1, 2, 1, 1, 128), (1, 0, 0, 2, 1, 48),
+    (0, 0, 0, 9, 5, 2048),
+])
+def test_dmma_gemm_matches_plain_fp64(api, al, bl, mode, Mt, Nt, K):
+    err = api.selftest_gemm(al, bl, mode, Mt, Nt, K)
+    assert err < 1e-11 * max(1, K / 64), err
+
+
+@pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 300, 640, 1500])
+def test_spd_factor_and_inverse(api, n):
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, n + 3))
+    A = B @ B.T / n + 0.5 * np.eye(n)
+    L, Ai, ld = api.spd_factor(A, want_factor=True, want_inverse=True)
+    Lr = scipy.linalg.cholesky(A, lower=True)
+    assert np.allclose(L, Lr, rtol=1e-11, atol=1e-12)
+    assert np.isclose(ld, np.sum(np.log(np.diag(Lr))), rtol=1e-12, atol=1e-12)
+    Air = np.linalg.inv(A)
+    assert np.allclose(Ai, Air, rtol=1e-9, atol=1e-10 * np.abs(Air).max())
+    assert np.allclose(Ai, Ai.T, rtol=0, atol=0)
+
+
+def test_not_positive_definite_raises_linalgerror(api):
+    A = np.eye(200)
+    A[150, 150] = -1.0
+    with pytest.raises(np.linalg.LinAlgError):
+        api.spd_factor(A)
+    # nll with a negative signal variance is not PD either; the reference's bare except relies on the raise
+    x = np.linspace(0, 3, 8)
+    with pytest.raises(np.linalg.LinAlgError):
+        api.nll_chol([1.0, 1.0, -1.0, 1e-10], x, np.ones(8), 8)
+
+
+# ------------------------------------------------------------------------------- fills
+LIT = dict(x=np.array([1.0, 2.0, 3.0]), y=np.array([0.0, 3.0, 2.0]), x0=np.array([1.0, 2.0]), y0=np.array([0.0, 3.0]),
+           hyp=np.array([0.5, 2.0, 0.4]), hypp=np.array([0.6, 1.9, 0.3]))
+
+
+@pytest.mark.parametrize("family", ["product", "sq"])
+def test_literal_inputs_of_test_sympgpr(api, family):
+    """python/05_tokamak/SympGPR/test_sympgpr.py:17-74 against the golden values."""
+    g = np.load(os.path.join(G, f"path_{family}.npz"))
+    x, y, x0, y0, hyp, hypp = (LIT[k] for k in ("x", "y", "x0", "y0", "hyp", "hypp"))
+    K = np.empty((3, 2), order="F")
+    api.buildkreg(x, y, x0, y0, hyp, K, family)
+    assert np.allclose(K, g["lit_buildkreg"], rtol=1e-12, atol=1e-12)
+    K = np.zeros((1, 2), order="F")
+    api.buildkreg(x[:1], y[:1], x0, y0, hyp, K, family)
+    assert np.allclose(K, g["lit_buildkreg_1"], rtol=1e-12, atol=1e-12)
+    K = np.empty((6, 4), order="F")
+    api.build_k(x, y, x0, y0, hyp, K, family)
+    assert np.allclose(K, g["lit_build_k"], rtol=1e-12, atol=1e-12)
+    # same through the func.py-level wrappers
+    K2 = np.empty((6, 4), order="F")
+    api.build_K(np.hstack((x, y)), np.hstack((x0, y0)), hyp, K2, family)
+    assert np.array_equal(K, K2)
+    Kyinvp = np.array([[0.9, -0.3], [0.3, 0.9]], order="F")
+    ztp = np.cos(x0 + y0)
+    assert np.allclose(api.guessp(x[0], y[0], hypp, x0, y0, ztp, Kyinvp, family), g["lit_guessp"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(api.guessP(x[0], y[0], hypp, np.hstack((x0, y0)), ztp, Kyinvp, family), g["lit_guessp"],
+                       rtol=1e-12, atol=1e-12)
+    Kyinv = np.reshape(np.arange(16), (4, 4), order="F")          # int64, as in the reference test
+    zt = np.hstack((np.cos(x0 + y0), np.sin(x0 + y0)))
+    assert np.allclose(api.calcq(x[0], y[0], x0, y0, hyp, Kyinv, zt, family), g["lit_calcq"], rtol=1e-12, atol=1e-12)
+    for solver in ("hybrd", "newton"):
+        p = api.calcp(x[0], y[0], hyp, hypp, x0, y0, ztp, Kyinvp, x0, y0, zt, Kyinv, family, solver=solver)
+        assert np.allclose(p, g["lit_calcp"], rtol=1e-12, atol=1e-12), (solver, p)
+    p = api.calcP(x[0], y[0], hyp, hypp, np.hstack((x0, y0)), ztp, Kyinvp, np.hstack((x0, y0)), zt, Kyinv, family)
+    assert np.allclose(p, g["lit_calcp"], rtol=1e-12, atol=1e-12)
+    if family == "product":
+        assert abs(p - 1.08172922) < 5e-9          # sympgpr.f90:106 "! pgss = 1.08172922d0"
+
+
+@pytest.mark.parametrize("family,per", [("product", 0.5), ("sq", 0.5), ("sum", 0.5), ("period", 0.8)])
+@pytest.mark.parametrize("N,N0", [(1, 1), (2, 7), (33, 65), (257, 130), (301, 299)])
+def test_fill_matches_oracle(api, O, family, per, N, N0):
+    rng = np.random.default_rng(N * 1000 + N0)
+    x, y = rng.uniform(0, 6.3, N), rng.uniform(-2, 2, N)
+    x0, y0 = rng.uniform(0, 6.3, N0), rng.uniform(-2, 2, N0)
+    hyp = np.array([0.7, 1.3, 2.5])
+    K = np.full((2 * N, 2 * N0), np.nan, order="F")
+    api.build_k(x, y, x0, y0, hyp, K, family, per)
+    Kr = O.build_k_vec(x, y, x0, y0, hyp, family, per)
+    assert np.allclose(K, Kr, rtol=1e-12, atol=1e-12 * hyp[2])
+    Kg = np.full((N, N0), np.nan, order="F")
+    api.buildkreg(x, y, x0, y0, hyp, Kg, family, per)
+    assert np.allclose(Kg, O.buildkreg_vec(x, y, x0, y0, hyp, family, per), rtol=1e-12, atol=1e-12)
+
+
+def test_fill_edge_cases(api, O):
+    x = np.array([0.3, 1.1]); y = np.array([0.2, -0.4]); hyp = np.array([0.8, 0.9, 2.0])
+    # odd dimensions: sympgpr.f90:21-22,37 -- last row/col untouched by the loop, then scaled
+    K = np.full((5, 4), 7.0, order="F")
+    api.build_k(x, y, x, y, hyp, K)
+    Kr = np.full((5, 4), 7.0, order="F")
+    O.build_k(x, y, x, y, hyp, Kr)
+    assert np.allclose(K, Kr, rtol=1e-12, atol=1e-12)
+    # C-ordered square matrix (python/functions/func.py:133,149 allocate it that way)
+    Kc = np.empty((4, 4))
+    api.build_k(x, y, x, y, hyp, Kc)
+    assert np.allclose(Kc, O.build_k_vec(x, y, x, y, hyp), rtol=1e-12, atol=1e-12)
+    # empty
+    api.build_k(np.zeros(0), np.zeros(0), np.zeros(0), np.zeros(0), hyp, np.zeros((0, 0), order="F"))
+    # int input arrays are converted like f2py intent(in)
+    Ki = np.empty((4, 4), order="F")
+    api.build_k(np.array([0, 1]), np.array([1, 2]), np.array([0, 1]), np.array([1, 2]), hyp, Ki)
+    assert np.allclose(Ki, O.build_k_vec([0.0, 1.0], [1.0, 2.0], [0.0, 1.0], [1.0, 2.0], hyp), rtol=1e-12, atol=1e-12)
+
+
+# ------------------------------------------------------------------------------- NLL / gradient
+@pytest.mark.parametrize("family", ["product", "sq"])
+def test_nll_and_gradient_match_reference_python_layer(api, family):
+    g = np.load(os.path.join(G, f"path_{family}.npz"))
+    N = int(g["N"][0])
+    xt, zt, xtp, ztp = g["xtrain"], g["ztrain"], g["xtrainp"], g["ztrainp"]
+    for k, h in enumerate(g["hyps"]):
+        assert np.isclose(api.nll_chol(h, xt, zt, 2 * N, family), g["nll_chol"][k], rtol=1e-9)
+        v, gr = api.nll_grad(h, xt, zt, 2 * N, family)
+        assert np.isclose(v, g["nll_grad_val"][k], rtol=1e-9)
+        assert np.allclose(gr, g["nll_grad_grad"][k], rtol=1e-6, atol=1e-6)     # reference = LU + full GEMM traces
+    for k, h in enumerate(g["hypps"]):
+        assert np.isclose(api.nll_chol_reg(h, xtp, ztp, N, family), g["nll_chol_reg"][k], rtol=1e-9)
+        v, gr = api.nll_grad_reg(h, xtp, ztp, N, family)
+        assert np.isclose(v, g["nll_grad_reg_val"][k], rtol=1e-9)
+        assert np.allclose(gr, g["nll_grad_reg_grad"][k], rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("family,per", [("product", 0.5), ("sq", 0.5), ("sum", 0.5), ("period", 0.7)])
+@pytest.mark.parametrize("N", [3, 64, 100, 200, 333])
+def test_nll_grad_matches_oracle(api, O, family, per, N):
+    """N = 200 is the size of BASELINE config 01_pendulum (n = 400)."""
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    if family == "sum":
+        hyp[3] = 1e-6
+    xt, zt = d["xtrain"], d["ztrain"]
+    v, gr = api.nll_grad(hyp, xt, zt, 2 * N, family, per, with_sig=True)
+    vr, grr = O.nll_grad(hyp, xt, zt, 2 * N, family, per, with_sig=True)
+    assert np.isclose(v, vr, rtol=1e-9), (v, vr)
+    assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr)
+    assert np.isclose(api.nll_chol(hyp, xt, zt, 2 * N, family, per), vr, rtol=1e-9)
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8)
+    v, gr = api.nll_grad_reg(hypp, d["xtrainp"], d["ztrainp"], N, family, per)
+    vr, grr = O.nll_grad_reg(hypp, d["xtrainp"], d["ztrainp"], N, family, per)
+    assert np.isclose(v, vr, rtol=1e-9)
+    assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max())
+
+
+def test_reference_third_gradient_component(api, O):
+    """python/05_tokamak/SympGPR/func.py:163-167 mixes dK[1] and dK[2] in its third entry; the
+    mirror reproduces it on request and otherwise returns the consistent derivative."""
+    N = 40
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    vr, gref = O.nll_grad3_reference(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    v, gq = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N, with_sig=True, reference_third_component=True)
+    assert np.isclose(v, vr, rtol=1e-9)
+    assert np.allclose(gq, gref, rtol=1e-7, atol=1e-7 * np.abs(gref).max())
+    # consistent d/dsig against a central difference of the oracle's NLL
+    _, gc = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N, with_sig=True)
+    e = 1e-4 * hyp[2]
+    hp_, hm_ = hyp.copy(), hyp.copy()
+    hp_[2] += e; hm_[2] -= e
+    fd = (O.nll_chol(hp_, d["xtrain"], d["ztrain"], 2 * N) - O.nll_chol(hm_, d["xtrain"], d["ztrain"], 2 * N)) / (2 * e)
+    assert np.isclose(gc[2], fd, rtol=1e-5)
+
+
+def test_fit_returns_alpha_inverse_and_factor(api, O):
+    N = 90
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    xt, zt = d["xtrain"], d["ztrain"]
+    f = api.fit(hyp, xt, zt, 2 * N, want_inverse=True, want_factor=True)
+    K = O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp[:3]) + hyp[3] * np.eye(2 * N)
+    Lr = scipy.linalg.cholesky(K, lower=True)
+    assert np.allclose(f["L"], Lr, rtol=1e-10, atol=1e-12)
+    ar = O.fit_alpha(hyp, xt, zt, 2 * N)
+    assert np.allclose(f["alpha"], ar, rtol=1e-9, atol=1e-9 * np.abs(ar).max())
+    Kir = scipy.linalg.inv(K)
+    assert np.allclose(f["Kyinv"], Kir, rtol=1e-8, atol=1e-9 * np.abs(Kir).max())
+    assert np.isclose(f["nll"], O.nll_chol(hyp, xt, zt, 2 * N), rtol=1e-9)
+    fr = api.fit(O.timing_hyp(N, d["sigp"]), d["xtrainp"], d["ztrainp"], N, reg=True)
+    arr = O.fit_alpha(O.timing_hyp(N, d["sigp"]), d["xtrainp"], d["ztrainp"], N, reg=True)
+    assert np.allclose(fr["alpha"], arr, rtol=1e-9, atol=1e-9 * np.abs(arr).max())
+
+
+def test_nll_grad_medium_size(api, O):
+    """n = 2048 (8 x 8 tiles... 16 tiles): exercises the recursive potrf/trsm/trtri and lauum."""
+    N = 1024
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    vr, grr = O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    assert np.isclose(v, vr, rtol=1e-9), (v, vr)
+    assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr)
+
+
+# ------------------------------------------------------------------------------- map
+def _model(O, N, family="product", lfac=2.0, kch=0.9):
+    d = O.standard_map_training(N, kch)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8)
+    hyp[:2] *= lfac
+    hypp[:2] *= lfac
+    xt, zt, xtp, ztp = d["xtrain"], d["ztrain"], d["xtrainp"], d["ztrainp"]
+    Kyinv = np.linalg.inv(O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp[:3], family) + hyp[3] * np.eye(2 * N))
+    Kyinvp = np.linalg.inv(O.buildkreg_vec(xtp[:N], xtp[N:], xtp[:N], xtp[N:], hypp[:3], family) + hypp[3] * np.eye(N))
+    return dict(N=N, hyp=hyp[:3].copy(), hypp=hypp[:3].copy(), xt=xt, zt=zt, xtp=xtp, ztp=ztp, Kyinv=Kyinv, Kyinvp=Kyinvp,
+                alpha=Kyinv @ zt, alphap=Kyinvp @ ztp)
+
+
+@pytest.mark.parametrize("kind,kname", [(0, "pendulum"), (1, "henon"), (2, "standard"), (3, "tokamak")])
+@pytest.mark.parametrize("solver", ["hybrd", "newton"])
+def test_applymap_matches_oracle(api, O, C, kind, kname, solver):
+    m = _model(O, 100)
+    N = m["N"]
+    E, nm = 37, 12
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 1.0 + O.halton(E, 7) * 4.0
+    if kind == 3:
+        p0 = p0 * 0.6          # some orbits fall below 0 / outside r < 0.5 and are lost
+    want_pd = kind == 2
+    ref = C.applymap_alpha(kind, nm, q0, p0, m["hyp"], m["hypp"], m["xtp"][:N], m["xtp"][N:], m["alphap"], m["xt"][:N],
+                           m["xt"][N:], m["alpha"], want_pdiff=want_pd)
+    fn = {0: api.applymap, 1: api.applymap_henon, 2: api.applymap_standard, 3: api.applymap_tok}[kind]
+    out = fn(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"], m["Kyinv"],
+             family="product", solver=solver, alphap=m["alphap"], alpha=m["alpha"], return_stats=True)
+    q, p = out[0], out[1]
+    qr, pr = ref[0], ref[1]
+    assert q.shape == (nm, E) and p.shape == (nm, E)
+    assert np.array_equal(np.isnan(p), np.isnan(pr)), "lost-orbit pattern differs"
+    assert np.array_equal(np.isnan(q), np.isnan(qr))
+    ok = ~np.isnan(pr)
+    # compare modulo the wrap (a value within 1e-9 of 0 / 2pi may land on either side)
+    dq = np.abs(q[ok] - qr[ok]);  dq = np.minimum(dq, np.abs(dq - 2 * np.pi)) if kind != 1 else dq
+    dp = np.abs(p[ok] - pr[ok]);  dp = np.minimum(dp, np.abs(dp - 2 * np.pi)) if kind == 2 else dp
+    assert dq.max() < 1e-8 and dp.max() < 1e-8, (dq.max(), dp.max())
+    if want_pd:
+        assert np.allclose(out[2], ref[2], rtol=1e-8, atol=1e-8)
+    st = out[-1]
+    assert st["evaluations"] > 0
+    if kind == 3:
+        assert np.isnan(pr).any() and not np.isnan(pr[:, :]).all()
+
+
+def test_applymap_first_step_matches_reference_python_layer(api):
+    """One map step against tests/golden/path_product.npz (reference calcQ / Pnewton root)."""
+    g = np.load(os.path.join(G, "path_product.npz"))
+    N = int(g["N"][0])
+    for solver in ("hybrd", "newton"):
+        q, p, pd = api.applymap_standard(g["map_q"].shape[0], g["map_q"].shape[1], g["hyps"][0, :3], g["hypps"][0, :3],
+                                         g["map_q"][0], g["map_p"][0], g["xtrainp"], g["ztrainp"], g["Kyinvp"], g["xtrain"],
+                                         g["ztrain"], g["Kyinv"], solver=solver)
+        assert np.allclose(q[1], g["map_q"][1], rtol=1e-9, atol=1e-9), solver
+        assert np.allclose(p[1], g["map_p"][1], rtol=1e-9, atol=1e-9), solver
+        assert np.allclose(q, g["map_q"], rtol=1e-6, atol=1e-6) and np.allclose(p, g["map_p"], rtol=1e-6, atol=1e-6)
+
+
+def test_applymap_tok_f2py_layout_and_strides(api, O, C):
+    m = _model(O, 64)
+    N = m["N"]
+    E, nm = 9, 5
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 1.0 + O.halton(E, 7) * 2.0
+    qmap = np.zeros((nm, E, 1), order="F")
+    pmap = np.zeros((nm, E, 1), order="F")
+    api.applymap_tok_f2py(m["hyp"], m["hypp"], q0, p0, m["xtp"][:N], m["xtp"][N:], m["ztp"], m["Kyinvp"], m["xt"][:N],
+                          m["xt"][N:], m["zt"], m["Kyinv"], qmap, pmap)
+    qr, pr, _ = C.applymap_alpha(3, nm, q0, p0, m["hyp"], m["hypp"], m["xtp"][:N], m["xtp"][N:], m["alphap"], m["xt"][:N],
+                                 m["xt"][N:], m["alpha"])
+    assert np.allclose(qmap[:, :, 0], qr, rtol=1e-8, atol=1e-8, equal_nan=True)
+    assert np.allclose(pmap[:, :, 0], pr, rtol=1e-8, atol=1e-8, equal_nan=True)
+    # strided history and final-only output
+    q2, p2, st = api.applymap(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"],
+                              m["Kyinv"], out_every=2, return_stats=True)
+    qf, pf = C.applymap_alpha(0, nm, q0, p0, m["hyp"], m["hypp"], m["xtp"][:N], m["xtp"][N:], m["alphap"], m["xt"][:N],
+                              m["xt"][N:], m["alpha"])[:2]
+    assert q2.shape == (3, E)
+    assert np.allclose(q2, qf[::2], rtol=1e-8, atol=1e-8) and np.allclose(p2, pf[::2], rtol=1e-8, atol=1e-8)
+    assert np.allclose(st["qfinal"], qf[-1], rtol=1e-8, atol=1e-8)
+
+
+def test_applymap_multi_chunk_training_set(api, O, C):
+    """Nt = 700 > 512: the training set is streamed through shared memory in two chunks."""
+    m = _model(O, 700, lfac=1.5)
+    N = m["N"]
+    E, nm = 130, 4          # 130 orbits: two thread blocks, second one partially filled
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 1.0 + O.halton(E, 7) * 4.0
+    qr, pr, nev = C.applymap_alpha(0, nm, q0, p0, m["hyp"], m["hypp"], m["xtp"][:N], m["xtp"][N:], m["alphap"], m["xt"][:N],
+                                   m["xt"][N:], m["alpha"])
+    for solver in ("hybrd", "newton"):
+        q, p = api.applymap(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"],
+                            m["Kyinv"], solver=solver, alphap=m["alphap"], alpha=m["alpha"])
+        dq = np.abs(q - qr); dq = np.minimum(dq, np.abs(dq - 2 * np.pi))
+        assert dq.max() < 1e-8 and np.abs(p - pr).max() < 1e-8, (solver, dq.max(), np.abs(p - pr).max())
+
+
+def test_thousand_steps_on_regular_orbits(api, O, C):
+    """BASELINE tolerance: 1e-8 after 1000 map steps, on orbits the oracle itself finds regular
+    (trajectories from p0 and p0 + 1e-12 stay within 1e-9)."""
+    m = _model(O, 200, lfac=2.0, kch=0.3)
+    N = m["N"]
+    E, nm = 12, 1001
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 1.5 + O.halton(E, 7) * 3.0
+    args = (m["hyp"], m["hypp"], m["xtp"][:N], m["xtp"][N:], m["alphap"], m["xt"][:N], m["xt"][N:], m["alpha"])
+    qa, pa, _ = C.applymap_alpha(0, nm, q0, p0, *args)
+    qb, pb, _ = C.applymap_alpha(0, nm, q0, p0 + 1e-12, *args)
+    dd = np.abs(qa[-1] - qb[-1]); dd = np.minimum(dd, np.abs(dd - 2 * np.pi))
+    regular = (dd < 1e-9) & (np.abs(pa[-1] - pb[-1]) < 1e-9)
+    assert regular.sum() >= 4, regular.sum()
+    for solver in ("hybrd", "newton"):
+        q, p, st = api.applymap(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"],
+                                m["Kyinv"], solver=solver, alphap=m["alphap"], alpha=m["alpha"], out_every=1000,
+                                return_stats=True)
+        dq = np.abs(q[-1] - qa[-1]); dq = np.minimum(dq, np.abs(dq - 2 * np.pi))
+        dp = np.abs(p[-1] - pa[-1])
+        assert dq[regular].max() < 1e-8 and dp[regular].max() < 1e-8, (solver, dq[regular].max(), dp[regular].max())
+
+
+def test_nan_and_empty_inputs(api, O):
+    m = _model(O, 32)
+    q0 = np.array([1.0, np.nan, 2.0]); p0 = np.array([2.0, 2.0, np.nan])
+    q, p = api.applymap(3, 3, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"], m["Kyinv"])
+    assert np.isfinite(q[:, 0]).all() and np.isnan(q[1:, 1]).all() and np.isnan(p[1:, 2]).all()
+    q, p = api.applymap(3, 0, m["hyp"], m["hypp"], np.zeros(0), np.zeros(0), m["xtp"], m["ztp"], m["Kyinvp"], m["xt"],
+                        m["zt"], m["Kyinv"])
+    assert q.shape == (3, 0)

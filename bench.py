@@ -1,0 +1,383 @@
+#!/usr/bin/env python3
+"""Benchmark of the SympGPR hot path on B200 (driver contract: one JSON line on stdout).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    torchrun --nproc-per-node N bench.py --gpus N ...        (one rank per GPU, NCCL)
+
+Headline metric (BASELINE.json): NLL+gradient evaluations per second at N = 16 384 training
+pairs (n = 32 768, fp64), synthetic standard map K = 0.9, product kernel.  One "step" = one
+NLL+gradient evaluation: fill -> potrf -> potrs -> trtri -> lauum -> gradient contraction.
+With N > 1 GPUs every rank evaluates its own multi-start restart (a different theta; the
+training Cholesky does not shard -- DESIGN.md "Multi-GPU") and its own slice of the orbit
+ensemble; NCCL only gathers the results ("scaling": "weak").
+
+Also reported on the same line: the map leg (orbit map-steps/s, BASELINE's second metric), the
+Hessian-block fill against the HBM roofline, the in-run cuBLAS DGEMM FP64 peak, and the CPU
+baseline (oracle = port of the reference maths, SciPy LAPACK on the host cores).
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "nll_grad_evals_per_s"
+UNIT = "evals/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n-train", type=int, default=16384, help="training pairs N (matrix order 2N)")
+    ap.add_argument("--map-train", type=int, default=4096, help="training pairs of the map leg (config 04_standard_map)")
+    ap.add_argument("--orbits", type=int, default=100000, help="orbits per GPU in the map leg")
+    ap.add_argument("--map-steps", type=int, default=20, help="map steps per launch in the map leg")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="training pairs of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-map", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------ reference arm
+def cpu_nll_grad_sample(N_s, N_full, steps, warmup):
+    """The reference maths on the host cores (oracle port; SciPy/OpenBLAS LAPACK with all threads):
+    one NLL+gradient evaluation at N_s pairs, scaled by (n_s/n)^3 to the full size (the evaluation
+    is n^3 LAPACK work: potrf + potri; the O(n^2) fill/contraction parts only make the scaled
+    figure flatter the CPU)."""
+    from oracle import oracle as O
+    d = O.standard_map_training(N_s)
+    hyp = O.timing_hyp(N_s, d["sig"], 1e-8)
+    for _ in range(warmup):
+        O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N_s)
+    ts = []
+    for _ in range(steps):
+        t = time.perf_counter()
+        O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N_s)
+        ts.append(time.perf_counter() - t)
+    t_s = float(np.mean(ts))
+    scale = (N_full / N_s) ** 3
+    return 1.0 / (t_s * scale), t_s
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([p.get("num_threads", 1) for p in threadpool_info()] + [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, a.steps), max(1, min(a.warmup, 1))
+    v, t_s = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
+    cores = blas_threads()
+    sample = (f"oracle nll_grad (C/NumPy fill, SciPy potrf+potri, elementwise contraction) at N={a.cpu_sample} "
+              f"(n={2 * a.cpu_sample}): {t_s:.3f} s/eval, scaled by (n/n_s)^3 to N={a.n_train}")
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(a),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a):
+    return {"workload": f"synthetic standard map K=0.9, N={a.n_train} training pairs (n={2 * a.n_train} fp64 Hessian-block "
+                        f"kernel, periodic x SE), NLL+gradient; map leg: N={a.map_train}, {a.orbits} orbits/GPU x "
+                        f"{a.map_steps} steps", "n_train": a.n_train, "matrix_order": 2 * a.n_train,
+            "hyp": "lx=ly=0.5*2pi/sqrt(N), sig2n=1e-8", "parallelism": f"restarts+ensemble x{a.gpus}",
+            "l2": "inputs larger than L2 (8.6 GB matrix vs 126 MB)"}
+
+
+# ------------------------------------------------------------------------------------------ b200 arm
+def main():
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from sympgpr_b200 import _lib, api, workloads as W
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available() or _lib.device_count() < 1:
+        raise RuntimeError("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    ctx = _lib.context(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    N = a.n_train
+    n = 2 * N
+    d = W.standard_map_training(N)
+    # multi-start restart of this rank: a different length-scale pair per GPU
+    hyp = W.timing_hyp(N, d["sig"], 1e-8)
+    hyp[:2] *= (1.0 + 0.02 * rank)
+    hyp_c = (ctypes.c_double * 4)(*hyp)
+    x_h = torch.from_numpy(d["xtrain"].copy()).pin_memory()
+    z_h = torch.from_numpy(d["ztrain"].copy()).pin_memory()
+    x_d = x_h.to(dev)
+    z_d = z_h.to(dev)
+    res_d = torch.zeros(16, dtype=torch.float64, device=dev)
+
+    def step_dev():
+        _lib.check(L.sgp_nll_dev(ctx.handle, 0, 0.5, 0, hyp_c, x_d.data_ptr(), z_d.data_ptr(), n, 2, res_d.data_ptr()),
+                   "sgp_nll_dev")
+
+    # ---- FP64 tensor peak of this GPU, measured in-run: cuBLAS DGEMM 8192^3 -----------------
+    A = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    B = torch.randn(8192, 8192, dtype=torch.float64, device=dev)
+    torch.matmul(A, B)
+    best = 1e9
+    for _ in range(4):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); torch.matmul(A, B); e1.record(); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1) * 1e-3)
+    dgemm_tflops = 2 * 8192 ** 3 / best / 1e12
+    del A, B
+    torch.cuda.empty_cache()
+
+    sampler = ClockSampler(local)
+    sampler.start()
+
+    # ---- device-resident NLL+grad: W warm-up, K timed steps ---------------------------------
+    for _ in range(max(a.warmup, 1)):
+        step_dev()
+    sync_all()
+    launches0 = L.sgp_launch_count()
+    t_wall0 = time.time()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(a.steps):
+        step_dev()
+    e1.record()
+    sync_all()
+    t_wall1 = time.time()
+    launches = int(L.sgp_launch_count() - launches0)
+    t_dev = max_over_ranks(e0.elapsed_time(e1) * 1e-3)
+    res = res_d.cpu().numpy()
+    if res[4] != 0:
+        raise RuntimeError(f"Cholesky failed in the timed region (info={res[4]})")
+    value = world * a.steps / t_dev
+    ms_per_step = 1e3 * t_dev / a.steps
+
+    # ---- end to end through the public API with host buffers --------------------------------
+    xh_np, zh_np = x_h.numpy(), z_h.numpy()
+    api.nll_grad(hyp, xh_np, zh_np, n)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        v_e2e, g_e2e = api.nll_grad(hyp, xh_np, zh_np, n)
+    torch.cuda.synchronize()
+    t_e2e = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * a.steps / t_e2e
+    h2d = int(x_h.numel() * 8 + z_h.numel() * 8)
+    d2h = 16 * 8
+
+    # ---- Hessian-block fill against the HBM roofline (full 2N x 2N matrix, 8 n^2 bytes) ------
+    Kbuf = torch.empty(n * n, dtype=torch.float64, device=dev)
+    hyp3 = (ctypes.c_double * 3)(*hyp[:3])
+    xq, yP = x_d[:N], x_d[N:]
+
+    def fill_full():
+        _lib.check(L.sgp_build_k_dev(ctx.handle, 0, 0.5, xq.data_ptr(), yP.data_ptr(), N, xq.data_ptr(), yP.data_ptr(), N,
+                                     hyp3, Kbuf.data_ptr(), n), "sgp_build_k_dev")
+    for _ in range(3):
+        fill_full()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(5):
+        fill_full()
+    f1.record(); f1.synchronize()
+    t_fill = f0.elapsed_time(f1) * 1e-3 / 5
+    fill_gbs = 8.0 * n * n / t_fill / 1e9
+    del Kbuf
+    ctx.release_workspace()
+    torch.cuda.empty_cache()
+
+    # ---- map leg: ensemble sharded over the GPUs, model replicated -----------------------------
+    map_info = None
+    if not a.no_map:
+        Nt = a.map_train
+        dm = W.standard_map_training(Nt)
+        hm = W.timing_hyp(Nt, dm["sig"], 1e-8, factor=1.0)
+        hpm = W.timing_hyp(Nt, dm["sigp"], 1e-8, factor=1.0)
+        fm = api.fit(hm, dm["xtrain"], dm["ztrain"], 2 * Nt)
+        fpm = api.fit(hpm, dm["xtrainp"], dm["ztrainp"], Nt, reg=True)
+        E = a.orbits
+        q0_all, p0_all = W.ensemble(E * world)
+        q0 = torch.from_numpy(q0_all[rank::world].copy()).to(dev)      # interleaved shards (load balance)
+        p0 = torch.from_numpy(p0_all[rank::world].copy()).to(dev)
+        qf, pf = torch.empty_like(q0), torch.empty_like(p0)
+        stats = torch.zeros(2, dtype=torch.int64, device=dev)
+        model = ctypes.c_void_p()
+        dp = _lib.dptr
+        xtp, xt = dm["xtrainp"], dm["xtrain"]
+        _lib.check(L.sgp_model_create(ctx.handle, 0, 0.5, dp(np.ascontiguousarray(hm[:3])), dp(np.ascontiguousarray(hpm[:3])),
+                                      dp(np.ascontiguousarray(xtp[:Nt])), dp(np.ascontiguousarray(xtp[Nt:])), dp(fpm["alpha"]),
+                                      Nt, dp(np.ascontiguousarray(xt[:Nt])), dp(np.ascontiguousarray(xt[Nt:])), dp(fm["alpha"]),
+                                      Nt, ctypes.byref(model)), "sgp_model_create")
+
+        def map_run(solver):
+            _lib.check(L.sgp_model_applymap_dev(ctx.handle, model, 2, solver, a.map_steps, E, q0.data_ptr(), p0.data_ptr(),
+                                                qf.data_ptr(), pf.data_ptr(), None, None, 0, stats.data_ptr()),
+                       "sgp_model_applymap_dev")
+        map_run(1)
+        sync_all()
+        stats.zero_()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        m0.record(); map_run(1); m1.record()
+        sync_all()
+        t_map = max_over_ranks(m0.elapsed_time(m1) * 1e-3)
+        st = stats.clone()
+        cks = torch.stack([qf.sum(), pf.sum()])
+        if world > 1:                                   # the only collectives of the path: gather statistics
+            dist.all_reduce(st, op=dist.ReduceOp.SUM)
+            dist.all_reduce(cks, op=dist.ReduceOp.SUM)
+        evals = int(st[0].item())
+        orbit_steps = float(E) * world * a.map_steps
+        # same launch with the reference's own solver (MINPACK hybrd1) for comparison
+        stats.zero_()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record(); map_run(0); h1.record()
+        sync_all()
+        t_map_h = max_over_ranks(h0.elapsed_time(h1) * 1e-3)
+        pair_evals = (Nt + evals / orbit_steps * Nt)      # per orbit-step: guess sweep + solver/dq sweeps
+        map_info = {"metric": "orbit_map_steps_per_s", "value": orbit_steps / t_map, "unit": "orbit-steps/s",
+                    "solver": "newton", "n_train": Nt, "orbits_total": E * world, "steps": a.map_steps,
+                    "sweeps_per_orbit_step": 1 + evals / orbit_steps,
+                    "pair_evals_per_s": orbit_steps * pair_evals / t_map,
+                    "hybrd_value": orbit_steps / t_map_h, "unconverged": int(st[1].item()),
+                    "checksum": [float(cks[0].item()), float(cks[1].item())]}
+        L.sgp_model_destroy(model)
+
+    sampler.stop()
+    clocks = sampler.summary(t_wall0, t_wall1)
+
+    # ---- CPU baseline (rank 0, single GPU runs only) --------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+        v_cpu, t_s = cpu_nll_grad_sample(a.cpu_sample, N, 2, 1)
+        cpu = {"value": v_cpu, "unit": UNIT, "cores": blas_threads(), "kind": "port",
+               "sample": f"oracle nll_grad at N={a.cpu_sample} (n={2 * a.cpu_sample}): {t_s:.3f} s/eval on the host cores, "
+                         f"scaled by (n/n_s)^3 to N={N}"}
+
+    if rank == 0:
+        flops = float(n) ** 3                                    # potrf n^3/3 + trtri n^3/3 + lauum n^3/3
+        achieved = flops / (t_dev / a.steps) / 1e12
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": workload_config(a),
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "clocks": clocks,
+                "roofline": {"kernel": "gemm_f64_kernel (DMMA m8n8k4 structured GEMM: potrf/trtri/lauum updates)",
+                             "bound": "tensor", "achieved": achieved, "peak": dgemm_tflops, "unit": "TFLOP/s",
+                             "frac": achieved / dgemm_tflops, "traffic": None,
+                             "note": "achieved = n^3 algorithmic flops of one NLL+grad evaluation / step time (the GEMM "
+                                     "kernel is >90% of the step); peak = cuBLAS DGEMM 8192^3 measured in this run "
+                                     "(MEASURED_PEAKS.json has no fp64 entry)"},
+                "roofline_fill": {"kernel": "fill_hess_kernel", "bound": "hbm", "achieved": fill_gbs,
+                                  "peak": read_hbm_peak(), "unit": "GB/s", "frac": fill_gbs / read_hbm_peak(),
+                                  "bytes": 8.0 * n * n, "ms": t_fill * 1e3},
+                "result": {"nll": float(res[0]), "grad": [float(res[1]), float(res[2])]},
+                }
+        if map_info:
+            line["map"] = map_info
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def read_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"])
+    except Exception:
+        return 6650.0          # fallback stated in B200_PROFILING.md
+
+
+if __name__ == "__main__":
+    main()

@@ -109,22 +109,31 @@ def compute_r(pth, th, rstart=0.3):
 
 
 def applymap_alpha(kind, nm, q0, p0, hyp, hypp, xtp, ytp, alphap, xt, yt, alpha, family="product", p=0.5,
-                   want_pdiff=False):
-    """Returns qmap, pmap (nm, E) [, pdiff], mean function evaluations per orbit-step."""
+                   want_pdiff=False, want_notconv=False):
+    """Returns qmap, pmap (nm, E) [, pdiff], mean function evaluations per orbit-step
+    [, per-orbit count of steps where hybrd1 returned info != 1, per-orbit largest
+    residual |f(P)| of an accepted root]."""
     q0, p0, hyp, hypp, xtp, ytp, alphap, xt, yt, alpha = map(
         _d, (q0, p0, hyp, hypp, xtp, ytp, alphap, xt, yt, alpha))
     E = len(q0)
     qmap = np.zeros((nm, E)); pmap = np.zeros((nm, E))
     pdiff = np.zeros((nm, E)) if want_pdiff else None
+    notconv = np.zeros(max(E, 1), dtype=np.int32)
+    maxres = np.zeros(max(E, 1))
     fev = lib().oracle_applymap_alpha(
         kind, _fam(family), ctypes.c_double(p), ctypes.c_long(nm), ctypes.c_long(E), _p(q0), _p(p0),
         _p(hyp), _p(hypp), _p(xtp), _p(ytp), _p(alphap), ctypes.c_long(len(xtp)),
         _p(xt), _p(yt), _p(alpha), ctypes.c_long(len(xt)), _p(qmap), _p(pmap),
-        _p(pdiff) if want_pdiff else None)
+        _p(pdiff) if want_pdiff else None, notconv.ctypes.data_as(c_ip), _p(maxres))
     nev = fev / max(1, E * (nm - 1))
+    out = [qmap, pmap]
     if want_pdiff:
-        return qmap, pmap, pdiff, nev
-    return qmap, pmap, nev
+        out.append(pdiff)
+    out.append(nev)
+    if want_notconv:
+        out.append(notconv[:E])
+        out.append(maxres[:E])
+    return tuple(out)
 
 
 def num_threads():

@@ -417,12 +417,14 @@ static double np_mod(double a, double b)
  *   MAP_STANDARD python/04_standard_map/func.py:218-254 (also fills pdiff if non-NULL)
  *   MAP_TOKAMAK  python/05_tokamak/SympGPR/func.py:182-211
  * qmap/pmap are (nm, E) C-order (row = step).  Returns total function
- * evaluations of the root solver (for the n_eval statistic). */
+ * evaluations of the root solver (for the n_eval statistic).  notconv (optional, E ints) counts per
+ * orbit the steps where hybrd1 returned info != 1 (the reference ignores info, sympgpr.f90:107);
+ * maxres (optional, E doubles) the largest residual |f(P)| any accepted root of the orbit left. */
 long oracle_applymap_alpha(int kind, int fam, double pper, long nm, long E, const double *q0, const double *p0,
                            const double *hyp, const double *hypp,
                            const double *xtp, const double *ytp, const double *alphap, long np,
                            const double *xt, const double *yt, const double *alpha, long nt,
-                           double *qmap, double *pmap, double *pdiff)
+                           double *qmap, double *pmap, double *pdiff, int *notconv, double *maxres)
 {
     const double two_pi = 2.0 * M_PI;
     model_t m = { fam, pper, hyp, hypp, np, nt, xtp, ytp, alphap, xt, yt, alpha };
@@ -431,6 +433,8 @@ long oracle_applymap_alpha(int kind, int fam, double pper, long nm, long E, cons
         pmap[k] = p0[k];
         qmap[k] = q0[k];
         if (pdiff) pdiff[k] = p0[k];
+        if (notconv) notconv[k] = 0;
+        if (maxres) maxres[k] = 0.0;
     }
 #pragma omp parallel for schedule(dynamic, 1) reduction(+ : total_fev)
     for (long k = 0; k < E; k++) {
@@ -444,6 +448,12 @@ long oracle_applymap_alpha(int kind, int fam, double pper, long nm, long E, cons
             }
             P = calcp_m(&m, q, p, &info, &nfev);
             total_fev += nfev + 1;
+            if (notconv && info != 1) notconv[k] += 1;   /* steps on which hybrd1 did not report convergence */
+            if (maxres) {                                 /* how good the accepted root really is */
+                target_ctx tc = { &m, q, p };
+                double rr = fabs(target_f(&tc, P));
+                if (!(rr <= maxres[k])) maxres[k] = rr;
+            }
             Pst = P;
             if (kind == MAP_STANDARD) {
                 if (pdiff) pdiff[(i + 1) * E + k] = pdiff[i * E + k] + (P - p);

@@ -12,6 +12,7 @@
 #include "chol.cuh"
 
 #include <limits.h>
+#include <stdlib.h>
 
 namespace sgp {
 
@@ -244,10 +245,78 @@ static int potrf_rec(Ctx& c, double* A, long lda, double* Dinv, double* logparts
     return potrf_rec(c, A, lda, Dinv, logparts, info, j0 + m1, m2);
 }
 
+static int env_int(const char* name, int dflt, int lo, int hi)
+{
+    const char* v = getenv(name);
+    if (!v || !*v) return dflt;
+    int x = atoi(v);
+    if (x < lo) x = lo;
+    if (x > hi) x = hi;
+    return x;
+}
+
+// Right-looking blocked factorisation: panels of NB = nb_tiles*128 columns.  The diagonal block is
+// factored recursively (small, latency-bound launches), the panel below it is one recursive TRSM over
+// all remaining rows and the trailing update one lower-triangular SYRK launch with K = NB, so almost
+// all flops run in launches that fill the 148 SMs.
 int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info)
 {
     if (n_pad % TILE || lda % 2) { set_error("potrf: n_pad %ld / lda %ld not tile aligned", n_pad, lda); return ST_BADARG; }
-    return potrf_rec(c, A, lda, Dinv, logparts, info, 0, (int)(n_pad / TILE));
+    const int nt = (int)(n_pad / TILE);
+    const int nb = env_int("SGP_POTRF_NB", 4, 1, 64);
+    const int lookahead = env_int("SGP_LOOKAHEAD", 1, 0, 1) && c.side != nullptr && nt > 2 * nb;
+    cudaStream_t s0 = c.stream, s1 = c.side;
+
+    auto panel = [&](int k0, int kb) -> int {            // diagonal block + everything below it
+        SGP_TRY(potrf_rec(c, A, lda, Dinv, logparts, info, k0, kb));
+        return trsm_rec(c, A, lda, Dinv, k0, kb, k0 + kb, nt - (k0 + kb));
+    };
+
+    if (!lookahead) {
+        for (int k0 = 0; k0 < nt; k0 += nb) {
+            const int kb = (nt - k0 < nb) ? (nt - k0) : nb;
+            SGP_TRY(panel(k0, kb));
+            const int rt = nt - (k0 + kb);
+            if (rt > 0) {
+                double* B = AT(A, lda, k0 + kb, k0);
+                SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, B, lda, AT(A, lda, k0 + kb, k0 + kb), lda, rt, rt,
+                             (long)kb * TILE, -1.0, 1.0, TM_LOWER));
+            }
+        }
+        return ST_OK;
+    }
+
+    // Look-ahead of depth one: after panel k, first update only the next block column, then factor
+    // panel k+1 on the high-priority side stream while the main stream applies panel k to the rest
+    // of the trailing matrix.  The two touch disjoint block columns.
+    SGP_TRY(panel(0, nb < nt ? nb : nt));
+    for (int k0 = 0; k0 < nt; k0 += nb) {
+        const int kb = (nt - k0 < nb) ? (nt - k0) : nb;
+        const int n0 = k0 + kb;                          // first tile of the next panel
+        const int rt = nt - n0;
+        if (rt <= 0) break;
+        const int kn = (rt < nb) ? rt : nb;              // width of the next panel
+        double* B = AT(A, lda, n0, k0);
+        // (a) next block column: rows n0.., cols n0..n0+kn
+        SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, B, lda, AT(A, lda, n0, n0), lda, rt, kn, (long)kb * TILE, -1.0, 1.0,
+                     TM_FULL));
+        SGP_CUDA(cudaEventRecord(c.ev[0], s0));
+        SGP_CUDA(cudaStreamWaitEvent(s1, c.ev[0], 0));
+        c.stream = s1;
+        int st = panel(n0, kn);
+        c.stream = s0;
+        SGP_TRY(st);
+        SGP_CUDA(cudaEventRecord(c.ev[1], s1));
+        // (b) rest of the trailing matrix: rows/cols from n0+kn
+        const int r2 = rt - kn;
+        if (r2 > 0) {
+            double* B2 = AT(A, lda, n0 + kn, k0);
+            SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B2, lda, B2, lda, AT(A, lda, n0 + kn, n0 + kn), lda, r2, r2, (long)kb * TILE,
+                         -1.0, 1.0, TM_LOWER));
+        }
+        SGP_CUDA(cudaStreamWaitEvent(s0, c.ev[1], 0));
+    }
+    return ST_OK;
 }
 
 int potrs(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w, double* alpha)
@@ -286,16 +355,36 @@ static int trtri_rec(Ctx& c, double* A, long lda, const double* Dinv, double* T,
     return ST_OK;
 }
 
+// Blocked lower-triangular inverse, last block column first (LAPACK dtrtri order):
+//   X_jj = inv(L_jj) (recursive);  T = X[j+1:, j+1:] * L[j+1:, j];  X[j+1:, j] = -T * X_jj
 int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T)
 {
-    return trtri_rec(c, A, lda, Dinv, T, 0, (int)(n_pad / TILE));
+    const int nt = (int)(n_pad / TILE);
+    const int nb = env_int("SGP_TRTRI_NB", 4, 1, 64);
+    int j0 = ((nt - 1) / nb) * nb;
+    for (; j0 >= 0; j0 -= nb) {
+        const int jb = (nt - j0 < nb) ? (nt - j0) : nb;
+        SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, jb));          // needs jb/2 x jb/2 tiles of T
+        const int rt = nt - (j0 + jb);
+        if (rt > 0) {
+            double* T2 = T + (size_t)(nb * TILE / 2 + TILE) * (size_t)(nb * TILE / 2 + TILE);   // past trtri_rec's scratch
+            const long ldt = (long)rt * TILE;
+            // T2 = X22 * L21          (X22 lower: k < (tm+1)*128)
+            SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + jb, j0 + jb), lda, AT(A, lda, j0 + jb, j0), lda, T2, ldt, rt, jb,
+                         (long)rt * TILE, 1.0, 0.0, TM_A_LOWER));
+            // L21 = -T2 * X_jj        (X_jj lower: k >= tn*128)
+            SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, T2, ldt, AT(A, lda, j0, j0), lda, AT(A, lda, j0 + jb, j0), lda, rt, jb,
+                         (long)jb * TILE, -1.0, 0.0, TM_B_LOWER));
+        }
+    }
+    return ST_OK;
 }
 
 size_t trtri_workspace_doubles(long n_pad)
 {
-    const long mt = n_pad / TILE;
-    const long m1 = mt / 2, m2 = mt - m1;
-    return (size_t)(m1 * TILE) * (size_t)(m2 * TILE);
+    const size_t nb = 64;                                        // upper bound of SGP_TRTRI_NB
+    const size_t rec = (nb * TILE / 2 + TILE) * (nb * TILE / 2 + TILE);
+    return rec + (size_t)n_pad * (nb * TILE);
 }
 
 int lauum(Ctx& c, const double* X, long n_pad, long lda, double* W, long ldw)

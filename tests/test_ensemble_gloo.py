@@ -1,0 +1,80 @@
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: sharding an orbit ensemble / a list
+of restarts over ranks and gathering the results.  The per-rank compute is a deterministic NumPy
+stand-in here (the CUDA kernels need a GPU); the GPU-side use is bench.py --gpus N."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_map(q0, p0, nm=4):
+    """stand-in for api.applymap: a standard-map history (nm, E_local)"""
+    q, p = np.zeros((nm, len(q0))), np.zeros((nm, len(q0)))
+    q[0], p[0] = q0, p0
+    for i in range(nm - 1):
+        p[i + 1] = p[i] + 0.9 * np.sin(q[i])
+        q[i + 1] = np.mod(q[i] + p[i + 1], 2 * np.pi)
+    return q, p
+
+
+def _worker(rank, world, port, E, T, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sympgpr_b200 import ensemble as ens
+    rng = np.random.default_rng(0)
+    q0, p0 = rng.uniform(0, 6.28, E), rng.uniform(0, 6.28, E)
+    q, p = ens.applymap_sharded("standard", 4, q0, p0, _fake_map)
+    qr, pr = _fake_map(q0, p0)
+    ok1 = np.array_equal(q, qr) and np.array_equal(p, pr)
+    idx = ens.shard_indices(E, rank, world)
+    ok2 = len(idx) in (E // world, E // world + 1) and (len(idx) == 0 or idx[0] == rank)
+    thetas = [np.array([0.1 * (i + 1), 0.2 * (i + 1)]) for i in range(T)]
+    calls = []
+
+    def evaluate(th):
+        calls.append(th)
+        return float(np.sum(th**2)), 2 * th
+    v, g = ens.restarts_sharded(thetas, evaluate)
+    ok3 = np.allclose(v, [np.sum(t**2) for t in thetas]) and np.allclose(g, [2 * t for t in thetas])
+    ok4 = len(calls) == len(range(rank, T, world))
+    out[rank] = int(ok1 and ok2 and ok3 and ok4)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("E,T", [(11, 5), (8, 2), (1, 1)])
+def test_sharded_ensemble_and_restarts_world2(E, T):
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, E, T, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(out) == [1] * world
+
+
+def test_single_process_paths():
+    from sympgpr_b200 import ensemble as ens
+    q0, p0 = np.linspace(0, 6, 7), np.linspace(1, 2, 7)
+    q, p = ens.applymap_sharded("standard", 4, q0, p0, _fake_map)
+    qr, pr = _fake_map(q0, p0)
+    assert np.array_equal(q, qr) and np.array_equal(p, pr)
+    v, g = ens.restarts_sharded([np.array([1.0, 2.0])], lambda t: (t.sum(), t))
+    assert v.shape == (1,) and g.shape == (1, 2)

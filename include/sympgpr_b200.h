@@ -72,6 +72,11 @@ int sgp_destroy(sgp_ctx* ctx);
 int sgp_set_stream(sgp_ctx* ctx, void* cuda_stream);  /* borrow a cudaStream_t (NULL: own)   */
 int sgp_synchronize(sgp_ctx* ctx);
 int sgp_release_workspace(sgp_ctx* ctx);          /* free cached device buffers              */
+/* Stage timers (bench.py): with profiling on, every NLL evaluation records CUDA events on the
+ * context's stream between its stages; sgp_stage_times waits for the last evaluation and returns
+ * the 7 durations in ms: fill, potrf, potrs, trtri, lauum, gradient contraction, finalize. */
+int sgp_set_profiling(sgp_ctx* ctx, int on);
+int sgp_stage_times(sgp_ctx* ctx, double* ms7);
 
 /* ---- kernels / kernels_sq / kernels_sum modules: the 19 scalar functions ------------------
  * replaces REAL*8 function <name>_num(x_a, y_a, x_b, y_b, lx, ly[, p]), kernels.f90:1-231.

@@ -42,6 +42,8 @@ _PROTOS = {
     "sgp_set_stream": (c_i, [c_vp, c_vp]),
     "sgp_synchronize": (c_i, [c_vp]),
     "sgp_release_workspace": (c_i, [c_vp]),
+    "sgp_set_profiling": (c_i, [c_vp, c_i]),
+    "sgp_stage_times": (c_i, [c_vp, c_dp]),
     "sgp_kernel_scalar": (c_d, [c_i, c_i, c_d, c_d, c_d, c_d, c_d, c_d, c_d]),
     "sgp_build_k": (c_i, [c_vp, c_i, c_d, c_dp, c_dp, c_l, c_dp, c_dp, c_l, c_dp, c_dp, c_l]),
     "sgp_buildkreg": (c_i, [c_vp, c_i, c_d, c_dp, c_dp, c_l, c_dp, c_dp, c_l, c_dp, c_dp, c_l]),

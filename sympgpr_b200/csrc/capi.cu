@@ -187,6 +187,7 @@ int sgp_destroy(sgp_ctx* ctx)
     if (c.own_stream && c.stream) cudaStreamDestroy(c.stream);
     if (c.side) cudaStreamDestroy(c.side);
     for (int i = 0; i < 4; i++) if (c.ev[i]) cudaEventDestroy(c.ev[i]);
+    for (int i = 0; i < NSTAGE_EV; i++) if (c.pev[i]) cudaEventDestroy(c.pev[i]);
     if (c.h_res) cudaFreeHost(c.h_res);
     delete ctx;
     return ST_OK;
@@ -214,6 +215,32 @@ int sgp_synchronize(sgp_ctx* ctx)
 {
     SGP_TRY(check_ctx(ctx));
     return sync(ctx->c);
+}
+
+int sgp_set_profiling(sgp_ctx* ctx, int on)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (on && !c.pev[0]) {
+        for (int i = 0; i < NSTAGE_EV; i++) SGP_CUDA(cudaEventCreate(&c.pev[i]));
+    }
+    c.prof = on != 0;
+    c.pev_valid = false;
+    return ST_OK;
+}
+
+int sgp_stage_times(sgp_ctx* ctx, double* ms7)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (!ms7 || !c.prof || !c.pev_valid) { set_error("stage_times: profiling is off or no evaluation was recorded"); return ST_BADARG; }
+    SGP_CUDA(cudaEventSynchronize(c.pev[NSTAGE_EV - 1]));
+    for (int i = 0; i + 1 < NSTAGE_EV; i++) {
+        float ms = 0.f;
+        SGP_CUDA(cudaEventElapsedTime(&ms, c.pev[i], c.pev[i + 1]));
+        ms7[i] = (double)ms;
+    }
+    return ST_OK;
 }
 
 // ---- scalar closed forms (host) -------------------------------------------------------------

@@ -21,26 +21,28 @@ namespace sgp {
 // sum(log(diag L)).  One CTA, tile resident in shared memory (row stride 129 doubles).
 // ------------------------------------------------------------------------------------------
 constexpr int PT_LD = TILE + 1;
-constexpr size_t PT_SMEM = (size_t)(TILE * PT_LD + 2 * 256) * sizeof(double);
+constexpr int PT_THREADS = 512;                      // 4 threads per row
+constexpr size_t PT_SMEM = (size_t)(TILE * PT_LD + 2 * PT_THREADS) * sizeof(double);
 
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(PT_THREADS, 1)
 potrf_tile_kernel(double* __restrict__ A, long lda, double* __restrict__ Dinv, double* __restrict__ logpart,
                   int* __restrict__ info, int col0)
 {
     extern __shared__ __align__(16) double sm[];
     double* S = sm;                      // S[r*PT_LD + c]
-    double* tmp = sm + TILE * PT_LD;     // 512 doubles scratch
+    double* tmp = sm + TILE * PT_LD;     // 2*PT_THREADS doubles scratch
     const int tid = threadIdx.x;
 
-    for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    for (int idx = tid; idx < TILE * TILE; idx += PT_THREADS) {
         int r = idx & (TILE - 1), c = idx >> 7;
         S[r * PT_LD + c] = (r >= c) ? A[r + (long)c * lda] : 0.0;
     }
     __syncthreads();
 
     const int r = tid & (TILE - 1);      // row owned in the trailing update
-    const int half = tid >> 7;           // columns of parity `half`
+    const int part = tid >> 7;           // columns c with (c - j - 1) % 4 == part
     double mylog = 0.0;
+    double* Sr = S + r * PT_LD;
 
     for (int j = 0; j < TILE; j++) {
         double d = S[j * PT_LD + j];
@@ -52,27 +54,33 @@ potrf_tile_kernel(double* __restrict__ A, long lda, double* __restrict__ Dinv, d
         const double dj = sqrt(d);
         const double inv = 1.0 / dj;
         __syncthreads();                 // everyone has read S[j][j]
-        if (half == 0) {
-            if (r > j) S[r * PT_LD + j] *= inv;
-            else if (r == j) { S[j * PT_LD + j] = dj; mylog = log(dj); }
+        if (part == 0) {
+            if (r > j) Sr[j] *= inv;
+            else if (r == j) { Sr[j] = dj; mylog = log(dj); }
         }
         __syncthreads();
         if (r > j) {
-            const double lrj = S[r * PT_LD + j];
-            // columns c in (j, r] with c % 2 == half
-            int c = j + 1 + ((j + 1 + half) & 1);
-            for (; c <= r; c += 2) S[r * PT_LD + c] -= lrj * S[c * PT_LD + j];
+            const double lrj = Sr[j];
+            // columns c = j+1+part, j+5+part, ... <= r ; four independent updates per trip
+            int c = j + 1 + part;
+            for (; c + 12 <= r; c += 16) {
+                const double l0 = S[c * PT_LD + j], l1 = S[(c + 4) * PT_LD + j], l2 = S[(c + 8) * PT_LD + j],
+                             l3 = S[(c + 12) * PT_LD + j];
+                const double s0 = Sr[c], s1 = Sr[c + 4], s2 = Sr[c + 8], s3 = Sr[c + 12];
+                Sr[c] = s0 - lrj * l0; Sr[c + 4] = s1 - lrj * l1; Sr[c + 8] = s2 - lrj * l2; Sr[c + 12] = s3 - lrj * l3;
+            }
+            for (; c <= r; c += 4) Sr[c] -= lrj * S[c * PT_LD + j];
         }
         __syncthreads();                 // S[j+1][j+1] final before the next pivot is read
     }
 
     // L back to global (lower + explicit zeros above the diagonal)
-    for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    for (int idx = tid; idx < TILE * TILE; idx += PT_THREADS) {
         int rr = idx & (TILE - 1), c = idx >> 7;
         A[rr + (long)c * lda] = S[rr * PT_LD + c];
     }
     // sum of log(diag): fixed order
-    if (half == 0) tmp[r] = mylog;
+    if (part == 0) tmp[r] = mylog;
     __syncthreads();
     if (tid == 0) {
         double s = 0.0;
@@ -85,20 +93,24 @@ potrf_tile_kernel(double* __restrict__ A, long lda, double* __restrict__ Dinv, d
     //   X[j][j] = 1/L[j][j];  X[j+1:, j] = -X[j+1:, j+1:] * L[j+1:, j] * X[j][j]
     for (int j = TILE - 1; j >= 0; j--) {
         const double xjj = 1.0 / S[j * PT_LD + j];
-        double part = 0.0;
+        double p0 = 0.0, p1 = 0.0;
         if (r > j) {
-            int k = j + 1 + ((j + 1 + half) & 1);
-            for (; k <= r; k += 2) part += S[r * PT_LD + k] * S[k * PT_LD + j];
+            int k = j + 1 + part;
+            for (; k + 4 <= r; k += 8) {
+                p0 += Sr[k] * S[k * PT_LD + j];
+                p1 += Sr[k + 4] * S[(k + 4) * PT_LD + j];
+            }
+            for (; k <= r; k += 4) p0 += Sr[k] * S[k * PT_LD + j];
         }
-        tmp[tid] = part;
+        tmp[tid] = p0 + p1;
         __syncthreads();                 // all reads of column j (still L) done
-        if (half == 0) {
-            if (r > j) S[r * PT_LD + j] = -(tmp[r] + tmp[r + TILE]) * xjj;
-            else if (r == j) S[j * PT_LD + j] = xjj;
+        if (part == 0) {
+            if (r > j) Sr[j] = -((tmp[r] + tmp[r + TILE]) + (tmp[r + 2 * TILE] + tmp[r + 3 * TILE])) * xjj;
+            else if (r == j) Sr[j] = xjj;
         }
         __syncthreads();
     }
-    for (int idx = tid; idx < TILE * TILE; idx += 256) {
+    for (int idx = tid; idx < TILE * TILE; idx += PT_THREADS) {
         int rr = idx & (TILE - 1), c = idx >> 7;
         Dinv[rr + c * TILE] = S[rr * PT_LD + c];
     }
@@ -197,7 +209,7 @@ static int launch_potrf_tile(Ctx& c, double* A, long lda, double* Dinv, double* 
         g_potrf_cfg = 1;
     }
     const long o = (long)jt * TILE;
-    potrf_tile_kernel<<<1, 256, PT_SMEM, c.stream>>>(A + o + o * lda, lda, Dinv + (long)jt * TILE * TILE, logparts + jt,
+    potrf_tile_kernel<<<1, PT_THREADS, PT_SMEM, c.stream>>>(A + o + o * lda, lda, Dinv + (long)jt * TILE * TILE, logparts + jt,
                                                       info, (int)o);
     SGP_CUDA(cudaGetLastError());
     count_launch();
@@ -263,7 +275,8 @@ int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logpart
 {
     if (n_pad % TILE || lda % 2) { set_error("potrf: n_pad %ld / lda %ld not tile aligned", n_pad, lda); return ST_BADARG; }
     const int nt = (int)(n_pad / TILE);
-    const int nb = env_int("SGP_POTRF_NB", 4, 1, 64);
+    const int nb = env_int("SGP_POTRF_NB", 0, 0, 64);
+    if (nb == 0) return potrf_rec(c, A, lda, Dinv, logparts, info, 0, nt);      // fully recursive
     const int lookahead = env_int("SGP_LOOKAHEAD", 1, 0, 1) && c.side != nullptr && nt > 2 * nb;
     cudaStream_t s0 = c.stream, s1 = c.side;
 
@@ -360,7 +373,8 @@ static int trtri_rec(Ctx& c, double* A, long lda, const double* Dinv, double* T,
 int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T)
 {
     const int nt = (int)(n_pad / TILE);
-    const int nb = env_int("SGP_TRTRI_NB", 4, 1, 64);
+    const int nb = env_int("SGP_TRTRI_NB", 0, 0, 64);
+    if (nb == 0) return trtri_rec(c, A, lda, Dinv, T, 0, nt);                    // fully recursive
     int j0 = ((nt - 1) / nb) * nb;
     for (; j0 >= 0; j0 -= nb) {
         const int jb = (nt - j0 < nb) ? (nt - j0) : nb;
@@ -384,7 +398,10 @@ size_t trtri_workspace_doubles(long n_pad)
 {
     const size_t nb = 64;                                        // upper bound of SGP_TRTRI_NB
     const size_t rec = (nb * TILE / 2 + TILE) * (nb * TILE / 2 + TILE);
-    return rec + (size_t)n_pad * (nb * TILE);
+    const size_t blocked = rec + (size_t)n_pad * (nb * TILE);
+    const size_t half = (size_t)(n_pad / 2 + TILE);
+    const size_t recursive = half * half;
+    return blocked > recursive ? blocked : recursive;
 }
 
 int lauum(Ctx& c, const double* X, long n_pad, long lda, double* W, long ldw)

@@ -67,6 +67,9 @@ inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
 //   [8..10] A_lx, A_ly, A_sig = alpha' dK alpha   [11..13] B_lx, B_ly, B_sig = trace(Kyinv dK)
 constexpr int RES_DOUBLES = 16;
 
+// stage boundaries of one NLL(+gradient) evaluation: start | fill | potrf | potrs | trtri | lauum | grad | finalize
+constexpr int NSTAGE_EV = 8;
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;    // main stream (borrowed or owned)
@@ -76,6 +79,17 @@ struct Ctx {
     DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io;
     double* h_res = nullptr;          // pinned host staging (RES_DOUBLES + spare)
     int sm_count = 148;
+    // optional stage timers of one NLL evaluation (sgp_set_profiling / sgp_stage_times)
+    bool prof = false;
+    cudaEvent_t pev[NSTAGE_EV] = {};
+    bool pev_valid = false;           // pev[] recorded by the last nll_enqueue
+    int mark(int k)
+    {
+        if (!prof) return ST_OK;
+        cudaError_t e = cudaEventRecord(pev[k], stream);
+        if (e != cudaSuccess) { set_error("cudaEventRecord: %s", cudaGetErrorString(e)); return ST_CUDA; }
+        return ST_OK;
+    }
 };
 
 }  // namespace sgp

@@ -27,6 +27,7 @@ namespace sgp {
 
 constexpr int MAP_THREADS = 128;
 constexpr int MAP_CH = 512;           // training points per shared-memory chunk
+constexpr int MAP_MIN_BLOCKS = 5;     // 640 threads / SM: registers capped at 96
 constexpr double TWO_PI = 6.283185307179586;
 
 __device__ __forceinline__ double np_mod(double a, double b)
@@ -102,7 +103,7 @@ __device__ __forceinline__ void sweep(const double* const* __restrict__ fld, lon
 }
 
 template <int FAM, int SOLVER>
-__global__ void __launch_bounds__(MAP_THREADS)
+__global__ void __launch_bounds__(MAP_THREADS, MAP_MIN_BLOCKS)
 map_kernel(MapArgs a)
 {
     __shared__ __align__(16) double sm[5 * MAP_CH];

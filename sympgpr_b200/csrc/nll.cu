@@ -124,6 +124,8 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     const HypC h = make_hypc(fam, job.hyp[0], job.hyp[1], job.hyp[2], job.per);
     const double noise = fabs(job.hyp[3]);
 
+    c.pev_valid = false;
+    SGP_TRY(c.mark(0));
     SGP_TRY(make_points(c, fam, job.per, job.d_x, job.d_x + N, N, pts));
     if (job.reg) SGP_TRY(fill_reg_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
     else SGP_TRY(fill_hess_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
@@ -131,8 +133,10 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     SGP_CUDA(cudaMemsetAsync(yv, 0, (size_t)n_pad * sizeof(double), st));
     SGP_CUDA(cudaMemcpyAsync(yv, job.d_z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), st));
+    SGP_TRY(c.mark(1));
 
     SGP_TRY(potrf(c, K, n_pad, n_pad, Dinv, logparts, info));
+    SGP_TRY(c.mark(2));
     if (job.d_L) {
         tril_out_kernel<<<1024, 256, 0, st>>>(K, n_pad, job.d_L, n);
         SGP_CUDA(cudaGetLastError());
@@ -140,23 +144,32 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     }
     SGP_TRY(potrs(c, K, n_pad, n_pad, Dinv, yv, wv, av));
     if (job.d_alpha) SGP_CUDA(cudaMemcpyAsync(job.d_alpha, av, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    SGP_TRY(c.mark(3));
 
     double* partial = c.partial.as<double>();
     if (need_inv) {
         double* W = c.Wmat.as<double>();
         SGP_TRY(trtri(c, K, n_pad, n_pad, Dinv, c.Tmat.as<double>()));
+        SGP_TRY(c.mark(4));
         SGP_TRY(lauum(c, K, n_pad, n_pad, W, n_pad));
+        SGP_TRY(c.mark(5));
         if (job.ngrad > 0) SGP_TRY(grad_contract(c, fam, job.reg, pts, N, h, W, n_pad, av, partial));
         if (job.d_kinv) {
             sym_out_kernel<<<1024, 256, 0, st>>>(W, n_pad, job.d_kinv, n);
             SGP_CUDA(cudaGetLastError());
-        count_launch();
+            count_launch();
         }
+    } else {
+        SGP_TRY(c.mark(4));
+        SGP_TRY(c.mark(5));
     }
+    SGP_TRY(c.mark(6));
     finalize_kernel<<<1, 256, 0, st>>>(job.d_z, av, n, logparts, nt, info, partial, job.ngrad > 0 ? npart : 0, job.hyp[2],
                                        job.ngrad, job.d_res);
     SGP_CUDA(cudaGetLastError());
     count_launch();
+    SGP_TRY(c.mark(7));
+    c.pev_valid = c.prof;
     return ST_OK;
 }
 

@@ -1,7 +1,7 @@
 """Scratch: panel-width scan of the blocked potrf / trtri on a GPU box."""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repo root
 from sympgpr_b200 import _lib, api, workloads as W
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 d = W.standard_map_training(N); hyp = W.timing_hyp(N, d["sig"], 1e-8); n = 2 * N

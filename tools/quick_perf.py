@@ -1,7 +1,7 @@
 """Scratch: quick timing of the stages on a GPU box (not part of the product)."""
 import ctypes, sys, time
 import numpy as np
-sys.path.insert(0, ".")
+sys.path.insert(0, ".")  # run from the repo root
 from oracle import oracle as O
 from sympgpr_b200 import _lib, api
 

@@ -169,6 +169,8 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
 /* DMMA GEMM self test: random operands, compares against a plain FP64 kernel; see csrc/dmma_gemm.cuh
  * for al/bl/mode.  Returns the largest absolute difference in *max_err. */
 int sgp_selftest_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, double* max_err);
+/* DMMA GEMM timing: `reps` launches on random operands (alpha = -1, beta = 1), average ms per launch */
+int sgp_bench_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, int reps, double* ms_avg);
 /* timing hooks for bench.py (device pointers, async): the individual stages of one evaluation */
 int sgp_fill_sym_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* d_xin,
                      long n, double* d_K, long ld);

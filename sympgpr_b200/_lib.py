@@ -66,6 +66,7 @@ _PROTOS = {
     "sgp_ath": (c_d, [c_d, c_d, c_d]),
     "sgp_spd_factor": (c_i, [c_vp, c_dp, c_l, c_dp, c_dp, c_dp]),
     "sgp_selftest_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
+    "sgp_bench_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
     "sgp_fill_sym_dev": (c_i, [c_vp, c_i, c_d, c_i, c_dp, c_vp, c_l, c_vp, c_l]),
     "sgp_potrf_dev": (c_i, [c_vp, c_vp, c_l, c_l, c_vp]),
     "sgp_build_k_dev": (c_i, [c_vp, c_i, c_d, c_vp, c_vp, c_l, c_vp, c_vp, c_l, c_dp, c_vp, c_l]),

@@ -782,6 +782,38 @@ int sgp_selftest_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, in
     return ST_OK;
 }
 
+int sgp_bench_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, int reps, double* ms_avg)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (Mt <= 0 || Nt <= 0 || K <= 0 || K % GK || reps <= 0 || !ms_avg) { set_error("bench_gemm: bad arguments"); return ST_BADARG; }
+    if ((mode == TM_LOWER || mode == TM_LOWER_KGE) && Mt != Nt) { set_error("bench_gemm: lower modes need Mt == Nt"); return ST_BADARG; }
+    const long M = (long)Mt * TILE, N = (long)Nt * TILE;
+    const long lda = (al == LAYOUT_MN) ? M : K, ldb = (bl == LAYOUT_MN) ? N : K;
+    const size_t szA = (size_t)M * K, szB = (size_t)N * K, szC = (size_t)M * N;
+    SGP_TRY(c.Kmat.reserve((szA + szB + szC + 1024) * sizeof(double)));
+    double* dA = c.Kmat.as<double>();
+    double* dB = dA + szA; double* dC = dB + szB;
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dA, (long)szA, 1ull, 1, 0);
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dB, (long)szB, 2ull, 1, 0);
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dC, (long)szC, 3ull, 1, 0);
+    GemmArgs g;
+    g.A = dA; g.lda = lda; g.B = dB; g.ldb = ldb; g.C = dC; g.ldc = M; g.Mt = Mt; g.Nt = Nt; g.K = K; g.alpha = -1.0; g.beta = 1.0; g.mode = mode;
+    SGP_TRY(dmma_gemm(c, al, bl, g));                       // warm-up
+    cudaEvent_t e0, e1;
+    SGP_CUDA(cudaEventCreate(&e0));
+    SGP_CUDA(cudaEventCreate(&e1));
+    SGP_CUDA(cudaEventRecord(e0, c.stream));
+    for (int r = 0; r < reps; r++) SGP_TRY(dmma_gemm(c, al, bl, g));
+    SGP_CUDA(cudaEventRecord(e1, c.stream));
+    SGP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    SGP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_avg = (double)ms / reps;
+    return ST_OK;
+}
+
 int sgp_fill_sym_dev(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* d_xin, long n, double* d_K, long ld)
 {
     SGP_TRY(check_ctx(ctx));

@@ -222,9 +222,7 @@ static int gemm(Ctx& c, int al, int bl, const double* A, long lda, const double*
     GemmArgs g;
     g.A = A; g.lda = lda; g.B = B; g.ldb = ldb; g.C = C; g.ldc = ldc;
     g.Mt = Mt; g.Nt = Nt; g.K = (int)K; g.alpha = alpha; g.beta = beta; g.mode = mode;
-    SGP_CUDA(gemm_launch(al, bl, g, c.stream));
-    count_launch();
-    return ST_OK;
+    return dmma_gemm(c, al, bl, g);
 }
 
 #define AT(A, lda, rt, ct) ((A) + (long)(rt) * TILE + (long)(ct) * TILE * (lda))
@@ -445,9 +443,13 @@ int ref_gemm(Ctx& c, int al, int bl, const GemmArgs& g, double* out)
     return ST_OK;
 }
 
+// SGP_GEMM=v1 selects the cp.async ring kernel (dmma_gemm.cuh); default is the warp-specialised
+// persistent kernel (dmma_gemm_ws.cuh).  Same arguments, same results up to summation order (identical).
 int dmma_gemm(Ctx& c, int al, int bl, const GemmArgs& g)
 {
-    SGP_CUDA(gemm_launch(al, bl, g, c.stream));
+    static const int use_v1 = [] { const char* v = getenv("SGP_GEMM"); return (v && v[0] == 'v' && v[1] == '1') ? 1 : 0; }();
+    if (use_v1) SGP_CUDA(gemm_launch(al, bl, g, c.stream));
+    else SGP_CUDA(gemm_ws_launch(al, bl, g, c.stream));
     count_launch();
     return ST_OK;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include "common.cuh"
 #include "dmma_gemm.cuh"
+#include "dmma_gemm_ws.cuh"
 
 namespace sgp {
 

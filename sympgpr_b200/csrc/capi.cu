@@ -174,7 +174,7 @@ int sgp_release_workspace(sgp_ctx* ctx)
     Ctx& c = ctx->c;
     cudaStreamSynchronize(c.stream);
     c.Kmat.release(); c.Wmat.release(); c.Tmat.release(); c.Dinv.release(); c.vecs.release();
-    c.pts.release(); c.partial.release(); c.small.release(); c.mapbuf.release(); c.io.release();
+    c.pts.release(); c.partial.release(); c.small.release(); c.mapbuf.release(); c.io.release(); c.flags.release();
     return ST_OK;
 }
 
@@ -644,6 +644,10 @@ int sgp_calcp(sgp_ctx* ctx, int fam, double per, int solver, double x, double y,
 static int check_res_info(const double* res)
 {
     const double info = res[SGP_RES_INFO];
+    if (info < 0.0) {
+        set_error("potrf kernel aborted: a tile dependency wait timed out");
+        return ST_CUDA;
+    }
     if (info > 0.0) {
         set_error("Cholesky failed: leading minor of order %d is not positive definite", (int)info);
         return (int)info;

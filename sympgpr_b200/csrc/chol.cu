@@ -273,6 +273,13 @@ int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logpart
 {
     if (n_pad % TILE || lda % 2) { set_error("potrf: n_pad %ld / lda %ld not tile aligned", n_pad, lda); return ST_BADARG; }
     const int nt = (int)(n_pad / TILE);
+    // default: the left-looking persistent kernel (potrf_ll.cu).  SGP_POTRF=rec selects the recursive /
+    // blocked multi-launch drivers below (kept for comparison).
+    static const int use_rec = [] { const char* v = getenv("SGP_POTRF"); return (v && v[0] == 'r') ? 1 : 0; }();
+    if (!use_rec) {
+        SGP_TRY(c.flags.reserve(potrf_ll_flag_bytes(n_pad)));
+        return potrf_ll(c, A, n_pad, lda, Dinv, logparts, info, c.flags.as<int>());
+    }
     const int nb = env_int("SGP_POTRF_NB", 0, 0, 64);
     if (nb == 0) return potrf_rec(c, A, lda, Dinv, logparts, info, 0, nt);      // fully recursive
     const int lookahead = env_int("SGP_LOOKAHEAD", 1, 0, 1) && c.side != nullptr && nt > 2 * nb;

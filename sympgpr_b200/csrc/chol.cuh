@@ -7,6 +7,9 @@
 namespace sgp {
 
 int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info);
+// one persistent cooperative kernel (potrf_ll.cu); flags: potrf_ll_flag_bytes(n_pad) bytes of device scratch
+int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags);
+size_t potrf_ll_flag_bytes(long n_pad);
 int potrs(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w, double* alpha);
 int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T);
 size_t trtri_workspace_doubles(long n_pad);

@@ -76,7 +76,7 @@ struct Ctx {
     bool own_stream = false;
     cudaStream_t side = nullptr;      // panel / look-ahead stream (owned)
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io;
+    DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io, flags;
     double* h_res = nullptr;          // pinned host staging (RES_DOUBLES + spare)
     int sm_count = 148;
     // optional stage timers of one NLL evaluation (sgp_set_profiling / sgp_stage_times)

@@ -142,7 +142,7 @@ __device__ __forceinline__ void load_frags_b(const double* sb, int wn, int g, in
 template <int AL, int BL>
 __global__ void __launch_bounds__(WS_THREADS, 1) gemm_f64_ws_kernel(GemmArgs p, long ntiles)
 {
-    extern __shared__ __align__(128) double smem[];
+    extern __shared__ __align__(16) double smem[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)WS_STAGES * 2 * STAGE_DOUBLES);
     unsigned long long* empty = full + WS_STAGES;
     const int tid = threadIdx.x;

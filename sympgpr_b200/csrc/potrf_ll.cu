@@ -1,0 +1,417 @@
+// Left-looking tile Cholesky as ONE persistent cooperative kernel (the whole potrf is one launch).
+//
+// Replaces scipy.linalg.cholesky (LAPACK dpotrf) of python/05_tokamak/SympGPR/func.py:147 and
+// python/02_pert_pendulum/func.py:136,195 on the 2N x 2N Hessian-block matrix.
+//
+// The matrix is cut into 128 x 128 tiles.  Tile (i,j), i >= j, is one task:
+//     C'   = A(i,j) - sum_{k<j} L(i,k) L(j,k)^T      one register-accumulated DMMA GEMM of depth 128 j
+//     i==j : L(j,j) = chol(C'), Dinv_j = L(j,j)^-1    in shared memory by the 8 consumer warps
+//     i> j : L(i,j) = C' Dinv_j^T                     a second, depth-128 pass through the same ring
+// so every flop of the update runs in a long-k main loop (no read-modify-write of the trailing matrix,
+// no short-k GEMM launches, no wave quantisation) and the only global traffic is the operand stream.
+// CTAs (one per SM, warp-specialised exactly like dmma_gemm_ws.cuh: producer warp + full/empty
+// mbarrier ring + 8 DMMA consumer warps) take tasks round-robin from a fixed order
+//     DIAG(0) | (1,0) DIAG(1) (2,0) ... (nt-1,0) | (2,1) DIAG(2) (3,1) ... | ...
+// i.e. column by column, with the next column's diagonal tile pulled forward to second place: its
+// factorisation (the latency-bound step) then overlaps the rest of the current column.  A task only
+// depends on tasks earlier in that order, all CTAs are co-resident (cooperative launch), so the CTA
+// holding the oldest unfinished task can always proceed.  Dependencies are tracked with one ready
+// flag per tile in global memory (release store after the tile is written, acquire load by the
+// producer lane before it streams the tile).
+//
+// A failed dependency wait (10 s) sets an abort word; every wait in the kernel returns early once it
+// is set and the launcher reports an error -- the kernel cannot hang the device.
+#include "chol.cuh"
+
+namespace sgp {
+
+namespace {
+
+constexpr int LL_LD = TILE + 1;                 // row stride of the diagonal tile in shared memory
+constexpr int LL_CONSUMERS = WS_CONSUMER_WARPS * 32;
+
+struct LLArgs {
+    double* A; long lda; int nt;
+    double* Dinv;          // nt tiles, ld 128
+    double* logparts;      // nt
+    int* info;
+    int* ready;            // nt*nt, ready[i + j*nt] = 1 once L(i,j) (and Dinv_j for i == j) is final
+    int* abort;
+};
+
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0u;
+}
+// returns when the phase completes, or early once the abort word is set
+__device__ __forceinline__ void mbar_wait_ab(unsigned long long* bar, uint32_t parity, const volatile int* abort)
+{
+    uint32_t spins = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        if ((++spins & 15u) == 0u && *abort) return;
+    }
+}
+__device__ __forceinline__ int ld_acquire(const int* p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v)
+{
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
+__device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(LL_CONSUMERS) : "memory"); }
+
+// one lane spins until the tile's ready flag is set (or abort)
+__device__ __forceinline__ void wait_ready(const int* flag, int* abort, int* info)
+{
+    if (ld_acquire(flag) != 0) return;
+    const unsigned long long t0 = globaltimer();
+    unsigned n = 0;
+    while (ld_acquire(flag) == 0) {
+        __nanosleep(100);
+        if ((++n & 255u) == 0u) {
+            if (*(volatile int*)abort) return;
+            if (globaltimer() - t0 > 10000000000ull) { atomicExch(abort, 1); atomicExch(info, -1); return; }
+        }
+    }
+}
+
+// task order (see the header comment): ticket -> tile (i,j)
+__device__ __forceinline__ void ll_ticket(long t, int nt, int& i, int& j)
+{
+    if (t == 0) { i = 0; j = 0; return; }
+    const long tp = t - 1;
+    const double b = 2.0 * nt + 1.0;
+    long c = (long)((b - sqrt(b * b - 8.0 * (double)tp)) * 0.5);
+    if (c < 0) c = 0;
+    if (c > nt - 2) c = nt - 2;
+    auto off = [nt](long q) { return q * nt - q * (q - 1) / 2; };
+    while (c < nt - 2 && off(c + 1) <= tp) c++;
+    while (c > 0 && off(c) > tp) c--;
+    const long r = tp - off(c);
+    if (r == 0) { i = (int)c + 1; j = (int)c; }
+    else if (r == 1) { i = (int)c + 1; j = (int)c + 1; }
+    else { i = (int)(c + r); j = (int)c; }
+}
+
+// producer: nk slabs of (A rows at pa, B rows at pb), both LAYOUT_MN, k advancing by GK columns
+__device__ __forceinline__ void ll_produce(const double* pa, long lda, const double* pb, long ldb, int nk, uint32_t& it, double* smem,
+                                           unsigned long long* full, unsigned long long* empty, int lane, const volatile int* abort)
+{
+    for (int kb = 0; kb < nk; kb++, it++) {
+        const int s = (int)(it % WS_STAGES);
+        const uint32_t ph = (it / WS_STAGES) & 1u;
+        mbar_wait_ab(empty + s, ph ^ 1u, abort);
+        if (lane == 0) mbar_arrive_expect_tx(full + s, 2u * WS_SLAB_BYTES);
+        __syncwarp();
+        double* sa = smem + (size_t)s * 2 * STAGE_DOUBLES;
+        const long kk = (long)kb * GK;
+        produce_slab<LAYOUT_MN>(sa, pa, lda, 0, kk, lane, full + s);
+        produce_slab<LAYOUT_MN>(sa + STAGE_DOUBLES, pb, ldb, 0, kk, lane, full + s);
+    }
+}
+
+// consumers: acc += sum over nk slabs
+__device__ __forceinline__ void ll_consume(double (&acc)[8][4][2], int nk, uint32_t& it, const double* smem, unsigned long long* full,
+                                           unsigned long long* empty, int wm, int wn, int g, int t, int lane, const volatile int* abort)
+{
+    for (int kb = 0; kb < nk; kb++, it++) {
+        const int s = (int)(it % WS_STAGES);
+        const uint32_t ph = (it / WS_STAGES) & 1u;
+        mbar_wait_ab(full + s, ph, abort);
+        const double* sa = smem + (size_t)s * 2 * STAGE_DOUBLES;
+        const double* sb = sa + STAGE_DOUBLES;
+        double af[2][8], bf[2][4];
+        load_frags_a<LAYOUT_MN>(sa, wm, g, t, 0, af[0]);
+        load_frags_b<LAYOUT_MN>(sb, wn, g, t, 0, bf[0]);
+#pragma unroll
+        for (int k4 = 0; k4 < GK / 4; k4++) {
+            const int cur = k4 & 1, nxt = cur ^ 1;
+            if (k4 + 1 < GK / 4) {
+                load_frags_a<LAYOUT_MN>(sa, wm, g, t, (k4 + 1) * 4, af[nxt]);
+                load_frags_b<LAYOUT_MN>(sb, wn, g, t, (k4 + 1) * 4, bf[nxt]);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) dmma884(acc[i][j][0], acc[i][j][1], af[cur][i], bf[cur][j]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + s);
+    }
+}
+
+// Cholesky factor and inverse of the 128 x 128 tile held in shared memory S[r*LL_LD + c] (lower part),
+// by the 256 consumer threads.  Unblocked right-looking factorisation, then the unblocked inverse of
+// the triangular factor (last column first).  Returns this thread's share of sum(log diag L).
+__device__ void diag_tile_factor(double* S, double* tmp, int tid, int* info, int col0, double& mylog)
+{
+    const int r = tid & (TILE - 1);
+    const int part = tid >> 7;                   // 0/1: columns c with (c - j - 1) % 2 == part
+    double* Sr = S + r * LL_LD;
+    mylog = 0.0;
+    for (int j = 0; j < TILE; j++) {
+        double d = S[j * LL_LD + j];
+        if (!(d > 0.0)) {                        // also NaN
+            if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
+            d = 1.0;
+        }
+        const double dj = sqrt(d);
+        const double inv = 1.0 / dj;
+        consumer_bar();                          // everyone has read S[j][j]
+        if (part == 0) {
+            if (r > j) Sr[j] *= inv;
+            else if (r == j) { Sr[j] = dj; mylog = log(dj); }
+        }
+        consumer_bar();
+        if (r > j) {
+            const double lrj = Sr[j];
+            int c = j + 1 + part;
+            for (; c + 6 <= r; c += 8) {
+                const double l0 = S[c * LL_LD + j], l1 = S[(c + 2) * LL_LD + j], l2 = S[(c + 4) * LL_LD + j], l3 = S[(c + 6) * LL_LD + j];
+                const double s0 = Sr[c], s1 = Sr[c + 2], s2 = Sr[c + 4], s3 = Sr[c + 6];
+                Sr[c] = s0 - lrj * l0; Sr[c + 2] = s1 - lrj * l1; Sr[c + 4] = s2 - lrj * l2; Sr[c + 6] = s3 - lrj * l3;
+            }
+            for (; c <= r; c += 2) Sr[c] -= lrj * S[c * LL_LD + j];
+        }
+        consumer_bar();                          // S[j+1][j+1] final before the next pivot is read
+    }
+}
+
+__device__ void diag_tile_invert(double* S, double* tmp, int tid)
+{
+    const int r = tid & (TILE - 1);
+    const int part = tid >> 7;
+    double* Sr = S + r * LL_LD;
+    // X[j][j] = 1/L[j][j];  X[j+1:, j] = -X[j+1:, j+1:] * L[j+1:, j] * X[j][j]
+    for (int j = TILE - 1; j >= 0; j--) {
+        const double xjj = 1.0 / S[j * LL_LD + j];
+        double p0 = 0.0, p1 = 0.0;
+        if (r > j) {
+            int k = j + 1 + part;
+            for (; k + 2 <= r; k += 4) {
+                p0 += Sr[k] * S[k * LL_LD + j];
+                p1 += Sr[k + 2] * S[(k + 2) * LL_LD + j];
+            }
+            for (; k <= r; k += 2) p0 += Sr[k] * S[k * LL_LD + j];
+        }
+        tmp[tid] = p0 + p1;
+        consumer_bar();                          // all reads of column j (still L) done
+        if (part == 0) {
+            if (r > j) Sr[j] = -(tmp[r] + tmp[r + TILE]) * xjj;
+            else if (r == j) Sr[j] = xjj;
+        }
+        consumer_bar();
+    }
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
+{
+    extern __shared__ __align__(16) double smem[];
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)WS_STAGES * 2 * STAGE_DOUBLES);
+    unsigned long long* empty = full + WS_STAGES;
+    unsigned long long* c2p = empty + WS_STAGES;           // consumers -> producer, once per task
+    int* s_stop = reinterpret_cast<int*>(c2p + 1);         // two slots (alternating per task)
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int nt = a.nt;
+    const long ntasks = (long)nt * (nt + 1) / 2;
+    const volatile int* vabort = a.abort;
+
+    if (tid == 0) {
+        for (int s = 0; s < WS_STAGES; s++) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, WS_CONSUMER_WARPS);
+        }
+        mbar_init(c2p, 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    if (warp == WS_CONSUMER_WARPS) {
+        // ------------------------------------------------------------------ producer warp
+        uint32_t it = 0, seq = 0;
+        for (long task = blockIdx.x; task < ntasks; task += gridDim.x, seq++) {
+            if (*vabort) return;
+            int i, j;
+            ll_ticket(task, nt, i, j);
+            const double* rowi = a.A + (long)i * TILE;
+            const double* rowj = a.A + (long)j * TILE;
+            for (int kb = 0; kb < j; kb++) {
+                if (lane == 0) {
+                    wait_ready(a.ready + i + (long)kb * nt, a.abort, a.info);
+                    if (i != j) wait_ready(a.ready + j + (long)kb * nt, a.abort, a.info);
+                }
+                __syncwarp();
+                fence_proxy_async();
+                ll_produce(rowi + (long)kb * TILE * a.lda, a.lda, rowj + (long)kb * TILE * a.lda, a.lda, TILE / GK, it, smem, full,
+                           empty, lane, vabort);
+            }
+            // consumers: C' stored (i > j) or diagonal tile finished with the ring memory (i == j)
+            mbar_wait_ab(c2p, seq & 1u, vabort);
+            if (i != j) {
+                if (lane == 0) wait_ready(a.ready + j + (long)j * nt, a.abort, a.info);
+                __syncwarp();
+                fence_proxy_async();
+                ll_produce(a.A + (long)i * TILE + (long)j * TILE * a.lda, a.lda, a.Dinv + (long)j * TILE * TILE, TILE, TILE / GK, it,
+                           smem, full, empty, lane, vabort);
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumer warps
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = (warp & 1) * 64;
+    const int wn = (warp >> 1) * 32;
+    uint32_t it = 0, seq = 0;
+    for (long task = blockIdx.x; task < ntasks; task += gridDim.x, seq++) {
+        // uniform stop decision for the 8 consumer warps (they share named barriers below)
+        if (tid == 0) s_stop[seq & 1u] = *vabort;
+        consumer_bar();
+        if (s_stop[seq & 1u]) return;
+
+        int i, j;
+        ll_ticket(task, nt, i, j);
+        double acc[8][4][2];
+#pragma unroll
+        for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+            for (int jj = 0; jj < 4; jj++) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
+        ll_consume(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort);
+
+        double* tile = a.A + (long)i * TILE + (long)j * TILE * a.lda;
+        if (i == j) {
+            // ---- diagonal tile: S = A(j,j) - acc in shared memory (ring is idle: the producer waits on c2p)
+            consumer_bar();                                  // every warp is out of the main loop
+            double* S = smem;
+            double* tmp = smem + TILE * LL_LD;
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++) {
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    const int row = wm + ii * 8 + g, col = wn + jj * 8 + 2 * t;
+                    if (row >= col) S[row * LL_LD + col] = tile[row + (long)col * a.lda] - acc[ii][jj][0];
+                    if (row >= col + 1) S[row * LL_LD + col + 1] = tile[row + (long)(col + 1) * a.lda] - acc[ii][jj][1];
+                }
+            }
+            consumer_bar();
+            double mylog;
+            diag_tile_factor(S, tmp, tid, a.info, j * TILE, mylog);
+            for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
+                const int rr = idx & (TILE - 1), c = idx >> 7;
+                tile[rr + (long)c * a.lda] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
+            }
+            if (tid < TILE) tmp[tid] = mylog;
+            consumer_bar();
+            if (tid == 0) {
+                double s = 0.0;
+                for (int k = 0; k < TILE; k++) s += tmp[k];
+                a.logparts[j] = s;
+            }
+            consumer_bar();
+            diag_tile_invert(S, tmp, tid);
+            double* Dj = a.Dinv + (long)j * TILE * TILE;
+            for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
+                const int rr = idx & (TILE - 1), c = idx >> 7;
+                Dj[rr + c * TILE] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
+            }
+            __threadfence();
+            consumer_bar();                                  // all stores issued and fenced; S no longer used
+            if (tid == 0) {
+                st_release(a.ready + j + (long)j * nt, 1);
+                mbar_arrive(c2p);                            // the producer may refill the ring
+            }
+        } else {
+            // ---- off-diagonal tile: C' = A(i,j) - acc, in place; then L(i,j) = C' Dinv_j^T through the ring
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++) {
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    double* c0 = tile + (wm + ii * 8 + g) + (long)(wn + jj * 8 + 2 * t) * a.lda;
+                    double* c1 = c0 + a.lda;
+                    *c0 = *c0 - acc[ii][jj][0];
+                    *c1 = *c1 - acc[ii][jj][1];
+                }
+            }
+            __threadfence();
+            fence_proxy_async();
+            consumer_bar();
+            if (tid == 0) mbar_arrive(c2p);                  // producer: C' is in global memory
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++)
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
+            ll_consume(acc, TILE / GK, it, smem, full, empty, wm, wn, g, t, lane, vabort);
+#pragma unroll
+            for (int ii = 0; ii < 8; ii++) {
+#pragma unroll
+                for (int jj = 0; jj < 4; jj++) {
+                    double* c0 = tile + (wm + ii * 8 + g) + (long)(wn + jj * 8 + 2 * t) * a.lda;
+                    double* c1 = c0 + a.lda;
+                    *c0 = acc[ii][jj][0];
+                    *c1 = acc[ii][jj][1];
+                }
+            }
+            __threadfence();
+            consumer_bar();
+            if (tid == 0) st_release(a.ready + i + (long)j * nt, 1);
+        }
+    }
+}
+
+constexpr size_t LL_SMEM = (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double) + (2 * WS_STAGES + 1) * sizeof(unsigned long long) + 16;
+
+}  // namespace
+
+size_t potrf_ll_flag_bytes(long n_pad)
+{
+    const size_t nt = (size_t)(n_pad / TILE);
+    return (nt * nt + 4) * sizeof(int);
+}
+
+// flags: potrf_ll_flag_bytes(n_pad) bytes of device scratch
+int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags)
+{
+    static bool configured = false;
+    if (!configured) {
+        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+        configured = true;
+    }
+    static_assert((size_t)TILE * LL_LD * sizeof(double) + 2 * LL_CONSUMERS * sizeof(double) <= (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double),
+                  "diagonal tile scratch must fit in the operand ring");
+    const int nt = (int)(n_pad / TILE);
+    const size_t nflags = (size_t)nt * nt;
+    SGP_CUDA(cudaMemsetAsync(flags, 0, (nflags + 4) * sizeof(int), c.stream));
+    LLArgs a;
+    a.A = A; a.lda = lda; a.nt = nt; a.Dinv = Dinv; a.logparts = logparts; a.info = info;
+    a.ready = flags; a.abort = flags + nflags;
+    const long ntasks = (long)nt * (nt + 1) / 2;
+    const int sms = c.sm_count > 0 ? c.sm_count : 148;
+    const unsigned grid = (unsigned)(ntasks < sms ? ntasks : sms);
+    void* args[] = {&a};
+    SGP_CUDA(cudaLaunchCooperativeKernel((const void*)potrf_ll_kernel, dim3(grid), dim3(WS_THREADS), args, LL_SMEM, c.stream));
+    count_launch();
+    return ST_OK;
+}
+
+}  // namespace sgp

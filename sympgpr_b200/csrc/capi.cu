@@ -19,9 +19,10 @@ struct sgp_model {
     int fam = 0;
     double per = 0.5;
     HypC h, hp;
-    long np = 0, nt = 0, np_pad = 0, nt_pad = 0;
-    DBuf buf;                       // 4*np_pad + 5*nt_pad doubles
-    double *gu, *gv, *gy, *ga, *tu, *tv, *ty, *taq, *taP;
+    long np = 0, nt = 0;
+    DBuf buf;                       // chunked training sets (map.cuh): guess GP, then symplectic GP
+    double *gch = nullptr, *tch = nullptr;
+    int nchg = 0, ncht = 0;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -350,19 +351,14 @@ static int model_build(Ctx& c, sgp_model* m, int fam, double per, const double* 
                        const double* d_xt, const double* d_yt, const double* d_alpha, long nt)
 {
     m->fam = fam; m->per = per; m->np = np; m->nt = nt;
-    m->np_pad = map_pad(np); m->nt_pad = map_pad(nt);
+    m->nchg = (int)map_chunks(np); m->ncht = (int)map_chunks(nt);
     m->h = make_hypc(fam, hyp3[0], hyp3[1], hyp3[2], per);
     m->hp = make_hypc(fam, hypp3[0], hypp3[1], hypp3[2], per);
-    SGP_TRY(m->buf.reserve((size_t)(4 * m->np_pad + 5 * m->nt_pad) * sizeof(double)));
-    double* b = m->buf.as<double>();
-    m->gu = b; m->gv = m->gu + m->np_pad; m->gy = m->gv + m->np_pad; m->ga = m->gy + m->np_pad;
-    m->tu = m->ga + m->np_pad; m->tv = m->tu + m->nt_pad; m->ty = m->tv + m->nt_pad;
-    m->taq = m->ty + m->nt_pad; m->taP = m->taq + m->nt_pad;
-    SGP_TRY(map_prepare(c, fam, per, d_xtp, d_ytp, np, m->gu, m->gv, m->gy));
-    SGP_TRY(map_pad_copy(c, d_alphap, np, m->ga));
-    SGP_TRY(map_prepare(c, fam, per, d_xt, d_yt, nt, m->tu, m->tv, m->ty));
-    SGP_TRY(map_pad_copy(c, d_alpha, nt, m->taq));
-    SGP_TRY(map_pad_copy(c, d_alpha + nt, nt, m->taP));
+    SGP_TRY(m->buf.reserve(map_model_doubles(np, nt) * sizeof(double)));
+    m->gch = m->buf.as<double>();
+    m->tch = m->gch + (size_t)m->nchg * MAP_GF * MAP_CHUNK;
+    SGP_TRY(map_prepare_guess(c, fam, per, d_xtp, d_ytp, d_alphap, np, m->gch));
+    SGP_TRY(map_prepare_sympl(c, fam, per, d_xt, d_yt, d_alpha, nt, m->tch));
     return ST_OK;
 }
 
@@ -402,9 +398,9 @@ int sgp_model_destroy(sgp_model* m)
 
 static void model_args(const sgp_model* m, MapArgs& a)
 {
-    a.gu = m->gu; a.gv = m->gv; a.gy = m->gy; a.ga = m->ga; a.np_pad = m->np_pad;
-    a.tu = m->tu; a.tv = m->tv; a.ty = m->ty; a.taq = m->taq; a.taP = m->taP; a.nt_pad = m->nt_pad;
+    a.gch = m->gch; a.nchg = m->nchg; a.tch = m->tch; a.ncht = m->ncht;
     a.h = m->h; a.hp = m->hp;
+    a.pdstate = nullptr; a.ticket = nullptr; a.slice_done = nullptr; a.slice_steps = 1;
 }
 
 int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solver, long nsteps, long E, const double* d_q0,
@@ -421,7 +417,9 @@ int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solve
     a.qout = d_qhist; a.pout = d_phist; a.pdiff = nullptr;
     a.step_stride = E; a.orbit_stride = 1; a.out_every = (d_qhist && d_phist) ? out_every : 0;
     a.qfinal = d_qfinal; a.pfinal = d_pfinal; a.stats = d_stats;
-    return map_launch(ctx->c, m->fam, solver, a);
+    if (E == 0) return ST_OK;
+    SGP_TRY(ctx->c.flags.reserve(map_sched_bytes(E)));
+    return map_launch(ctx->c, m->fam, solver, a, ctx->c.flags.p);
 }
 
 // shared implementation of the host-buffer map entry points
@@ -439,13 +437,14 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
     const bool hist = (qmap && pmap && out_every > 0);
     const long rows = hist ? 1 + (nm - 1) / out_every : 0;
     const size_t hsz = (size_t)rows * (size_t)E;
-    const size_t need = (size_t)(4 * E) + hsz * (pdiff ? 3 : 2) + 4;
+    const size_t need = (size_t)(5 * E) + hsz * (pdiff ? 3 : 2) + 4;
     if (!st) st = c.mapbuf.reserve(need * sizeof(double));
+    if (!st) st = c.flags.reserve(map_sched_bytes(E > 0 ? E : 1));
     if (st) { m.buf.release(); return st; }
     double* d = c.mapbuf.as<double>();
     unsigned long long* dstats = (unsigned long long*)d;
-    double *dq0 = d + 2, *dp0 = dq0 + E, *dqf = dp0 + E, *dpf = dqf + E;
-    double *dqh = dpf + E, *dph = dqh + hsz, *dpd = dph + hsz;
+    double *dq0 = d + 2, *dp0 = dq0 + E, *dqf = dp0 + E, *dpf = dqf + E, *dpds = dpf + E;
+    double *dqh = dpds + E, *dph = dqh + hsz, *dpd = dph + hsz;
     MapArgs a;
     model_args(&m, a);
     a.kind = kind; a.E = E; a.nsteps = nm - 1; a.q0 = dq0; a.p0 = dp0;
@@ -453,11 +452,13 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
     // history is (rows, E) row-major on the device and on the host
     a.step_stride = E; a.orbit_stride = 1; a.out_every = hist ? out_every : 0;
     a.qfinal = dqf; a.pfinal = dpf; a.stats = dstats;
+    a.pdstate = a.pdiff ? dpds : nullptr;
     auto run = [&]() -> int {
         SGP_CUDA(cudaMemsetAsync(dstats, 0, 2 * sizeof(unsigned long long), c.stream));
         SGP_TRY(upload(c, dq0, q0, E));
         SGP_TRY(upload(c, dp0, p0, E));
-        SGP_TRY(map_launch(c, fam, solver, a));
+        SGP_TRY(map_launch(c, fam, solver, a, c.flags.p));
+        if (E > 0) SGP_CUDA(cudaMemcpyAsync(c.h_res + 40, (char*)c.flags.p + 8, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
         if (hist) {
             SGP_TRY(download(c, qmap, dqh, hsz));
             SGP_TRY(download(c, pmap, dph, hsz));
@@ -466,7 +467,13 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
         if (qfinal) SGP_TRY(download(c, qfinal, dqf, E));
         if (pfinal) SGP_TRY(download(c, pfinal, dpf, E));
         if (stats) SGP_CUDA(cudaMemcpyAsync(stats, dstats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-        return sync(c);
+        SGP_TRY(sync(c));
+        if (E > 0) {
+            unsigned long long err;
+            memcpy(&err, c.h_res + 40, sizeof(err));
+            if (err != 0ull) { set_error("applymap: work-item dependency wait timed out in the map kernel"); return ST_CUDA; }
+        }
+        return ST_OK;
     };
     st = run();
     m.buf.release();

@@ -22,6 +22,7 @@
 // profiles/r01_gemm_v1_ncu.txt.)
 #pragma once
 #include "dmma_gemm.cuh"
+#include "mbar.cuh"
 
 namespace sgp {
 
@@ -30,42 +31,6 @@ constexpr int WS_CONSUMER_WARPS = 8;
 constexpr int WS_THREADS = (WS_CONSUMER_WARPS + 1) * 32;
 constexpr uint32_t WS_SLAB_BYTES = GT * GK * sizeof(double);               // bytes of one operand slab (128 x GK)
 constexpr size_t WS_SMEM = (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double) + 2 * WS_STAGES * sizeof(unsigned long long);
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory"); }
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra LAB_DONE;\n"
-        "bra LAB_WAIT;\n"
-        "LAB_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
 
 struct TileInfo {
     int tm, tn;
@@ -99,11 +64,6 @@ __device__ __forceinline__ TileInfo tile_info(const GemmArgs& p, long b)
     t.nk = (int)((k1 - k0) / GK);
     if (t.nk < 0) t.nk = 0;
     return t;
-}
-
-__device__ __forceinline__ void cp_async_mbar_arrive_noinc(unsigned long long* bar)
-{
-    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // producer side: one operand slab (128 x GK) of one stage, spread over the 32 lanes.

@@ -11,13 +11,15 @@ enum MapKind : int {
     MAP_TOKAMAK = 3,    // pendulum wrap + loss test (compute_r)         python/05_tokamak/SympGPR/func.py:182-211
 };
 
+constexpr int MAP_CHUNK = 64;        // training points per chunk (one bulk copy)
+constexpr int MAP_GF = 4;            // fields of a guess-GP chunk:      u, v, y, alpha
+constexpr int MAP_TF = 5;            // fields of a symplectic-GP chunk: u, v, y, alpha_q, alpha_P
+
 struct MapArgs {
-    // ordinary GP (guess): features + alphap, padded to map_pad(np)
-    const double *gu, *gv, *gy, *ga;
-    long np_pad;
-    // symplectic GP: features + alpha (q part, P part), padded to map_pad(nt)
-    const double *tu, *tv, *ty, *taq, *taP;
-    long nt_pad;
+    // training sets in chunked structure-of-arrays form: chunk c = [field0(64) field1(64) ...], padded with
+    // neutral points (alpha = 0) to a whole number of chunks, at least two
+    const double* gch; int nchg;     // ordinary GP (guess)
+    const double* tch; int ncht;     // symplectic GP
     HypC h, hp;
     int kind;
     long E, nsteps;
@@ -25,13 +27,22 @@ struct MapArgs {
     // history: row r (= step / out_every) of orbit k at [r*step_stride + k*orbit_stride]; out_every = 0: none
     double *qout, *pout, *pdiff;
     long step_stride, orbit_stride, out_every;
-    double *qfinal, *pfinal;
-    unsigned long long* stats;   // [0] residual evaluations, [1] solver exits without convergence
+    double *qfinal, *pfinal;         // last state; also carries the state from one work item to the next
+    double* pdstate;                 // running pdiff between work items (only when pdiff != nullptr)
+    unsigned long long* stats;       // [0] residual evaluations, [1] solver exits without convergence
+    // work distribution: item t = (batch t % nbatches of 32 orbits, slice t / nbatches of slice_steps steps)
+    long slice_steps;
+    unsigned long long* ticket;      // [0] work counter, [1] scheduler error word; zeroed before launch
+    int* slice_done;                 // nbatches ints, zeroed before launch
 };
 
-long map_pad(long n);
-int map_prepare(Ctx& c, int fam, double per, const double* x, const double* y, long n, double* u, double* v, double* yo);
-int map_pad_copy(Ctx& c, const double* src, long n, double* dst);
-int map_launch(Ctx& c, int fam, int solver, const MapArgs& a);
+long map_chunks(long n);                                   // chunks a set of n points occupies
+size_t map_model_doubles(long np, long nt);
+size_t map_sched_bytes(long E);                            // ticket + slice_done scratch
+// chunked layouts from plain arrays (device pointers)
+int map_prepare_guess(Ctx& c, int fam, double per, const double* x, const double* y, const double* alpha, long n, double* gch);
+int map_prepare_sympl(Ctx& c, int fam, double per, const double* x, const double* y, const double* alpha, long n, double* tch);
+// a.ticket / a.slice_done / a.slice_steps are filled in by map_launch from `sched` (map_sched_bytes(E) bytes)
+int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched);
 
 }  // namespace sgp

@@ -39,45 +39,6 @@ struct LLArgs {
     int* abort;
 };
 
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity)
-{
-    uint32_t ok;
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-        "selp.u32 %0, 1, 0, p;\n"
-        "}\n"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    return ok != 0u;
-}
-// returns when the phase completes, or early once the abort word is set
-__device__ __forceinline__ void mbar_wait_ab(unsigned long long* bar, uint32_t parity, const volatile int* abort)
-{
-    uint32_t spins = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++spins & 15u) == 0u && *abort) return;
-    }
-}
-__device__ __forceinline__ int ld_acquire(const int* p)
-{
-    int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release(int* p, int v)
-{
-    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
-    return t;
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;\n" ::: "memory"); }
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(LL_CONSUMERS) : "memory"); }
 
 // one lane spins until the tile's ready flag is set (or abort)

@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--n-train", type=int, default=16384, help="training pairs N (matrix order 2N)")
     ap.add_argument("--map-train", type=int, default=4096, help="training pairs of the map leg (config 04_standard_map)")
     ap.add_argument("--orbits", type=int, default=100000, help="orbits per GPU in the map leg")
-    ap.add_argument("--map-steps", type=int, default=20, help="map steps per launch in the map leg")
+    ap.add_argument("--map-steps", type=int, default=64, help="map steps per launch in the map leg")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="training pairs of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-map", action="store_true")

@@ -400,7 +400,7 @@ static void model_args(const sgp_model* m, MapArgs& a)
 {
     a.gch = m->gch; a.nchg = m->nchg; a.tch = m->tch; a.ncht = m->ncht;
     a.h = m->h; a.hp = m->hp;
-    a.pdstate = nullptr; a.ticket = nullptr; a.slice_done = nullptr; a.slice_steps = 1;
+    a.pdstate = nullptr; a.ticket = nullptr; a.slots = nullptr; a.progress = nullptr; a.slice_steps = 1;
 }
 
 int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solver, long nsteps, long E, const double* d_q0,

@@ -66,6 +66,39 @@ __host__ __device__ inline double compute_r_dev(double pth, double th, double rs
 
 enum SweepMode : int { SW_GUESS = 0, SW_F_DF = 1, SW_F = 2, SW_DQ = 3 };
 
+// 2^(j/64), j = 0..63, correctly rounded (filled by the host on first launch; copied to shared memory per block)
+__constant__ double c_exp2_tab[64];
+
+// exp(x) for x <= 0 in the sweeps: N = round(64 x / ln2) = 64 k + j, r = x - N ln2/64 (two-term
+// Cody-Waite, |r| <= ln2/128), exp(x) = 2^k * T[j] * (1 + q), q = e^r - 1 by a degree-5 polynomial;
+// T from a 64-entry table in shared memory.  About 12 DP instructions and one LDS, against 21 for the
+// table-free exp_neg of forms.cuh; relative error < 1.2 ulp.  Arguments below -700 are clamped (the
+// result, < 1e-304, stands for a true value that is smaller still); the sweeps never pass NaN (dead
+// orbits are masked out before).
+__device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict__ tab)
+{
+    const double C = 92.33248261689366;             // 64 / ln 2
+    const double SHIFT = 6755399441055744.0;        // 1.5 * 2^52
+    const double L_HI = 0.010830424695086549;       // ln2/64, low 20 mantissa bits zero
+    const double L_LO = 1.162596423439437e-12;
+    // clamp to >= -700 (x <= 0: the order of magnitudes is the unsigned order of the high words)
+    const unsigned hic = min((unsigned)__double2hiint(x), 0xC085E000u);
+    const double xc = __hiloint2double((int)hic, __double2loint(x));
+    const double t = fma(xc, C, SHIFT);
+    const int N = __double2loint(t);
+    const double kd = t - SHIFT;
+    double r = fma(kd, -L_HI, xc);
+    r = fma(kd, -L_LO, r);
+    double q = fma(r, 8.3333333333333332e-03, 4.1666666666666664e-02);
+    q = fma(q, r, 1.6666666666666666e-01);
+    q = fma(q, r, 0.5);
+    q = fma(q, r, 1.0);
+    q = q * r;
+    const double T = tab[N & 63];
+    double res = fma(T, q, T);
+    return __hiloint2double(__double2hiint(res) + ((N >> 6) << 20), __double2loint(res));
+}
+
 // per-warp chunk stream: two buffers, one mbarrier each; `seq` counts the chunks consumed so far
 struct Stream {
     double* buf;                 // 2 * MAP_BUF_DOUBLES
@@ -79,15 +112,68 @@ __device__ __forceinline__ void stream_issue(const Stream& s, uint32_t slot, con
     bulk_g2s(s.buf + slot * MAP_BUF_DOUBLES, src, bytes, s.bar + slot);
 }
 
+// Accumulators of one sweep: two interleaved partial sums (even / odd training points) of up to four
+// weighted sums; what they mean depends on the mode (see the end of sweep()).
+struct Acc {
+    double a0, a1, b0, b1, c0, c1, d0, d1;
+};
+
+// One training point against the lane's query point b, product (periodic x SE) and SE x SE families,
+// with every hyper-parameter factor pulled out of the sum (they are applied once at the end of sweep()):
+//   E = exp(-dy^2 hy - s^2 hx),  bxx = lx^2 cos(2 p dx) - s^2 c^2 | lx^2 - dx^2,  odd = s c | dx
+//   F    = sig        (cxx sum E bxx aq         - cxy sum E dy odd aP)            kernels.f90:58-94
+//   dF   = sig / ly^2 (cxx sum E dy bxx aq      + cxy sum E (ly^2 - dy^2) odd aP) kernels.f90:95-132
+//   dq   = sig        (cyy sum E (ly^2-dy^2) aP - cxy sum E dy odd aq)
+//   pg   = sigp sum E alpha                                                        kernels.f90:1-11
+template <int FAM, int MODE>
+__device__ __forceinline__ void point_eval(double au, double av, double ay, double w0, double w1, const Pt& b, double nhx,
+                                           double nhy, double lx2, double ly2, const double* __restrict__ tab, double& A,
+                                           double& B, double& C, double& D)
+{
+    const double dy = ay - b.y;
+    double s, odd, bxx;
+    if (FAM == FAM_SQ) {
+        s = au - b.u;
+        odd = s;
+        bxx = fma(-s, s, lx2);
+    } else {
+        s = fma(au, b.v, -(av * b.u));
+        const double c = fma(av, b.v, au * b.u);
+        odd = s * c;
+        const double s2 = s * s;
+        bxx = fma(lx2, fma(-2.0, s2, 1.0), -(odd * odd));
+    }
+    const double E = exp_neg_tab(fma(s * s, nhx, (dy * dy) * nhy), tab);
+    if (MODE == SW_GUESS) {
+        A = fma(E, w0, A);
+    } else if (MODE == SW_F_DF || MODE == SW_F) {
+        const double ea = E * (bxx * w0);        // E bxx aq
+        const double eb = E * (odd * w1);        // E odd aP
+        A += ea;
+        B = fma(dy, eb, B);
+        if (MODE == SW_F_DF) {
+            C = fma(dy, ea, C);
+            D = fma(fma(-dy, dy, ly2), eb, D);
+        }
+    } else {
+        const double eb = E * (odd * w0);        // E odd aq
+        A = fma(fma(-dy, dy, ly2) * E, w1, A);   // E (ly^2 - dy^2) aP
+        B = fma(dy, eb, B);
+    }
+}
+
 // One sweep of the warp over a whole training set (nch chunks of NF fields); the first two chunks are
 // already in flight.  While chunk c is evaluated, chunk c+2 is fetched -- for the last two chunks that
-// is chunk 0/1 of the set the NEXT sweep will read (nxt, NXF fields).
+// is chunk 0/1 of the set the NEXT sweep will read (nxt, nxf fields).
 template <int FAM, int MODE>
 __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set, int nch, const double* __restrict__ nxt, int nxf,
-                                      int lane, const Pt& b, const HypC& h, bool active, double& o0, double& o1)
+                                      int lane, const Pt& b, const HypC& h, const double* __restrict__ tab, bool active,
+                                      double& o0, double& o1)
 {
     constexpr int NF = (MODE == SW_GUESS) ? MAP_GF : MAP_TF;
-    double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+    Acc z;
+    z.a0 = z.a1 = z.b0 = z.b1 = z.c0 = z.c1 = z.d0 = z.d1 = 0.0;
+    const double nhx = -h.hx, nhy = -h.hy, lx2 = h.lx2, ly2 = h.ly2;
     const bool any = __any_sync(0xffffffffu, active);
     for (int c = 0; c < nch; c++) {
         const uint32_t slot = st.seq & 1u, par = (st.seq >> 1) & 1u;
@@ -100,25 +186,30 @@ __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set
                 const double2 v2 = *reinterpret_cast<const double2*>(sm + 1 * MAP_CHUNK + j);
                 const double2 y2 = *reinterpret_cast<const double2*>(sm + 2 * MAP_CHUNK + j);
                 const double2 a2 = *reinterpret_cast<const double2*>(sm + 3 * MAP_CHUNK + j);
-                Pt p0, p1;
-                p0.u = u2.x; p0.v = v2.x; p0.y = y2.x;
-                p1.u = u2.y; p1.v = v2.y; p1.y = y2.y;
-                const Pair<FAM> q0(p0, b, h), q1(p1, b, h);
-                if (MODE == SW_GUESS) {
-                    s0 += q0.k() * a2.x;
-                    s1 += q1.k() * a2.y;
+                double2 c2 = make_double2(0.0, 0.0);
+                if (MODE != SW_GUESS) c2 = *reinterpret_cast<const double2*>(sm + 4 * MAP_CHUNK + j);
+                if (FAM != FAM_SUM) {
+                    point_eval<FAM, MODE>(u2.x, v2.x, y2.x, a2.x, c2.x, b, nhx, nhy, lx2, ly2, tab, z.a0, z.b0, z.c0, z.d0);
+                    point_eval<FAM, MODE>(u2.y, v2.y, y2.y, a2.y, c2.y, b, nhx, nhy, lx2, ly2, tab, z.a1, z.b1, z.c1, z.d1);
                 } else {
-                    const double2 c2 = *reinterpret_cast<const double2*>(sm + 4 * MAP_CHUNK + j);
-                    if (MODE == SW_F_DF || MODE == SW_F) {
-                        s0 += q0.kxx(h) * a2.x + q0.kxy(h) * c2.x;
-                        s1 += q1.kxx(h) * a2.y + q1.kxy(h) * c2.y;
+                    // sum family (kernels_expl_per_q_sq_p.f90): generic closed forms; a0/a1 = value, c0/c1 = derivative
+                    Pt p0, p1;
+                    p0.u = u2.x; p0.v = v2.x; p0.y = y2.x;
+                    p1.u = u2.y; p1.v = v2.y; p1.y = y2.y;
+                    const Pair<FAM> q0(p0, b, h), q1(p1, b, h);
+                    if (MODE == SW_GUESS) {
+                        z.a0 += q0.k() * a2.x;
+                        z.a1 += q1.k() * a2.y;
+                    } else if (MODE == SW_F_DF || MODE == SW_F) {
+                        z.a0 += q0.kxx(h) * a2.x + q0.kxy(h) * c2.x;
+                        z.a1 += q1.kxx(h) * a2.y + q1.kxy(h) * c2.y;
                         if (MODE == SW_F_DF) {
-                            t0 += q0.kxx_yb(h) * a2.x + q0.kxy_yb(h) * c2.x;
-                            t1 += q1.kxx_yb(h) * a2.y + q1.kxy_yb(h) * c2.y;
+                            z.c0 += q0.kxx_yb(h) * a2.x + q0.kxy_yb(h) * c2.x;
+                            z.c1 += q1.kxx_yb(h) * a2.y + q1.kxy_yb(h) * c2.y;
                         }
                     } else {
-                        s0 += q0.kxy(h) * a2.x + q0.kyy(h) * c2.x;
-                        s1 += q1.kxy(h) * a2.y + q1.kyy(h) * c2.y;
+                        z.a0 += q0.kxy(h) * a2.x + q0.kyy(h) * c2.x;
+                        z.a1 += q1.kxy(h) * a2.y + q1.kyy(h) * c2.y;
                     }
                 }
             }
@@ -130,8 +221,20 @@ __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set
         }
         st.seq++;
     }
-    o0 = h.sig * (s0 + s1);
-    o1 = h.sig * (t0 + t1);
+    const double A = z.a0 + z.a1, B = z.b0 + z.b1, C = z.c0 + z.c1, D = z.d0 + z.d1;
+    if (FAM == FAM_SUM) {
+        o0 = h.sig * A;
+        o1 = h.sig * C;
+    } else if (MODE == SW_GUESS) {
+        o0 = h.sig * A;
+        o1 = 0.0;
+    } else if (MODE == SW_F_DF || MODE == SW_F) {
+        o0 = h.sig * (h.cxx * A - h.cxy * B);
+        o1 = h.sig * h.ily2 * (h.cxx * C + h.cxy * D);
+    } else {
+        o0 = h.sig * (h.cyy * A - h.cxy * B);
+        o1 = 0.0;
+    }
 }
 
 template <int FAM, int SOLVER>
@@ -140,6 +243,9 @@ map_kernel(MapArgs a)
 {
     __shared__ __align__(16) double s_buf[MAP_WARPS][2 * MAP_BUF_DOUBLES];
     __shared__ unsigned long long s_bar[MAP_WARPS][2];
+    __shared__ double s_tab[64];
+    if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    __syncthreads();                                         // the only block-wide barrier: before any work
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Stream st;
     st.buf = s_buf[warp];
@@ -162,30 +268,40 @@ map_kernel(MapArgs a)
     const unsigned long long nitems = (unsigned long long)nbatches * (unsigned long long)nslices;
     unsigned long long evals = 0ull;
     unsigned int fails = 0u;
-    volatile unsigned long long* verr = a.ticket + 1;      // scheduler error word (dependency wait timed out)
+    volatile unsigned long long* verr = a.ticket + 1;      // scheduler error word (a queue wait timed out)
 
     for (;;) {
+        // ---- pop the next work item from the FIFO of runnable batches --------------------------------
+        // Position t of the queue is claimed with one atomic; positions 0..nbatches-1 are the batches in
+        // their initial state, later positions are filled (in completion order) by warps that finished a
+        // slice of a batch with steps left.  A claimed position that is not filled yet means there is no
+        // runnable work at the moment (tail of the launch): wait for the push.
         unsigned long long tk = 0ull;
         if (lane == 0) tk = atomicAdd(a.ticket, 1ull);
         tk = __shfl_sync(0xffffffffu, tk, 0);
         if (tk >= nitems) break;
-        const long batch = (long)(tk % (unsigned long long)nbatches);
-        const long slice = (long)(tk / (unsigned long long)nbatches);
-        // the previous slice of these orbits must be finished (its state is in qfinal/pfinal)
-        if (slice > 0) {
-            int ok = 1;
-            if (lane == 0) {
+        long batch = (long)tk, slice = 0;
+        int ok = 1;
+        if (lane == 0) {
+            unsigned long long* slot = a.slots + (tk % (unsigned long long)nbatches);
+            if (tk >= (unsigned long long)nbatches) {
                 const unsigned long long t0 = globaltimer();
                 unsigned n = 0;
-                while (ld_acquire(a.slice_done + batch) < (int)slice) {
+                unsigned long long v;
+                while (((v = ld_acquire_u64(slot)) >> 32) != ((tk + 1ull) & 0xffffffffull) || (unsigned)v == 0xffffffffu) {
                     __nanosleep(200);
                     if ((++n & 255u) == 0u && (*verr != 0ull || globaltimer() - t0 > 20000000000ull)) { ok = 0; break; }
                 }
-                if (!ok) atomicExch(a.ticket + 1, 1ull);
+                batch = (long)(unsigned)v;
+                if (ok) slice = a.progress[batch];
             }
-            ok = __shfl_sync(0xffffffffu, ok, 0);
-            if (!ok) break;
+            if (ok) st_release_u64(slot, ((tk + 1ull) << 32) | 0xffffffffull);      // consumed: the slot may be refilled
+            else atomicExch(a.ticket + 1, 1ull);
         }
+        ok = __shfl_sync(0xffffffffu, ok, 0);
+        if (!ok) break;
+        batch = __shfl_sync(0xffffffffu, batch, 0);
+        slice = __shfl_sync(0xffffffffu, slice, 0);
         const long k = batch * 32 + lane;
         const bool mine = k < a.E;
         double q = 0.0, p = 0.0, pd = 0.0;
@@ -210,7 +326,7 @@ map_kernel(MapArgs a)
             if (alive) { b = make_pt<FAM>(q, p, a.h.p); } else { b.u = 0; b.v = 1; b.y = 0; }
 
             double pg, dummy;
-            sweep<FAM, SW_GUESS>(st, a.gch, a.nchg, a.tch, MAP_TF, lane, b, a.hp, alive, pg, dummy);
+            sweep<FAM, SW_GUESS>(st, a.gch, a.nchg, a.tch, MAP_TF, lane, b, a.hp, s_tab, alive, pg, dummy);
             if (alive && !(fabs(pg) <= DBL_MAX)) alive = false;
 
             double P;
@@ -222,7 +338,7 @@ map_kernel(MapArgs a)
                     const bool run = !sv.done();
                     b.y = sv.query();
                     double F, dF;
-                    sweep<FAM, SW_F>(st, a.tch, a.ncht, a.tch, MAP_TF, lane, b, a.h, run, F, dF);
+                    sweep<FAM, SW_F>(st, a.tch, a.ncht, a.tch, MAP_TF, lane, b, a.h, s_tab, run, F, dF);
                     if (run) { sv.feed(F - p + b.y); evals++; }
                 }
                 P = sv.root();
@@ -235,7 +351,7 @@ map_kernel(MapArgs a)
                     const bool run = !sv.done();
                     b.y = sv.query();
                     double F, dF;
-                    sweep<FAM, SW_F_DF>(st, a.tch, a.ncht, a.tch, MAP_TF, lane, b, a.h, run, F, dF);
+                    sweep<FAM, SW_F_DF>(st, a.tch, a.ncht, a.tch, MAP_TF, lane, b, a.h, s_tab, run, F, dF);
                     if (run) { sv.feed(F - p + b.y, 1.0 + dF); evals++; }
                 }
                 P = sv.root();
@@ -257,7 +373,7 @@ map_kernel(MapArgs a)
             const bool qalive = alive && (Pst == Pst);
             b.y = Pst;
             double dq;
-            sweep<FAM, SW_DQ>(st, a.tch, a.ncht, a.gch, MAP_GF, lane, b, a.h, qalive, dq, dummy);
+            sweep<FAM, SW_DQ>(st, a.tch, a.ncht, a.gch, MAP_GF, lane, b, a.h, s_tab, qalive, dq, dummy);
             if (qalive) evals++;
             double qn;
             if (!qalive) qn = nan("");
@@ -280,9 +396,22 @@ map_kernel(MapArgs a)
             if (a.pdstate) a.pdstate[k] = pd;
         }
         if (slice + 1 < nslices) {
+            // ---- push the batch back: its state is in qfinal/pfinal, progress = slices done ------------
             __threadfence();
             __syncwarp();
-            if (lane == 0) st_release(a.slice_done + batch, (int)slice + 1);
+            if (lane == 0) {
+                a.progress[batch] = (int)slice + 1;
+                const unsigned long long pt = (unsigned long long)nbatches + atomicAdd(a.ticket + 2, 1ull);
+                unsigned long long* slot = a.slots + (pt % (unsigned long long)nbatches);
+                const unsigned long long want = ((pt - (unsigned long long)nbatches + 1ull) << 32) | 0xffffffffull;
+                const unsigned long long t0 = globaltimer();
+                unsigned n = 0;
+                while (ld_acquire_u64(slot) != want) {       // previous occupant of the slot not consumed yet (rare)
+                    __nanosleep(100);
+                    if ((++n & 255u) == 0u && (*verr != 0ull || globaltimer() - t0 > 20000000000ull)) { atomicExch(a.ticket + 1, 1ull); break; }
+                }
+                st_release_u64(slot, ((pt + 1ull) << 32) | (unsigned long long)(unsigned)batch);
+            }
         }
     }
 
@@ -318,7 +447,7 @@ size_t map_model_doubles(long np, long nt)
 size_t map_sched_bytes(long E)
 {
     const size_t nb = (size_t)((E + 31) / 32);
-    return 16 + (nb + 4) * sizeof(int);
+    return 4 * sizeof(unsigned long long) + nb * sizeof(unsigned long long) + (nb + 4) * sizeof(int);
 }
 
 template <int FAM, int NF>
@@ -361,13 +490,28 @@ int map_prepare_sympl(Ctx& c, int fam, double per, const double* x, const double
     return ST_OK;
 }
 
+static int init_exp_table()
+{
+    static bool done[64] = {};
+    int dev = 0;
+    SGP_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || done[dev]) return ST_OK;
+    double tab[64];
+    for (int j = 0; j < 64; j++) tab[j] = (double)exp2l((long double)j / 64.0L);
+    SGP_CUDA(cudaMemcpyToSymbol(c_exp2_tab, tab, sizeof(tab)));
+    done[dev] = true;
+    return ST_OK;
+}
+
 int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched)
 {
     if (a.E <= 0) return ST_OK;
+    SGP_TRY(init_exp_table());
     const long nbatches = (a.E + 31) / 32;
     SGP_CUDA(cudaMemsetAsync(sched, 0, map_sched_bytes(a.E), c.stream));
     a.ticket = (unsigned long long*)sched;
-    a.slice_done = (int*)((char*)sched + 16);
+    a.slots = a.ticket + 4;
+    a.progress = (int*)(a.slots + nbatches);
     // work items of about 1/16 of the step loop, 1..16 steps each: enough items to balance the tail
     long ss = a.nsteps / 16;
     if (ss < 1) ss = 1;

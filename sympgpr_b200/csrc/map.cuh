@@ -30,10 +30,12 @@ struct MapArgs {
     double *qfinal, *pfinal;         // last state; also carries the state from one work item to the next
     double* pdstate;                 // running pdiff between work items (only when pdiff != nullptr)
     unsigned long long* stats;       // [0] residual evaluations, [1] solver exits without convergence
-    // work distribution: item t = (batch t % nbatches of 32 orbits, slice t / nbatches of slice_steps steps)
+    // work distribution: a work item is slice_steps steps of one batch of 32 orbits; runnable batches wait
+    // in a FIFO (map.cu).  All of it is zeroed before launch.
     long slice_steps;
-    unsigned long long* ticket;      // [0] work counter, [1] scheduler error word; zeroed before launch
-    int* slice_done;                 // nbatches ints, zeroed before launch
+    unsigned long long* ticket;      // [0] pop counter, [1] scheduler error word, [2] push counter
+    unsigned long long* slots;       // nbatches queue slots: (position + 1) << 32 | batch, or ... | 0xffffffff once consumed
+    int* progress;                   // nbatches: slices already done
 };
 
 long map_chunks(long n);                                   // chunks a set of n points occupies
@@ -42,7 +44,7 @@ size_t map_sched_bytes(long E);                            // ticket + slice_don
 // chunked layouts from plain arrays (device pointers)
 int map_prepare_guess(Ctx& c, int fam, double per, const double* x, const double* y, const double* alpha, long n, double* gch);
 int map_prepare_sympl(Ctx& c, int fam, double per, const double* x, const double* y, const double* alpha, long n, double* tch);
-// a.ticket / a.slice_done / a.slice_steps are filled in by map_launch from `sched` (map_sched_bytes(E) bytes)
+// a.ticket / a.slots / a.progress / a.slice_steps are filled in by map_launch from `sched` (map_sched_bytes(E) bytes)
 int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched);
 
 }  // namespace sgp

@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--n-train", type=int, default=16384, help="training pairs N (matrix order 2N)")
     ap.add_argument("--map-train", type=int, default=4096, help="training pairs of the map leg (config 04_standard_map)")
     ap.add_argument("--orbits", type=int, default=100000, help="orbits per GPU in the map leg")
-    ap.add_argument("--map-steps", type=int, default=64, help="map steps per launch in the map leg")
+    ap.add_argument("--map-steps", type=int, default=1000, help="map steps per launch in the map leg (config 04: 1000)")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="training pairs of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-map", action="store_true")
@@ -309,36 +309,53 @@ def main():
                                       Nt, dp(np.ascontiguousarray(xt[:Nt])), dp(np.ascontiguousarray(xt[Nt:])), dp(fm["alpha"]),
                                       Nt, ctypes.byref(model)), "sgp_model_create")
 
-        def map_run(solver):
-            _lib.check(L.sgp_model_applymap_dev(ctx.handle, model, 2, solver, a.map_steps, E, q0.data_ptr(), p0.data_ptr(),
+        def map_run(solver, steps):
+            _lib.check(L.sgp_model_applymap_dev(ctx.handle, model, 2, solver, steps, E, q0.data_ptr(), p0.data_ptr(),
                                                 qf.data_ptr(), pf.data_ptr(), None, None, 0, stats.data_ptr()),
                        "sgp_model_applymap_dev")
-        map_run(1)
+        map_run(1, 8)                                   # warm-up
         sync_all()
         stats.zero_()
         m0, m1 = ev(), ev()
-        m0.record(stream); map_run(1); m1.record(stream)
+        m0.record(stream); map_run(1, a.map_steps); m1.record(stream)
         sync_all()
         t_map = max_over_ranks(m0.elapsed_time(m1) * 1e-3)
         st = stats.clone()
-        cks = torch.stack([qf.sum(), pf.sum()])
+        cks = torch.stack([torch.nansum(qf), torch.nansum(pf)])
         if world > 1:                                   # the only collectives of the path: gather statistics
             dist.all_reduce(st, op=dist.ReduceOp.SUM)
             dist.all_reduce(cks, op=dist.ReduceOp.SUM)
         evals = int(st[0].item())
         orbit_steps = float(E) * world * a.map_steps
-        # same launch with the reference's own solver (MINPACK hybrd1) for comparison
+        # the reference's own solver (MINPACK hybrd1) for comparison, on a shorter run
+        hsteps = min(a.map_steps, 50)
         stats.zero_()
         h0, h1 = ev(), ev()
-        h0.record(stream); map_run(0); h1.record(stream)
+        h0.record(stream); map_run(0, hsteps); h1.record(stream)
         sync_all()
         t_map_h = max_over_ranks(h0.elapsed_time(h1) * 1e-3)
+        # end to end through the public API: host arrays in, final states out (model staging, H2D of the
+        # initial conditions and D2H of the result inside the timed region)
+        q0_h, p0_h = q0_all[rank::world].copy(), p0_all[rank::world].copy()
+        sync_all()
+        t0 = time.perf_counter()
+        out = api.applymap_standard(a.map_steps + 1, E, hm[:3], hpm[:3], q0_h, p0_h, xtp, None, None, xt, None, None,
+                                    solver="newton", alphap=fpm["alpha"], alpha=fm["alpha"], out_every=0, want_pdiff=False)
+        t_map_e2e = max_over_ranks(time.perf_counter() - t0)
         pair_evals = (Nt + evals / orbit_steps * Nt)      # per orbit-step: guess sweep + solver/dq sweeps
+        dp_instr = 34.0                                   # DP instructions per pair evaluation (SASS of the F/dF sweep)
+        fp64_peak = 148 * 64 * 1.965e9                    # thread-level DP instructions/s: SMs x FP64 lanes x max SM clock
         map_info = {"metric": "orbit_map_steps_per_s", "value": orbit_steps / t_map, "unit": "orbit-steps/s",
                     "solver": "newton", "n_train": Nt, "orbits_total": E * world, "steps": a.map_steps,
                     "sweeps_per_orbit_step": 1 + evals / orbit_steps,
                     "pair_evals_per_s": orbit_steps * pair_evals / t_map,
-                    "hybrd_value": orbit_steps / t_map_h, "unconverged": int(st[1].item()),
+                    "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe",
+                                 "achieved": orbit_steps * pair_evals * dp_instr / t_map / world, "peak": fp64_peak,
+                                 "unit": "DP instr/s per GPU", "frac": orbit_steps * pair_evals * dp_instr / t_map / world / fp64_peak},
+                    "e2e": {"value": orbit_steps / t_map_e2e, "unit": "orbit-steps/s",
+                            "h2d_bytes_per_step": int(16 * E + 8 * (3 * Nt + 4 * Nt)), "d2h_bytes_per_step": int(16 * E)},
+                    "hybrd_value": float(E) * world * hsteps / t_map_h, "hybrd_steps": hsteps,
+                    "unconverged": int(st[1].item()),
                     "checksum": [float(cks[0].item()), float(cks[1].item())]}
         L.sgp_model_destroy(model)
 

@@ -42,10 +42,15 @@ extern "C" {
 #define SGP_MAP_HENON    1  /* python/functions/func.py:239-260                       */
 #define SGP_MAP_STANDARD 2  /* python/04_standard_map/func.py:218-254                 */
 #define SGP_MAP_TOKAMAK  3  /* python/05_tokamak/SympGPR/func.py:182-211              */
+#define SGP_MAP_TOKAMAK_SPLIT 5  /* python/05_tokamak/Split_SympGPR/func.py:184-219 (sgp_applymap_split) */
+#define SGP_MAP_STANDARD_EXPL 4 /* applymap_expl python/04_standard_map/func.py:256-285: p wrapped, pdiff, q NOT wrapped */
 
 /* root solver of the implicit equation (argument `solver`) */
 #define SGP_SOLVER_HYBRD  0 /* MINPACK hybrd1, n = 1, tol 1e-13 (sympgpr.f90:107)     */
 #define SGP_SOLVER_NEWTON 1 /* Newton with the analytic derivative, same tolerance   */
+#define SGP_SOLVER_EXPLICIT 2 /* no root solve: P = p - F_q(q, p); the explicit maps calcP_expl
+                               * python/04_standard_map/func.py:174-179, python/01_pendulum/explicit/func_expl.py:107-127
+                               * (the guess-GP arguments are ignored and may be empty) */
 
 /* layout of the 16-double result block of the NLL entry points */
 #define SGP_RES_NLL   0     /* 0.5 y'alpha + sum log diag L                           */
@@ -121,7 +126,9 @@ int sgp_applymap_tok(sgp_ctx* ctx, int fam, double per, int solver, int kind, lo
 /* ---- batched entry points (additive; what func.py's nll_* / main.py's inv() collapse into) -- */
 /* nll_chol / nll_chol_reg / nll_grad / nll_grad_reg: python/05_tokamak/SympGPR/func.py:134-168,
  * python/02_pert_pendulum/func.py:132-162.  xin = [x(0:N); y(0:N)], z = observations (n),
- * hyp4 = [lx, ly, sig, sig2n]; reg = 0: derivative kernel, n = 2N; reg = 1: plain kernel, n = N.
+ * hyp4 = [lx, ly, sig, sig2n]; reg = 0: derivative kernel, n = 2N; reg = 1: plain kernel, n = N;
+ * reg = 2 / 3: the (q,q) / (P,P) Hessian block alone, n = N, value only -- nll_expl
+ * python/04_standard_map/func.py:126-141 (the sum kernel's matrix is block diagonal and is fitted per block).
  * ngrad = 0 value only, 2 or 3 also the gradient.  res: SGP_RES_LEN doubles. */
 int sgp_nll(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* xin,
             const double* z, long n, int ngrad, double* res);
@@ -144,6 +151,17 @@ int sgp_applymap(sgp_ctx* ctx, int kind, int fam, double per, int solver, long n
                  const double* xtrain, const double* ytrain, const double* alpha, long nt,
                  double* qmap, double* pmap, double* pdiff, long out_every,
                  double* qfinal, double* pfinal, unsigned long long* stats);
+
+/* Split map: nmodels learned maps (one per toroidal section) applied in turn, step s with map (s-1) mod nmodels;
+ * loss test at the new angle, lost orbits NaN in q and p -- applymap_tok
+ * python/05_tokamak/Split_SympGPR/func.py:184-219.  All sub-maps have np / nt training pairs; every model
+ * array holds them one after the other (hyp3, hypp3: 3 each; xtrainp, ytrainp, alphap: np each; xtrain,
+ * ytrain: nt each; alpha: 2 nt each).  qmap/pmap: (nsteps + 1, E) C order, row 0 = initial conditions. */
+int sgp_applymap_split(sgp_ctx* ctx, int fam, double per, int solver, int nmodels, long nsteps, long E,
+                       const double* q0, const double* p0, const double* hyp3, const double* hypp3,
+                       const double* xtrainp, const double* ytrainp, const double* alphap, long np,
+                       const double* xtrain, const double* ytrain, const double* alpha, long nt,
+                       double* qmap, double* pmap, unsigned long long* stats);
 
 /* Device-resident model + ensemble for repeated launches (bench, multi-GPU shards). */
 int sgp_model_create(sgp_ctx* ctx, int fam, double per, const double* hyp3, const double* hypp3,

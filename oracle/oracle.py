@@ -306,6 +306,93 @@ def calcp(x, y, hyp, hypp, xtrainp, ytrainp, ztrainp, kyinvp, xtrain, ytrain, zt
     return float(sol[0])
 
 
+def calcp_expl(x, y, hyp, xtrain, ytrain, ztrain, kyinv, family="sum", p=0.5):
+    """Explicit map, momentum step: P = p - F_q(q, p) with the generating function taken at the OLD momentum.
+    calcP_expl python/04_standard_map/func.py:174-179 (returns -pGP[0] + y); calcP
+    python/01_pendulum/explicit/func_expl.py:107-112 (returns -pGP[0], added to p by its caller :121)."""
+    Kstar = build_k_vec(np.atleast_1d(x), np.atleast_1d(y), xtrain, ytrain, hyp, family, p)
+    return float(y) - float(Kstar[0, :].dot(np.asarray(kyinv, float).dot(ztrain)))
+
+
+def applymap_expl(variant, nm, q0, p0, hyp, xtrain, ytrain, ztrain, kyinv, family="sum", p=0.5):
+    """Explicit ensemble loops.  variant "standard": applymap_expl python/04_standard_map/func.py:256-285
+    (pdiff, p = mod(P, 2pi), q = q + dq NOT wrapped) -> (qmap, pmap, pdiff); variant "pendulum": applymap
+    python/01_pendulum/explicit/func_expl.py:114-128 (q = mod(q + dq, 2pi), p not wrapped) -> (qmap, pmap)."""
+    q0 = np.asarray(q0, float); p0 = np.asarray(p0, float)
+    E = len(q0)
+    pmap = np.zeros((nm, E)); qmap = np.zeros((nm, E)); pdiff = np.zeros((nm, E))
+    pmap[0] = p0; qmap[0] = q0; pdiff[0] = p0
+    for i in range(nm - 1):
+        for k in range(E):
+            pmap[i + 1, k] = calcp_expl(qmap[i, k], pmap[i, k], hyp, xtrain, ytrain, ztrain, kyinv, family, p)
+            if variant == "standard":
+                pdiff[i + 1, k] = pdiff[i, k] + (pmap[i + 1, k] - pmap[i, k])
+                pmap[i + 1, k] = np.mod(pmap[i + 1, k], TWO_PI)
+        for k in range(E):
+            if np.isnan(pmap[i + 1, k]):
+                qmap[i + 1, k] = np.nan
+            else:
+                dq = calcq(qmap[i, k], pmap[i + 1, k], xtrain, ytrain, hyp, kyinv, ztrain, family, p)
+                qmap[i + 1, k] = dq + qmap[i, k] if variant == "standard" else np.mod(dq + qmap[i, k], TWO_PI)
+    if variant == "standard":
+        return qmap, pmap, pdiff
+    return qmap, pmap
+
+
+def applymap_tok_split(nphmap, nm, q0, p0, xtrainp, ztrainp, kyinvp, hypp, xtrain, ztrain, kyinv, hyp, family="product", p=0.5):
+    """Split map, literal: applymap_tok python/05_tokamak/Split_SympGPR/func.py:184-219 (array layout of
+    python/05_tokamak/Split_SympGPR/main.py:91-112).  Whole turns only (`while i < nm - nphmap`); loss test at the
+    new angle with phi = 2 pi/nphmap mod(i+1, nphmap) (compute_r ignores it, fieldlines.f90:34-47)."""
+    q0 = np.asarray(q0, float); p0 = np.asarray(p0, float)
+    E = len(q0)
+    pmap = np.zeros((nm, E)); qmap = np.zeros((nm, E))
+    pmap[0] = p0; qmap[0] = q0
+    Np, Nt = xtrainp.shape[0] // 2, xtrain.shape[0] // 2
+    i = 0
+    while i < nm - nphmap:
+        for m in range(nphmap):
+            for k in range(E):
+                if np.isnan(pmap[i, k]):
+                    pmap[i + 1, k] = np.nan
+                else:
+                    pmap[i + 1, k] = calcp(qmap[i, k], pmap[i, k], hyp[m], hypp[m], xtrainp[:Np, m], xtrainp[Np:, m],
+                                           ztrainp[:, m], kyinvp[m], xtrain[:Nt, m], xtrain[Nt:, m], ztrain[:, m], kyinv[m],
+                                           family, p)
+            for k in range(E):
+                if np.isnan(pmap[i + 1, k]):
+                    qmap[i + 1, k] = np.nan
+                else:
+                    dq = calcq(qmap[i, k], pmap[i + 1, k], xtrain[:Nt, m], xtrain[Nt:, m], hyp[m], kyinv[m], ztrain[:, m],
+                               family, p)
+                    qmap[i + 1, k] = np.mod(dq + qmap[i, k], TWO_PI)
+                    ph = TWO_PI / nphmap * np.mod(i + 1, nphmap)
+                    zk = np.array([pmap[i + 1, k] * 1e-2, qmap[i + 1, k], ph])
+                    if compute_r(zk, 0.3) > 0.5 or pmap[i + 1, k] < 0.0:
+                        pmap[i + 1, k] = np.nan
+                        qmap[i + 1, k] = np.nan
+            i = i + 1
+    return qmap, pmap
+
+
+def nll_expl(hyp, x, y, n, ind, p=0.5):
+    """nll_expl python/04_standard_map/func.py:126-141: the sum kernel's matrix is block diagonal, so lx is
+    fitted on the (q,q) block with the first half of the observations (ind = 0) and ly on the (P,P) block
+    with the second half (ind = 1).  hyp = [l, sig, sig2n]; x = [q; P] (n values), y = the matching n/2
+    observations.  (The reference fills the whole n x n matrix with the other length-scale set to 0 and then
+    slices; only the block it keeps is finite, and only that block is formed here.)"""
+    N = n // 2
+    xq, xP = np.asarray(x[:N], float), np.asarray(x[N:2 * N], float)
+    l, sig, sig2n = float(hyp[0]), float(hyp[1]), float(hyp[2])
+    f = _fam("sum")
+    fn = f.d2kdxdx0_num if ind == 0 else f.d2kdydy0_num
+    # rows: x point (b), cols: x0 point (a) -- build_K_expl python/04_standard_map/func.py:104-124
+    K = sig * (fn(xq[None, :], xP[None, :], xq[:, None], xP[:, None], l, l) + np.zeros((N, N)))
+    Ky = K + abs(sig2n) * np.eye(N)
+    L = scipy.linalg.cholesky(Ky, lower=True)
+    alpha = solve_cholesky(L, np.asarray(y, float))
+    return float(0.5 * np.asarray(y, float).dot(alpha) + np.sum(np.log(np.diag(L))))
+
+
 # ------------------------------------------------------------------- M5 tokamak
 def compute_r(z, rstart=0.3):
     """fieldlines.f90:94-107 with f_r :82-91, Ath :34-39, dAthdr :42-47

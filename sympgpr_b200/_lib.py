@@ -25,8 +25,8 @@ RES_NLL, RES_DLX, RES_DLY, RES_DSIG, RES_INFO, RES_QUAD, RES_LOGD, RES_A, RES_B 
 E_BADARG, E_CUDA, E_NOMEM, E_NODEV = -1, -2, -3, -4
 
 FAMILIES = {"product": 0, "sq": 1, "sum": 2, "period": 0}
-MAP_KINDS = {"pendulum": 0, "henon": 1, "standard": 2, "tokamak": 3}
-SOLVERS = {"hybrd": 0, "newton": 1}
+MAP_KINDS = {"pendulum": 0, "henon": 1, "standard": 2, "tokamak": 3, "standard_expl": 4}
+SOLVERS = {"hybrd": 0, "newton": 1, "explicit": 2}
 
 _lib = None
 _lock = threading.Lock()
@@ -58,6 +58,8 @@ _PROTOS = {
     "sgp_fit": (c_i, [c_vp, c_i, c_d, c_i, c_dp, c_dp, c_dp, c_l, c_dp, c_dp, c_dp, c_dp]),
     "sgp_applymap": (c_i, [c_vp, c_i, c_i, c_d, c_i, c_l, c_l, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp,
                            c_dp, c_dp, c_l, c_dp, c_dp, c_dp, c_l, c_dp, c_dp, c_ullp]),
+    "sgp_applymap_split": (c_i, [c_vp, c_i, c_d, c_i, c_i, c_l, c_l, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp, c_dp,
+                                 c_dp, c_l, c_dp, c_dp, c_ullp]),
     "sgp_model_create": (c_i, [c_vp, c_i, c_d, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp, c_dp, c_dp, c_l,
                                ctypes.POINTER(c_vp)]),
     "sgp_model_destroy": (c_i, [c_vp]),

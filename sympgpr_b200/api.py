@@ -163,6 +163,18 @@ def nll_grad_reg(hyp, x, y, N, family="product", per=0.5):
     return float(r[RES_NLL]), np.array([r[RES_DLX], r[RES_DLX + 1]])
 
 
+def nll_expl(hyp, x, y, N, ind, family="sum", per=0.5):
+    """nll_expl(hyp=[l, sig, sig2n], x, y, N, ind) -- python/04_standard_map/func.py:126-141.
+
+    N is the order 2*len(y) of the full derivative-kernel matrix, x = [q; p] its N coordinates, y the N/2
+    observations of the block: ind = 0 fits lx on the (q,q) block, ind = 1 fits ly on the (P,P) block."""
+    hyp = as_f64(hyp).ravel()
+    if hyp.size != 3:
+        raise ValueError("nll_expl: hyp must be [l, sig, sig2n]")
+    h4 = np.array([hyp[0], hyp[0], hyp[1], hyp[2]])
+    return float(_nll(h4, x, y, int(N) // 2, 2 if int(ind) == 0 else 3, 0, family, per)[RES_NLL])
+
+
 def fit(hyp, x, z, n, reg=False, want_inverse=False, want_factor=False, family="product", per=0.5):
     """Model finalisation: alpha = (K + |sig2n| I)^-1 z [, Kyinv, L]; returns a dict."""
     hyp = as_f64(hyp).ravel()
@@ -286,6 +298,9 @@ def applymap_tok_f2py(hyp, hypp, q0map, p0map, xtrainp, ytrainp, ztrainp, kyinvp
 
 def _applymap(kind, nm, Ntest, l, hypp, Q0map, P0map, xtrainp, ztrainp, Kyinvp, xtrain, ztrain, Kyinv, family, per, solver,
               alphap=None, alpha=None, out_every=1, want_pdiff=False, return_stats=False):
+    if _solver(solver) == SOLVERS["explicit"]:
+        # no guess GP in the explicit maps: an empty ordinary-GP model
+        hypp, xtrainp, alphap = [1.0, 1.0, 1.0], np.zeros(0), np.zeros(0)
     hyp, hypp = _hyp3(l), _hyp3(hypp, "hypp")
     q0, p0 = as_f64(Q0map).ravel(), as_f64(P0map).ravel()
     E = int(Ntest)
@@ -349,6 +364,67 @@ def applymap_tok(nm, Ntest, l, hypp, Q0map, P0map, xtrainp, ztrainp, Kyinvp, xtr
     """python/05_tokamak/SympGPR/func.py:182-211 (NaN marks lost orbits)."""
     return _applymap("tokamak", nm, Ntest, l, hypp, Q0map, P0map, xtrainp, ztrainp, Kyinvp, xtrain, ztrain, Kyinv, family,
                      per, solver, **kw)
+
+
+def applymap_tok_split(nphmap, nm, Ntest, Q0map, P0map, xtrainp, ztrainp, Kyinvp, hypp, xtrain, ztrain, Kyinv, hyp,
+                       family="product", per=0.5, solver="hybrd", alphap=None, alpha=None, return_stats=False):
+    """applymap_tok(nphmap, nm, Ntest, Q0map, P0map, xtrainp, ztrainp, Kyinvp, hypp, xtrain, ztrain, Kyinv, hyp)
+    -> (qmap, pmap) -- python/05_tokamak/Split_SympGPR/func.py:184-219: nphmap learned maps applied in turn.
+
+    Array layout as in python/05_tokamak/Split_SympGPR/main.py:91-112: xtrainp (2N, nphmap), ztrainp (N, nphmap),
+    Kyinvp (nphmap, N, N), hypp (nphmap, 3), xtrain (2N, nphmap), ztrain (2N, nphmap), Kyinv (nphmap, 2N, 2N),
+    hyp (nphmap, 3).  Like the reference loop (`while i < nm - nphmap`, whole turns only) the last rows of the
+    (nm, Ntest) result stay zero when nm - 1 is not reached by whole turns."""
+    nph, nm, E = int(nphmap), int(nm), int(Ntest)
+    xtrainp, xtrain = np.asarray(xtrainp, float), np.asarray(xtrain, float)
+    ztrainp, ztrain = np.asarray(ztrainp, float), np.asarray(ztrain, float)
+    hyp, hypp = np.asarray(hyp, float).reshape(nph, 3), np.asarray(hypp, float).reshape(nph, 3)
+    np_, nt = xtrainp.shape[0] // 2, xtrain.shape[0] // 2
+    if alphap is None:
+        alphap = np.stack([np.asarray(Kyinvp[m], float).dot(ztrainp[:, m]) for m in range(nph)])
+    if alpha is None:
+        alpha = np.stack([np.asarray(Kyinv[m], float).dot(ztrain[:, m]) for m in range(nph)])
+    alphap, alpha = as_f64(alphap).reshape(nph, np_), as_f64(alpha).reshape(nph, 2 * nt)
+    q0, p0 = as_f64(Q0map).ravel()[:E], as_f64(P0map).ravel()[:E]
+    turns = -(-(nm - nph) // nph) if nm > nph else 0
+    nsteps = turns * nph
+    xp, yp = as_f64(xtrainp[:np_, :].T), as_f64(xtrainp[np_:2 * np_, :].T)          # (nph, np): sub-maps one after the other
+    xs, ys = as_f64(xtrain[:nt, :].T), as_f64(xtrain[nt:2 * nt, :].T)
+    qh, ph = np.zeros((nsteps + 1, E)), np.zeros((nsteps + 1, E))
+    stats = (ctypes.c_ulonglong * 2)()
+    st = _lib.lib().sgp_applymap_split(_lib.context().handle, _fam(family), per, _solver(solver), nph, nsteps, E, dptr(q0), dptr(p0),
+                                       dptr(as_f64(hyp)), dptr(as_f64(hypp)), dptr(xp), dptr(yp), dptr(alphap), np_, dptr(xs),
+                                       dptr(ys), dptr(alpha), nt, dptr(qh), dptr(ph), stats)
+    check(st, "applymap_tok_split")
+    qmap, pmap = np.zeros((nm, E)), np.zeros((nm, E))
+    qmap[0], pmap[0] = q0, p0
+    qmap[:nsteps + 1], pmap[:nsteps + 1] = qh, ph
+    if return_stats:
+        return qmap, pmap, dict(evaluations=int(stats[0]), unconverged=int(stats[1]))
+    return qmap, pmap
+
+
+def applymap_expl(nm, Ntest, l, Q0map, P0map, xtrain, ztrain, Kyinv, family="sum", per=0.5, **kw):
+    """applymap_expl(nm, Ntest, l, Q0map, P0map, xtrain, ztrain, Kyinv) -> (qmap, pmap, pdiff) --
+    python/04_standard_map/func.py:256-285: P = p - F_q(q, p) (calcP_expl :174-179), pdiff, p = mod(P, 2pi),
+    q = q + dq (not wrapped)."""
+    kw.setdefault("want_pdiff", True)
+    return _applymap("standard_expl", nm, Ntest, l, None, Q0map, P0map, None, None, None, xtrain, ztrain, Kyinv, family, per,
+                     "explicit", **kw)
+
+
+def applymap_expl_pendulum(l, Q0map, P0map, xtrain, ztrain, Kyinv, Ntest, nm, family="sum", per=0.5, **kw):
+    """applymap(l, Q0map, P0map, xtrain, ztrain, Kyinv, Ntest, nm) -> (qmap, pmap) --
+    python/01_pendulum/explicit/func_expl.py:114-128: p = p - F_q(q, p), q = mod(q + dq, 2pi)."""
+    return _applymap("pendulum", nm, Ntest, l, None, Q0map, P0map, None, None, None, xtrain, ztrain, Kyinv, family, per,
+                     "explicit", **kw)
+
+
+def calcP_expl(x, y, l, xtrain, ztrain, Kyinv, family="sum", per=0.5):
+    """calcP_expl(x, y, l, xtrain, ztrain, Kyinv) -- python/04_standard_map/func.py:174-179."""
+    out = _applymap("henon", 2, 1, l, None, [x], [y], None, None, None, xtrain, ztrain, Kyinv, family, per, "explicit",
+                    out_every=0)
+    return float(out[1][0])
 
 
 # --------------------------------------------------------------------------- scalar forms / fieldlines

@@ -18,11 +18,10 @@ struct sgp_model {
     int device = 0;
     int fam = 0;
     double per = 0.5;
-    HypC h, hp;
-    long np = 0, nt = 0;
-    DBuf buf;                       // chunked training sets (map.cuh): guess GP, then symplectic GP
-    double *gch = nullptr, *tch = nullptr;
-    int nchg = 0, ncht = 0;
+    int nmodels = 1;                // > 1: split map, one learned map per section (Split_SympGPR)
+    long np = 0, nt = 0;            // training pairs per sub-map (all sub-maps have the same sizes)
+    DBuf buf;                       // chunked training sets (map.cuh) of all sub-maps: guess GP, symplectic GP, ...
+    DBuf tab;                       // nmodels MapModelDev entries
 };
 
 // ------------------------------------------------------------------------------------------
@@ -346,19 +345,31 @@ int sgp_buildkreg(sgp_ctx* ctx, int fam, double per, const double* x, const doub
 }
 
 // ---- models -----------------------------------------------------------------------------------
-static int model_build(Ctx& c, sgp_model* m, int fam, double per, const double* hyp3, const double* hypp3,
+// nmodels sub-maps with identical sizes; every array holds the sub-maps one after the other
+// (hyp3/hypp3: 3 values each; xtp/ytp/alphap: np each; xt/yt: nt each; alpha: 2 nt each)
+static int model_build(Ctx& c, sgp_model* m, int fam, double per, int nmodels, const double* hyp3, const double* hypp3,
                        const double* d_xtp, const double* d_ytp, const double* d_alphap, long np,
                        const double* d_xt, const double* d_yt, const double* d_alpha, long nt)
 {
-    m->fam = fam; m->per = per; m->np = np; m->nt = nt;
-    m->nchg = (int)map_chunks(np); m->ncht = (int)map_chunks(nt);
-    m->h = make_hypc(fam, hyp3[0], hyp3[1], hyp3[2], per);
-    m->hp = make_hypc(fam, hypp3[0], hypp3[1], hypp3[2], per);
-    SGP_TRY(m->buf.reserve(map_model_doubles(np, nt) * sizeof(double)));
-    m->gch = m->buf.as<double>();
-    m->tch = m->gch + (size_t)m->nchg * MAP_GF * MAP_CHUNK;
-    SGP_TRY(map_prepare_guess(c, fam, per, d_xtp, d_ytp, d_alphap, np, m->gch));
-    SGP_TRY(map_prepare_sympl(c, fam, per, d_xt, d_yt, d_alpha, nt, m->tch));
+    if (nmodels < 1 || nmodels > 4096) { set_error("model: number of sub-maps must be 1..4096"); return ST_BADARG; }
+    m->fam = fam; m->per = per; m->np = np; m->nt = nt; m->nmodels = nmodels;
+    const int nchg = (int)map_chunks(np), ncht = (int)map_chunks(nt);
+    const size_t per_model = map_model_doubles(np, nt);
+    SGP_TRY(m->buf.reserve(per_model * nmodels * sizeof(double)));
+    SGP_TRY(m->tab.reserve(sizeof(MapModelDev) * (size_t)nmodels));
+    std::vector<MapModelDev> tab((size_t)nmodels);
+    for (int k = 0; k < nmodels; k++) {
+        double* gch = m->buf.as<double>() + per_model * k;
+        double* tch = gch + (size_t)nchg * MAP_GF * MAP_CHUNK;
+        MapModelDev& t = tab[(size_t)k];
+        t.gch = gch; t.nchg = nchg; t.tch = tch; t.ncht = ncht;
+        t.h = make_hypc(fam, hyp3[3 * k], hyp3[3 * k + 1], hyp3[3 * k + 2], per);
+        t.hp = make_hypc(fam, hypp3[3 * k], hypp3[3 * k + 1], hypp3[3 * k + 2], per);
+        SGP_TRY(map_prepare_guess(c, fam, per, d_xtp + np * k, d_ytp + np * k, d_alphap + np * k, np, gch));
+        SGP_TRY(map_prepare_sympl(c, fam, per, d_xt + nt * k, d_yt + nt * k, d_alpha + 2 * nt * k, nt, tch));
+    }
+    SGP_CUDA(cudaMemcpyAsync(m->tab.p, tab.data(), sizeof(MapModelDev) * (size_t)nmodels, cudaMemcpyHostToDevice, c.stream));
+    SGP_CUDA(cudaStreamSynchronize(c.stream));      // `tab` leaves scope
     return ST_OK;
 }
 
@@ -380,9 +391,9 @@ int sgp_model_create(sgp_ctx* ctx, int fam, double per, const double* hyp3, cons
     double *dxp = d, *dyp = dxp + np, *dap = dyp + np, *dx = dap + np, *dy = dx + nt, *da = dy + nt;
     st = upload(c, dxp, xtrainp, np); if (!st) st = upload(c, dyp, ytrainp, np); if (!st) st = upload(c, dap, alphap, np);
     if (!st) st = upload(c, dx, xtrain, nt); if (!st) st = upload(c, dy, ytrain, nt); if (!st) st = upload(c, da, alpha, 2 * nt);
-    if (!st) st = model_build(c, m, fam, per, hyp3, hypp3, dxp, dyp, dap, np, dx, dy, da, nt);
+    if (!st) st = model_build(c, m, fam, per, 1, hyp3, hypp3, dxp, dyp, dap, np, dx, dy, da, nt);
     if (!st) st = sync(c);
-    if (st) { m->buf.release(); delete m; return st; }
+    if (st) { m->buf.release(); m->tab.release(); delete m; return st; }
     *out = m;
     return ST_OK;
 }
@@ -392,14 +403,14 @@ int sgp_model_destroy(sgp_model* m)
     if (!m) return ST_OK;
     cudaSetDevice(m->device);
     m->buf.release();
+    m->tab.release();
     delete m;
     return ST_OK;
 }
 
 static void model_args(const sgp_model* m, MapArgs& a)
 {
-    a.gch = m->gch; a.nchg = m->nchg; a.tch = m->tch; a.ncht = m->ncht;
-    a.h = m->h; a.hp = m->hp;
+    a.models = m->tab.as<MapModelDev>(); a.nmodels = m->nmodels;
     a.pdstate = nullptr; a.ticket = nullptr; a.slots = nullptr; a.progress = nullptr; a.slice_steps = 1;
 }
 
@@ -408,7 +419,7 @@ int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solve
                            long out_every, unsigned long long* d_stats)
 {
     SGP_TRY(check_ctx(ctx));
-    if (!m || E < 0 || nsteps < 0 || kind < 0 || kind > 3 || !d_qfinal || !d_pfinal || !d_stats) {
+    if (!m || E < 0 || nsteps < 0 || kind < 0 || kind > 5 || solver < 0 || solver > 2 || !d_qfinal || !d_pfinal || !d_stats) {
         set_error("model_applymap_dev: bad arguments"); return ST_BADARG;
     }
     MapArgs a;
@@ -423,7 +434,7 @@ int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solve
 }
 
 // shared implementation of the host-buffer map entry points
-static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver, long nm, long E, const double* q0,
+static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver, int nmodels, long nm, long E, const double* q0,
                          const double* p0, const double* hyp3, const double* hypp3, const double* d_xtp, const double* d_ytp,
                          const double* d_alphap, long np, const double* d_xt, const double* d_yt, const double* d_alpha, long nt,
                          double* qmap, double* pmap, double* pdiff, long out_every,
@@ -433,14 +444,14 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
     if (nm < 1) { set_error("applymap: nm must be >= 1"); return ST_BADARG; }
     sgp_model m;
     m.device = c.device;
-    int st = model_build(c, &m, fam, per, hyp3, hypp3, d_xtp, d_ytp, d_alphap, np, d_xt, d_yt, d_alpha, nt);
+    int st = model_build(c, &m, fam, per, nmodels, hyp3, hypp3, d_xtp, d_ytp, d_alphap, np, d_xt, d_yt, d_alpha, nt);
     const bool hist = (qmap && pmap && out_every > 0);
     const long rows = hist ? 1 + (nm - 1) / out_every : 0;
     const size_t hsz = (size_t)rows * (size_t)E;
     const size_t need = (size_t)(5 * E) + hsz * (pdiff ? 3 : 2) + 4;
     if (!st) st = c.mapbuf.reserve(need * sizeof(double));
     if (!st) st = c.flags.reserve(map_sched_bytes(E > 0 ? E : 1));
-    if (st) { m.buf.release(); return st; }
+    if (st) { m.buf.release(); m.tab.release(); return st; }
     double* d = c.mapbuf.as<double>();
     unsigned long long* dstats = (unsigned long long*)d;
     double *dq0 = d + 2, *dp0 = dq0 + E, *dqf = dp0 + E, *dpf = dqf + E, *dpds = dpf + E;
@@ -477,6 +488,7 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
     };
     st = run();
     m.buf.release();
+    m.tab.release();
     return st;
 }
 
@@ -487,15 +499,36 @@ int sgp_applymap(sgp_ctx* ctx, int kind, int fam, double per, int solver, long n
 {
     SGP_TRY(check_ctx(ctx));
     Ctx& c = ctx->c;
-    if (E < 0 || np < 0 || nt < 0 || kind < 0 || kind > 3 || fam < 0 || fam > 2) { set_error("applymap: bad arguments"); return ST_BADARG; }
+    if (E < 0 || np < 0 || nt < 0 || kind < 0 || kind > 4 || solver < 0 || solver > 2 || fam < 0 || fam > 2) { set_error("applymap: bad arguments"); return ST_BADARG; }
     const size_t tot = (size_t)(3 * np + 4 * nt);
     SGP_TRY(c.io.reserve((tot + 8) * sizeof(double)));
     double* d = c.io.as<double>();
     double *dxp = d, *dyp = dxp + np, *dap = dyp + np, *dx = dap + np, *dy = dx + nt, *da = dy + nt;
     SGP_TRY(upload(c, dxp, xtrainp, np)); SGP_TRY(upload(c, dyp, ytrainp, np)); SGP_TRY(upload(c, dap, alphap, np));
     SGP_TRY(upload(c, dx, xtrain, nt)); SGP_TRY(upload(c, dy, ytrain, nt)); SGP_TRY(upload(c, da, alpha, 2 * nt));
-    return applymap_host(ctx, kind, fam, per, solver, nm, E, q0, p0, hyp3, hypp3, dxp, dyp, dap, np, dx, dy, da, nt, qmap, pmap,
+    return applymap_host(ctx, kind, fam, per, solver, 1, nm, E, q0, p0, hyp3, hypp3, dxp, dyp, dap, np, dx, dy, da, nt, qmap, pmap,
                          pdiff, out_every, qfinal, pfinal, stats);
+}
+
+int sgp_applymap_split(sgp_ctx* ctx, int fam, double per, int solver, int nmodels, long nsteps, long E, const double* q0,
+                       const double* p0, const double* hyp3, const double* hypp3, const double* xtrainp, const double* ytrainp,
+                       const double* alphap, long np, const double* xtrain, const double* ytrain, const double* alpha, long nt,
+                       double* qmap, double* pmap, unsigned long long* stats)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (E < 0 || np < 0 || nt < 0 || nmodels < 1 || nsteps < 0 || solver < 0 || solver > 1 || fam < 0 || fam > 2 || !qmap || !pmap) {
+        set_error("applymap_split: bad arguments"); return ST_BADARG;
+    }
+    const size_t M = (size_t)nmodels;
+    const size_t tot = M * (size_t)(3 * np + 4 * nt);
+    SGP_TRY(c.io.reserve((tot + 8) * sizeof(double)));
+    double* d = c.io.as<double>();
+    double *dxp = d, *dyp = dxp + M * np, *dap = dyp + M * np, *dx = dap + M * np, *dy = dx + M * nt, *da = dy + M * nt;
+    SGP_TRY(upload(c, dxp, xtrainp, M * np)); SGP_TRY(upload(c, dyp, ytrainp, M * np)); SGP_TRY(upload(c, dap, alphap, M * np));
+    SGP_TRY(upload(c, dx, xtrain, M * nt)); SGP_TRY(upload(c, dy, ytrain, M * nt)); SGP_TRY(upload(c, da, alpha, M * 2 * nt));
+    return applymap_host(ctx, MAP_TOKAMAK_SPLIT, fam, per, solver, nmodels, nsteps + 1, E, q0, p0, hyp3, hypp3, dxp, dyp, dap, np,
+                         dx, dy, da, nt, qmap, pmap, nullptr, 1, nullptr, nullptr, stats);
 }
 
 // alpha = Kyinv * z on the device for the f2py-signature entry points (sympgpr.f90:72,85,121)
@@ -544,7 +577,7 @@ int sgp_applymap_tok(sgp_ctx* ctx, int fam, double per, int solver, int kind, lo
     SGP_TRY(stage_kyinv_model(c, xtrainp, ytrainp, ztrainp, kyinvp, np, xtrain, ytrain, ztrain, kyinv, nt, in));
     // history comes back (nm, ntest) row-major; the f2py arrays are (nm, ntest, 1) Fortran order
     std::vector<double> hq((size_t)nm * ntest), hp((size_t)nm * ntest);
-    SGP_TRY(applymap_host(ctx, kind, fam, per, solver, nm, ntest, q0map, p0map, hyp3, hypp3, in.dxp, in.dyp, in.dap, np, in.dx,
+    SGP_TRY(applymap_host(ctx, kind, fam, per, solver, 1, nm, ntest, q0map, p0map, hyp3, hypp3, in.dxp, in.dyp, in.dap, np, in.dx,
                           in.dy, in.da, nt, hq.data(), hp.data(), nullptr, 1, nullptr, nullptr, nullptr));
     for (long i = 0; i < nm; i++)
         for (long k = 0; k < ntest; k++) {
@@ -641,7 +674,7 @@ int sgp_calcp(sgp_ctx* ctx, int fam, double per, int solver, double x, double y,
     SGP_TRY(stage_kyinv_model(c, xtrainp, ytrainp, ztrainp, kyinvp, np, xtrain, ytrain, ztrain, kyinv, nt, in));
     // one orbit, one step, no post-processing of P (MAP_HENON leaves P untouched): pfinal = P
     double qf = 0.0, pf = 0.0;
-    SGP_TRY(applymap_host(ctx, MAP_HENON, fam, per, solver, 2, 1, &x, &y, hyp3, hypp3, in.dxp, in.dyp, in.dap, np, in.dx, in.dy,
+    SGP_TRY(applymap_host(ctx, MAP_HENON, fam, per, solver, 1, 2, 1, &x, &y, hyp3, hypp3, in.dxp, in.dyp, in.dap, np, in.dx, in.dy,
                           in.da, nt, nullptr, nullptr, nullptr, 0, &qf, &pf, nullptr));
     *out = pf;
     return ST_OK;

@@ -269,17 +269,26 @@ static int env_int(const char* name, int dflt, int lo, int hi)
 // factored recursively (small, latency-bound launches), the panel below it is one recursive TRSM over
 // all remaining rows and the trailing update one lower-triangular SYRK launch with K = NB, so almost
 // all flops run in launches that fill the 148 SMs.
-int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info)
+static int potrf_multi(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info);
+
+int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* y, double* w)
 {
     if (n_pad % TILE || lda % 2) { set_error("potrf: n_pad %ld / lda %ld not tile aligned", n_pad, lda); return ST_BADARG; }
-    const int nt = (int)(n_pad / TILE);
-    // default: the left-looking persistent kernel (potrf_ll.cu).  SGP_POTRF=rec selects the recursive /
-    // blocked multi-launch drivers below (kept for comparison).
+    // default: the left-looking persistent kernel (potrf_ll.cu) with the forward substitution fused in.
+    // SGP_POTRF=rec selects the recursive / blocked multi-launch drivers below (kept for comparison).
     static const int use_rec = [] { const char* v = getenv("SGP_POTRF"); return (v && v[0] == 'r') ? 1 : 0; }();
     if (!use_rec) {
         SGP_TRY(c.flags.reserve(potrf_ll_flag_bytes(n_pad)));
-        return potrf_ll(c, A, n_pad, lda, Dinv, logparts, info, c.flags.as<int>());
+        return potrf_ll(c, A, n_pad, lda, Dinv, logparts, info, c.flags.as<int>(), y, w);
     }
+    SGP_TRY(potrf_multi(c, A, n_pad, lda, Dinv, logparts, info));
+    if (y && w) SGP_TRY(trsv_fwd(c, A, n_pad, lda, Dinv, y, w));
+    return ST_OK;
+}
+
+static int potrf_multi(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info)
+{
+    const int nt = (int)(n_pad / TILE);
     const int nb = env_int("SGP_POTRF_NB", 0, 0, 64);
     if (nb == 0) return potrf_rec(c, A, lda, Dinv, logparts, info, 0, nt);      // fully recursive
     const int lookahead = env_int("SGP_LOOKAHEAD", 1, 0, 1) && c.side != nullptr && nt > 2 * nb;
@@ -337,21 +346,147 @@ int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logpart
     return ST_OK;
 }
 
-int potrs(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w, double* alpha)
+int trsv_fwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w)
 {
     const int nt = (int)(n_pad / TILE);
     for (int j = 0; j < nt; j++) {
         trsv_fwd_step_kernel<<<nt - j, TILE, 0, c.stream>>>(L, lda, Dinv, y, w, j);
     }
     SGP_CUDA(cudaGetLastError());
-    count_launch(2ull * nt);
+    count_launch((unsigned long long)nt);
+    return ST_OK;
+}
+
+int trsv_bwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* w, double* alpha)
+{
+    const int nt = (int)(n_pad / TILE);
     for (int j = nt - 1; j >= 0; j--) {
         trsv_bwd_step_kernel<<<1 + 2 * j, 256, 0, c.stream>>>(L, lda, Dinv, w, alpha, j);
     }
     SGP_CUDA(cudaGetLastError());
+    count_launch((unsigned long long)nt);
     return ST_OK;
 }
 
+// alpha = W y, W symmetric, lower triangle stored (tiles tm >= tn complete, as lauum writes them).  One CTA
+// per tile row i: the tiles to the left (j <= i) contribute W(i,j) y_j, the tiles below (k > i) their
+// transposes W(k,i)^T y_k.  Every row reads nt tiles, so the CTAs are balanced; each tile is read twice
+// overall (8 n^2 bytes); the summation order is fixed.
+__global__ void __launch_bounds__(256)
+symv_lower_kernel(const double* __restrict__ W, long ld, const double* __restrict__ y, double* __restrict__ alpha, int nt)
+{
+    __shared__ double ys[TILE];
+    __shared__ double part[2][TILE];
+    __shared__ double colacc[TILE];
+    const int i = blockIdx.x, tid = threadIdx.x;
+    const int r = tid & (TILE - 1), half = tid >> 7;
+    const int warp = tid >> 5, lane = tid & 31;
+    double acc = 0.0;
+    // left part: row r of W(i,j), columns [half*64, half*64+64)
+    for (int j = 0; j <= i; j++) {
+        __syncthreads();
+        if (tid < TILE) ys[tid] = y[(long)j * TILE + tid];
+        __syncthreads();
+        const double* Wt = W + (long)i * TILE + r + ((long)j * TILE + half * 64) * ld;
+        double a0 = 0.0, a1 = 0.0;
+#pragma unroll 8
+        for (int cc = 0; cc < 64; cc += 2) {
+            a0 = fma(Wt[(long)cc * ld], ys[half * 64 + cc], a0);
+            a1 = fma(Wt[(long)(cc + 1) * ld], ys[half * 64 + cc + 1], a1);
+        }
+        acc += a0 + a1;
+    }
+    part[half][r] = acc;
+    if (tid < TILE) colacc[tid] = 0.0;
+    // lower part: column c of W(k,i), reduced over its 128 rows by one warp (16 columns per warp)
+    for (int k = i + 1; k < nt; k++) {
+        __syncthreads();
+        if (tid < TILE) ys[tid] = y[(long)k * TILE + tid];
+        __syncthreads();
+        for (int cc = 0; cc < 16; cc++) {
+            const int col = warp * 16 + cc;
+            const double* Wc = W + (long)k * TILE + ((long)i * TILE + col) * ld;
+            double sacc = Wc[lane] * ys[lane] + Wc[lane + 32] * ys[lane + 32] + Wc[lane + 64] * ys[lane + 64] + Wc[lane + 96] * ys[lane + 96];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sacc += __shfl_xor_sync(0xffffffffu, sacc, o);
+            if (lane == 0) colacc[col] += sacc;
+        }
+    }
+    __syncthreads();
+    if (tid < TILE) alpha[(long)i * TILE + tid] = (part[0][tid] + part[1][tid]) + colacc[tid];
+}
+
+// alpha = X^T w for the explicit lower-triangular X = L^-1 (alpha = L^-T w, the second half of potrs, once the
+// inverse factor exists): one warp per column, the column's n - c entries are contiguous, 4 loads in flight per
+// lane, fixed summation order.  4 n^2 bytes, HBM-read bound.
+__global__ void __launch_bounds__(256)
+gemv_t_lower_kernel(const double* __restrict__ X, long ld, const double* __restrict__ w, double* __restrict__ alpha, long n)
+{
+    const int lane = threadIdx.x & 31;
+    const long c = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (c >= n) return;
+    const double* col = X + c * ld;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    long r = c + lane;
+    for (; r + 96 < n; r += 128) {
+        s0 = fma(col[r], w[r], s0);
+        s1 = fma(col[r + 32], w[r + 32], s1);
+        s2 = fma(col[r + 64], w[r + 64], s2);
+        s3 = fma(col[r + 96], w[r + 96], s3);
+    }
+    for (; r < n; r += 32) s0 = fma(col[r], w[r], s0);
+    double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) alpha[c] = s;
+}
+
+int gemv_t_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* w, double* alpha)
+{
+    gemv_t_lower_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, c.stream>>>(X, ldx, w, alpha, n_pad);
+    SGP_CUDA(cudaGetLastError());
+    count_launch();
+    return ST_OK;
+}
+
+int symv_lower(Ctx& c, const double* W, long n_pad, long ldw, const double* y, double* alpha)
+{
+    const int nt = (int)(n_pad / TILE);
+    symv_lower_kernel<<<nt, 256, 0, c.stream>>>(W, ldw, y, alpha, nt);
+    SGP_CUDA(cudaGetLastError());
+    count_launch();
+    return ST_OK;
+}
+
+// scratch (in 128x128 tiles) of trtri_rec on mt tiles: the m2 x m1 product T of this level, after the two
+// halves, which may run concurrently and therefore get disjoint regions
+static size_t trtri_tiles(int mt)
+{
+    if (mt <= 1) return 0;
+    const int m1 = mt / 2, m2 = mt - m1;
+    const size_t own = (size_t)m1 * m2, kids = trtri_tiles(m1) + trtri_tiles(m2);
+    return own > kids ? own : kids;
+}
+
+constexpr int TRTRI_FORK_MAX = 32;     // blocks of up to 32 tiles run their two halves on different streams
+
+// side streams / events for the forked sub-trees (created on first use, live as long as the process)
+static cudaStream_t g_fork_streams[8];
+static cudaEvent_t g_fork_events[64];
+static int g_fork_ready = 0, g_fork_next_stream = 0, g_fork_next_event = 0;
+
+static int fork_init()
+{
+    if (g_fork_ready) return ST_OK;
+    for (auto& s : g_fork_streams) SGP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& e : g_fork_events) SGP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g_fork_ready = 1;
+    return ST_OK;
+}
+
+// X = L^-1 for the diagonal block of mt tiles starting at tile j0, in place, on c.stream.
+// X11 and X22 are independent; X21 = -X22 L21 X11.  The small blocks at the bottom of the recursion are
+// launches of a few CTAs each: their two halves are forked onto side streams so that they fill the GPU together.
 static int trtri_rec(Ctx& c, double* A, long lda, const double* Dinv, double* T, int j0, int mt)
 {
     if (mt == 1) {
@@ -361,8 +496,26 @@ static int trtri_rec(Ctx& c, double* A, long lda, const double* Dinv, double* T,
         return ST_OK;
     }
     const int m1 = mt / 2, m2 = mt - m1;
-    SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, m1));
-    SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0 + m1, m2));
+    double* T2 = T + trtri_tiles(m1) * TILE * TILE;          // scratch of the second half
+    if (mt <= TRTRI_FORK_MAX && mt >= 2) {
+        SGP_TRY(fork_init());
+        cudaStream_t s0 = c.stream;
+        cudaStream_t s1 = g_fork_streams[g_fork_next_stream++ % 8];
+        cudaEvent_t ef = g_fork_events[g_fork_next_event++ % 64];
+        cudaEvent_t ej = g_fork_events[g_fork_next_event++ % 64];
+        SGP_CUDA(cudaEventRecord(ef, s0));
+        SGP_CUDA(cudaStreamWaitEvent(s1, ef, 0));
+        SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, m1));
+        c.stream = s1;
+        const int st = trtri_rec(c, A, lda, Dinv, T2, j0 + m1, m2);
+        c.stream = s0;
+        SGP_TRY(st);
+        SGP_CUDA(cudaEventRecord(ej, s1));
+        SGP_CUDA(cudaStreamWaitEvent(s0, ej, 0));
+    } else {
+        SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, m1));
+        SGP_TRY(trtri_rec(c, A, lda, Dinv, T2, j0 + m1, m2));
+    }
     const long ldt = (long)m2 * TILE;
     // T = L21 * X11        (X11 lower: k >= tn*128)
     SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + m1, j0), lda, AT(A, lda, j0, j0), lda, T, ldt, m2, m1,
@@ -386,7 +539,7 @@ int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T
         SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, jb));          // needs jb/2 x jb/2 tiles of T
         const int rt = nt - (j0 + jb);
         if (rt > 0) {
-            double* T2 = T + (size_t)(nb * TILE / 2 + TILE) * (size_t)(nb * TILE / 2 + TILE);   // past trtri_rec's scratch
+            double* T2 = T + (trtri_tiles(nb) + 1) * TILE * TILE;   // past trtri_rec's scratch
             const long ldt = (long)rt * TILE;
             // T2 = X22 * L21          (X22 lower: k < (tm+1)*128)
             SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + jb, j0 + jb), lda, AT(A, lda, j0 + jb, j0), lda, T2, ldt, rt, jb,
@@ -402,10 +555,9 @@ int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T
 size_t trtri_workspace_doubles(long n_pad)
 {
     const size_t nb = 64;                                        // upper bound of SGP_TRTRI_NB
-    const size_t rec = (nb * TILE / 2 + TILE) * (nb * TILE / 2 + TILE);
+    const size_t rec = (trtri_tiles((int)nb) + 1) * TILE * TILE;
     const size_t blocked = rec + (size_t)n_pad * (nb * TILE);
-    const size_t half = (size_t)(n_pad / 2 + TILE);
-    const size_t recursive = half * half;
+    const size_t recursive = (trtri_tiles((int)(n_pad / TILE)) + 1) * TILE * TILE;
     return blocked > recursive ? blocked : recursive;
 }
 

@@ -6,11 +6,20 @@
 
 namespace sgp {
 
-int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info);
+// Cholesky factor in place; with y and w given also the forward substitution L w = y (y is overwritten
+// on the multi-launch path, left alone on the fused one)
+int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* y = nullptr, double* w = nullptr);
 // one persistent cooperative kernel (potrf_ll.cu); flags: potrf_ll_flag_bytes(n_pad) bytes of device scratch
-int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags);
+int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags, const double* y,
+             double* w);
 size_t potrf_ll_flag_bytes(long n_pad);
-int potrs(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w, double* alpha);
+// blocked substitutions with the tile inverses: forward L w = y (y destroyed), backward L^T alpha = w (w destroyed)
+int trsv_fwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w);
+int trsv_bwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* w, double* alpha);
+// alpha = X^T w for the explicit lower-triangular inverse factor X (entries above the diagonal are not read)
+int gemv_t_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* w, double* alpha);
+// alpha = W y for the symmetric W given by its lower triangle (tiles on and below the diagonal complete)
+int symv_lower(Ctx& c, const double* W, long n_pad, long ldw, const double* y, double* alpha);
 int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T);
 size_t trtri_workspace_doubles(long n_pad);
 int lauum(Ctx& c, const double* X, long n_pad, long lda, double* W, long ldw);

@@ -1,12 +1,13 @@
 // Warp-specialised, persistent version of the structured FP64 DMMA GEMM (dmma_gemm.cuh has the
 // operand layouts, tile modes and the GemmArgs contract; this file only changes HOW a CTA runs).
 //
-// One CTA per SM, 9 warps:
-//   warp 8      producer: streams the A and B k-slabs of the CTA's tiles global -> shared into the
+// One CTA per SM, 10 warps:
+//   warps 8, 9  producers: stream the A and B k-slabs of the CTA's tiles global -> shared into the
 //               same padded, bank-conflict-free layouts as before; LAYOUT_MN slabs by cp.async.bulk
 //               (SASS UBLKCP, the TMA engine's 1-D path, one 1 KB copy per k-row, completion by
 //               expect_tx / complete_tx), LAYOUT_K slabs by 16-byte LDGSTS (completion by
-//               cp.async.mbarrier.arrive.noinc); both land on one "full" mbarrier per stage.
+//               cp.async.mbarrier.arrive.noinc, rows split over both producer warps); both kinds land
+//               on one "full" mbarrier per stage.
 //   warps 0..7  consumers: 2(M) x 4(N) warp grid, 64x32 warp tile, 32 DMMA.8x8x4 per k4 step fed by
 //               12 LDS.64; fragments are double-buffered in registers so the shared loads of step
 //               k+1 are in flight while the DMMAs of step k issue.
@@ -28,7 +29,11 @@ namespace sgp {
 
 constexpr int WS_STAGES = 5;
 constexpr int WS_CONSUMER_WARPS = 8;
-constexpr int WS_THREADS = (WS_CONSUMER_WARPS + 1) * 32;
+constexpr int WS_THREADS = (WS_CONSUMER_WARPS + 1) * 32;       // potrf_ll.cu: one producer warp (all operands LAYOUT_MN)
+// the GEMM kernel runs two producer warps: LAYOUT_K slabs take 32 LDGSTS per lane with one warp, and ncu
+// showed the consumers waiting on the full barriers then (DMMA pipe 86 % against 95 % for bulk-copied slabs)
+constexpr int WS_PRODUCER_WARPS = 2;
+constexpr int WS_GEMM_THREADS = (WS_CONSUMER_WARPS + WS_PRODUCER_WARPS) * 32;
 constexpr uint32_t WS_SLAB_BYTES = GT * GK * sizeof(double);               // bytes of one operand slab (128 x GK)
 constexpr size_t WS_SMEM = (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double) + 2 * WS_STAGES * sizeof(unsigned long long);
 
@@ -71,18 +76,20 @@ __device__ __forceinline__ TileInfo tile_info(const GemmArgs& p, long b)
 //             UBLKCP takes uniform operands, the warp issues the rows one after the other).
 //  LAYOUT_K : 128 m-rows of GK contiguous doubles (128 B) -> 16-byte LDGSTS, 32 per lane; a bulk copy
 //             per 128 B row would cost 128 serialised UBLKCP issues per slab and starve the consumers.
+// `part` of `nparts` producer warps: bulk copies are issued by part 0 only, LDGSTS rows are split evenly
 template <int LAY>
 __device__ __forceinline__ void produce_slab(double* sm, const double* __restrict__ g, long ld, long r0, long kk, int lane,
-                                             unsigned long long* bar)
+                                             unsigned long long* bar, int part = 0, int nparts = 1)
 {
     if (LAY == LAYOUT_MN) {
-        if (lane < GK) bulk_g2s(sm + lane * LDMN, g + (kk + lane) * ld + r0, GT * sizeof(double), bar);
+        if (part == 0 && lane < GK) bulk_g2s(sm + lane * LDMN, g + (kk + lane) * ld + r0, GT * sizeof(double), bar);
     } else {
-        const double* src = g + (r0 + (lane >> 3)) * ld + kk + (lane & 7) * 2;
-        double* dst = sm + (lane >> 3) * LDKK + (lane & 7) * 2;
+        const int rows = GT / nparts, row0 = part * rows;
+        const double* src = g + (r0 + row0 + (lane >> 3)) * ld + kk + (lane & 7) * 2;
+        double* dst = sm + (row0 + (lane >> 3)) * LDKK + (lane & 7) * 2;
         const long step = 4 * ld;
 #pragma unroll 8
-        for (int i = 0; i < GT / 4; i++) cp_async16(dst + i * 4 * LDKK, src + i * step);
+        for (int i = 0; i < rows / 4; i++) cp_async16(dst + i * 4 * LDKK, src + i * step);
     }
 }
 
@@ -100,7 +107,7 @@ __device__ __forceinline__ void load_frags_b(const double* sb, int wn, int g, in
 }
 
 template <int AL, int BL>
-__global__ void __launch_bounds__(WS_THREADS, 1) gemm_f64_ws_kernel(GemmArgs p, long ntiles)
+__global__ void __launch_bounds__(WS_GEMM_THREADS, 1) gemm_f64_ws_kernel(GemmArgs p, long ntiles)
 {
     extern __shared__ __align__(16) double smem[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)WS_STAGES * 2 * STAGE_DOUBLES);
@@ -113,15 +120,17 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_f64_ws_kernel(GemmArgs p, 
         for (int s = 0; s < WS_STAGES; s++) {
             // producer arrivals per phase: lane 0's arrive.expect_tx when an operand comes by bulk copy,
             // plus one cp.async.mbarrier.arrive.noinc per lane when an operand comes by LDGSTS
-            mbar_init(full + s, (AL == LAYOUT_MN || BL == LAYOUT_MN ? 1 : 0) + (AL == LAYOUT_K || BL == LAYOUT_K ? 32 : 0));
+            mbar_init(full + s, (AL == LAYOUT_MN || BL == LAYOUT_MN ? 1 : 0) + (AL == LAYOUT_K || BL == LAYOUT_K ? 32 * WS_PRODUCER_WARPS : 0));
             mbar_init(empty + s, WS_CONSUMER_WARPS);      // one arrive per consumer warp
         }
         mbar_fence_init();
     }
     __syncthreads();
 
-    if (warp == WS_CONSUMER_WARPS) {
-        // ------------------------------------------------------------------ producer warp
+    if (warp >= WS_CONSUMER_WARPS) {
+        // ------------------------------------------------------------------ producer warps
+        const int part = warp - WS_CONSUMER_WARPS;
+        if (part > 0 && AL == LAYOUT_MN && BL == LAYOUT_MN) return;      // nothing to do for bulk-only operands
         uint32_t it = 0;
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
             const TileInfo ti = tile_info(p, tile);
@@ -131,14 +140,14 @@ __global__ void __launch_bounds__(WS_THREADS, 1) gemm_f64_ws_kernel(GemmArgs p, 
                 const uint32_t ph = (it / WS_STAGES) & 1u;
                 mbar_wait(empty + s, ph ^ 1u);
                 constexpr uint32_t tx = (AL == LAYOUT_MN ? WS_SLAB_BYTES : 0u) + (BL == LAYOUT_MN ? WS_SLAB_BYTES : 0u);
-                if (tx != 0u) {
+                if (tx != 0u && part == 0) {
                     if (lane == 0) mbar_arrive_expect_tx(full + s, tx);
                     __syncwarp();
                 }
                 double* sa = smem + (size_t)s * 2 * STAGE_DOUBLES;
                 const long kk = ti.k0 + (long)kb * GK;
-                produce_slab<AL>(sa, p.A, p.lda, m0, kk, lane, full + s);
-                produce_slab<BL>(sa + STAGE_DOUBLES, p.B, p.ldb, n0, kk, lane, full + s);
+                produce_slab<AL>(sa, p.A, p.lda, m0, kk, lane, full + s, part, WS_PRODUCER_WARPS);
+                produce_slab<BL>(sa + STAGE_DOUBLES, p.B, p.ldb, n0, kk, lane, full + s, part, WS_PRODUCER_WARPS);
                 if (AL == LAYOUT_K || BL == LAYOUT_K) cp_async_mbar_arrive_noinc(full + s);
             }
         }
@@ -229,7 +238,7 @@ inline cudaError_t gemm_ws_launch_t(const GemmArgs& a, cudaStream_t st)
     if (nt <= 0 || a.K <= 0) return cudaSuccess;
     const int sms = ws_sm_count();
     const unsigned grid = (unsigned)(nt < sms ? nt : sms);
-    gemm_f64_ws_kernel<AL, BL><<<grid, WS_THREADS, WS_SMEM, st>>>(a, nt);
+    gemm_f64_ws_kernel<AL, BL><<<grid, WS_GEMM_THREADS, WS_SMEM, st>>>(a, nt);
     return cudaGetLastError();
 }
 

@@ -182,7 +182,7 @@ int fill_hess_sym(Ctx& c, int fam, const Pt* pts, long N, const HypC& h, double 
 template <int FAM>
 __global__ void __launch_bounds__(FILL_THREADS)
 fill_reg_kernel(const Pt* __restrict__ pb, long N, const Pt* __restrict__ pa, long N0, HypC h, double noise, int sym,
-                double* __restrict__ K, long ld, int vec)
+                double* __restrict__ K, long ld, int vec, int which)
 {
     __shared__ Pt sa[FILL_COLS];
     const long j0 = (long)blockIdx.y * FILL_COLS;
@@ -204,7 +204,12 @@ fill_reg_kernel(const Pt* __restrict__ pb, long N, const Pt* __restrict__ pa, lo
         const Pt a = sa[jj];
         const Pair<FAM> q0(a, b0, h), q1(a, b1, h);
         const long j = j0 + jj;
-        double k0 = h.sig * q0.k(), k1 = h.sig * q1.k();
+        // which: 0 kernel value (buildKreg); 1 / 2 the (q,q) / (P,P) Hessian block alone (nll_expl,
+        // python/04_standard_map/func.py:126-141: the sum kernel's matrix is block diagonal)
+        double k0, k1;
+        if (which == 0) { k0 = h.sig * q0.k(); k1 = h.sig * q1.k(); }
+        else if (which == 1) { k0 = h.sig * q0.kxx(h); k1 = h.sig * q1.kxx(h); }
+        else { k0 = h.sig * q0.kyy(h); k1 = h.sig * q1.kyy(h); }
         if (sym) { if (i == j) k0 += noise; if (i + 1 == j) k1 += noise; }
         double* c0 = K + i + j * ld;
         if (v2) st2(c0, k0, k1, true);
@@ -218,9 +223,9 @@ int fill_reg(Ctx& c, int fam, const Pt* pb, long N, const Pt* pa, long N0, const
     dim3 grid((unsigned)((N + 2 * FILL_THREADS - 1) / (2 * FILL_THREADS)), (unsigned)((N0 + FILL_COLS - 1) / FILL_COLS));
     const int vec = (ld % 2 == 0) && (((size_t)K & 15) == 0);
     switch (fam) {
-    case FAM_PRODUCT: fill_reg_kernel<FAM_PRODUCT><<<grid, FILL_THREADS, 0, c.stream>>>(pb, N, pa, N0, h, 0.0, 0, K, ld, vec); break;
-    case FAM_SQ: fill_reg_kernel<FAM_SQ><<<grid, FILL_THREADS, 0, c.stream>>>(pb, N, pa, N0, h, 0.0, 0, K, ld, vec); break;
-    case FAM_SUM: fill_reg_kernel<FAM_SUM><<<grid, FILL_THREADS, 0, c.stream>>>(pb, N, pa, N0, h, 0.0, 0, K, ld, vec); break;
+    case FAM_PRODUCT: fill_reg_kernel<FAM_PRODUCT><<<grid, FILL_THREADS, 0, c.stream>>>(pb, N, pa, N0, h, 0.0, 0, K, ld, vec, 0); break;
+    case FAM_SQ: fill_reg_kernel<FAM_SQ><<<grid, FILL_THREADS, 0, c.stream>>>(pb, N, pa, N0, h, 0.0, 0, K, ld, vec, 0); break;
+    case FAM_SUM: fill_reg_kernel<FAM_SUM><<<grid, FILL_THREADS, 0, c.stream>>>(pb, N, pa, N0, h, 0.0, 0, K, ld, vec, 0); break;
     default: set_error("unknown kernel family %d", fam); return ST_BADARG;
     }
     SGP_CUDA(cudaGetLastError());
@@ -228,14 +233,14 @@ int fill_reg(Ctx& c, int fam, const Pt* pb, long N, const Pt* pa, long N0, const
     return ST_OK;
 }
 
-int fill_reg_sym(Ctx& c, int fam, const Pt* pts, long N, const HypC& h, double noise, double* K, long ld, long n_pad)
+int fill_reg_sym(Ctx& c, int fam, const Pt* pts, long N, const HypC& h, double noise, double* K, long ld, long n_pad, int which)
 {
     dim3 grid((unsigned)((N + 2 * FILL_THREADS - 1) / (2 * FILL_THREADS)), (unsigned)((N + FILL_COLS - 1) / FILL_COLS));
     const int vec = (ld % 2 == 0) && (((size_t)K & 15) == 0);
     switch (fam) {
-    case FAM_PRODUCT: fill_reg_kernel<FAM_PRODUCT><<<grid, FILL_THREADS, 0, c.stream>>>(pts, N, pts, N, h, noise, 1, K, ld, vec); break;
-    case FAM_SQ: fill_reg_kernel<FAM_SQ><<<grid, FILL_THREADS, 0, c.stream>>>(pts, N, pts, N, h, noise, 1, K, ld, vec); break;
-    case FAM_SUM: fill_reg_kernel<FAM_SUM><<<grid, FILL_THREADS, 0, c.stream>>>(pts, N, pts, N, h, noise, 1, K, ld, vec); break;
+    case FAM_PRODUCT: fill_reg_kernel<FAM_PRODUCT><<<grid, FILL_THREADS, 0, c.stream>>>(pts, N, pts, N, h, noise, 1, K, ld, vec, which); break;
+    case FAM_SQ: fill_reg_kernel<FAM_SQ><<<grid, FILL_THREADS, 0, c.stream>>>(pts, N, pts, N, h, noise, 1, K, ld, vec, which); break;
+    case FAM_SUM: fill_reg_kernel<FAM_SUM><<<grid, FILL_THREADS, 0, c.stream>>>(pts, N, pts, N, h, noise, 1, K, ld, vec, which); break;
     default: set_error("unknown kernel family %d", fam); return ST_BADARG;
     }
     SGP_CUDA(cudaGetLastError());

@@ -104,6 +104,7 @@ struct Stream {
     double* buf;                 // 2 * MAP_BUF_DOUBLES
     unsigned long long* bar;     // 2
     uint32_t seq;
+    const double* primed;        // the set whose chunks 0 and 1 are in flight between sweeps
 };
 
 __device__ __forceinline__ void stream_issue(const Stream& s, uint32_t slot, const double* src, uint32_t bytes)
@@ -221,6 +222,7 @@ __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set
         }
         st.seq++;
     }
+    st.primed = nxt;
     const double A = z.a0 + z.a1, B = z.b0 + z.b1, C = z.c0 + z.c1, D = z.d0 + z.d1;
     if (FAM == FAM_SUM) {
         o0 = h.sig * A;
@@ -257,10 +259,16 @@ map_kernel(MapArgs a)
         mbar_fence_init();
     }
     __syncwarp();
-    // prime the stream with the first two chunks of the guess set (every work item starts with a guess sweep)
-    if (lane == 0) {
-        stream_issue(st, 0, a.gch, MAP_GF * MAP_CHUNK * sizeof(double));
-        stream_issue(st, 1, a.gch + MAP_GF * MAP_CHUNK, MAP_GF * MAP_CHUNK * sizeof(double));
+    // prime the stream with the first two chunks of the set a step starts with: the guess set of its model,
+    // or the symplectic set for the explicit map, which has no guess sweep
+    constexpr int first_nf = (SOLVER == 2) ? MAP_TF : MAP_GF;
+    {
+        const double* fs = (SOLVER == 2) ? a.models[0].tch : a.models[0].gch;
+        if (lane == 0) {
+            stream_issue(st, 0, fs, first_nf * MAP_CHUNK * sizeof(double));
+            stream_issue(st, 1, fs + first_nf * MAP_CHUNK, first_nf * MAP_CHUNK * sizeof(double));
+        }
+        st.primed = fs;
     }
 
     const long nbatches = (a.E + 31) / 32;
@@ -319,18 +327,46 @@ map_kernel(MapArgs a)
         if (step_end > a.nsteps) step_end = a.nsteps;
 
         for (long step = step_begin; step <= step_end; step++) {
+            const MapModelDev& M = a.models[(step - 1) % a.nmodels];
+            const MapModelDev& Mn = a.models[step % a.nmodels];                   // model of the next step
+            const double* first_set = (SOLVER == 2) ? M.tch : M.gch;
+            const double* next_first = (SOLVER == 2) ? Mn.tch : Mn.gch;
+            if (st.primed != first_set) {
+                // the chunks in flight belong to another model's set (a work item that starts in the middle of a
+                // split-map turn): discard them and prime again
+                mbar_wait(st.bar + (st.seq & 1u), (st.seq >> 1) & 1u);
+                mbar_wait(st.bar + ((st.seq + 1u) & 1u), ((st.seq + 1u) >> 1) & 1u);
+                __syncwarp();
+                st.seq += 2;
+                if (lane == 0) {
+                    stream_issue(st, st.seq & 1u, first_set, first_nf * MAP_CHUNK * sizeof(double));
+                    stream_issue(st, (st.seq + 1u) & 1u, first_set + first_nf * MAP_CHUNK, first_nf * MAP_CHUNK * sizeof(double));
+                }
+                st.primed = first_set;
+            }
             // an orbit that is already NaN stays NaN (tokamak: explicit test, func.py:192-193; the
             // other variants propagate it through the arithmetic)
             bool alive = mine && (q == q) && (p == p);
             Pt b;
-            if (alive) { b = make_pt<FAM>(q, p, a.h.p); } else { b.u = 0; b.v = 1; b.y = 0; }
+            if (alive) { b = make_pt<FAM>(q, p, M.h.p); } else { b.u = 0; b.v = 1; b.y = 0; }
 
-            double pg, dummy;
-            sweep<FAM, SW_GUESS>(st, a.gch, a.nchg, a.tch, MAP_TF, lane, b, a.hp, s_tab, alive, pg, dummy);
-            if (alive && !(fabs(pg) <= DBL_MAX)) alive = false;
+            double pg = 0.0, dummy;
+            if (SOLVER != 2) {
+                sweep<FAM, SW_GUESS>(st, M.gch, M.nchg, M.tch, MAP_TF, lane, b, M.hp, s_tab, alive, pg, dummy);
+                if (alive && !(fabs(pg) <= DBL_MAX)) alive = false;
+            }
 
             double P;
-            if (SOLVER == 0) {
+            if (SOLVER == 2) {
+                // explicit map (no root solve): P = p - F_q(q, p), the generating function taken at the OLD
+                // momentum -- calcP_expl python/04_standard_map/func.py:174-179, calcP
+                // python/01_pendulum/explicit/func_expl.py:107-112.  No guess GP.
+                b.y = p;
+                double F, dF;
+                sweep<FAM, SW_F>(st, M.tch, M.ncht, M.tch, MAP_TF, lane, b, M.h, s_tab, alive, F, dF);
+                if (alive) evals++;
+                P = p - F;
+            } else if (SOLVER == 0) {
                 Hybrd1 sv;
                 sv.start(alive ? pg : 0.0);
                 if (!alive) sv.phase = 3;
@@ -338,7 +374,7 @@ map_kernel(MapArgs a)
                     const bool run = !sv.done();
                     b.y = sv.query();
                     double F, dF;
-                    sweep<FAM, SW_F>(st, a.tch, a.ncht, a.tch, MAP_TF, lane, b, a.h, s_tab, run, F, dF);
+                    sweep<FAM, SW_F>(st, M.tch, M.ncht, M.tch, MAP_TF, lane, b, M.h, s_tab, run, F, dF);
                     if (run) { sv.feed(F - p + b.y); evals++; }
                 }
                 P = sv.root();
@@ -351,7 +387,7 @@ map_kernel(MapArgs a)
                     const bool run = !sv.done();
                     b.y = sv.query();
                     double F, dF;
-                    sweep<FAM, SW_F_DF>(st, a.tch, a.ncht, a.tch, MAP_TF, lane, b, a.h, s_tab, run, F, dF);
+                    sweep<FAM, SW_F_DF>(st, M.tch, M.ncht, M.tch, MAP_TF, lane, b, M.h, s_tab, run, F, dF);
                     if (run) { sv.feed(F - p + b.y, 1.0 + dF); evals++; }
                 }
                 P = sv.root();
@@ -360,7 +396,7 @@ map_kernel(MapArgs a)
 
             double Pst = P;
             if (alive) {
-                if (a.kind == MAP_STANDARD) {
+                if (a.kind == MAP_STANDARD || a.kind == MAP_STANDARD_EXPL) {
                     pd = pd + (P - p);
                     Pst = np_mod(P, TWO_PI);
                 } else if (a.kind == MAP_TOKAMAK) {
@@ -373,12 +409,18 @@ map_kernel(MapArgs a)
             const bool qalive = alive && (Pst == Pst);
             b.y = Pst;
             double dq;
-            sweep<FAM, SW_DQ>(st, a.tch, a.ncht, a.gch, MAP_GF, lane, b, a.h, s_tab, qalive, dq, dummy);
+            sweep<FAM, SW_DQ>(st, M.tch, M.ncht, next_first, first_nf, lane, b, M.h, s_tab, qalive, dq, dummy);
             if (qalive) evals++;
             double qn;
             if (!qalive) qn = nan("");
-            else if (a.kind == MAP_HENON) qn = dq + q;
+            else if (a.kind == MAP_HENON || a.kind == MAP_STANDARD_EXPL) qn = dq + q;
             else qn = np_mod(dq + q, TWO_PI);
+            if (a.kind == MAP_TOKAMAK_SPLIT && qalive) {
+                // loss test at the NEW angle; a lost orbit is NaN in both coordinates (Split_SympGPR/func.py:212-217;
+                // compute_r does not depend on the toroidal angle, fieldlines.f90:34-47,94-107)
+                const double r = compute_r_dev(Pst * 1e-2, qn, 0.3);
+                if (r > 0.5 || Pst < 0.0) { Pst = nan(""); qn = nan(""); }
+            }
             if (mine && !alive) pd = nan("");
             q = qn;
             p = Pst;
@@ -516,6 +558,7 @@ int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched)
     long ss = a.nsteps / 16;
     if (ss < 1) ss = 1;
     if (ss > 16) ss = 16;
+    if (a.nmodels > 1) ss = (ss + a.nmodels - 1) / a.nmodels * a.nmodels;      // work items start at a turn boundary of a split map
     a.slice_steps = ss;
     const long warps_needed = nbatches;
     long blocks = (warps_needed + MAP_WARPS - 1) / MAP_WARPS;
@@ -528,6 +571,13 @@ int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched)
         case FAM_PRODUCT: ML(FAM_PRODUCT, 0); break;
         case FAM_SQ: ML(FAM_SQ, 0); break;
         case FAM_SUM: ML(FAM_SUM, 0); break;
+        default: set_error("unknown kernel family %d", fam); return ST_BADARG;
+        }
+    } else if (solver == 2) {
+        switch (fam) {
+        case FAM_PRODUCT: ML(FAM_PRODUCT, 2); break;
+        case FAM_SQ: ML(FAM_SQ, 2); break;
+        case FAM_SUM: ML(FAM_SUM, 2); break;
         default: set_error("unknown kernel family %d", fam); return ST_BADARG;
         }
     } else {

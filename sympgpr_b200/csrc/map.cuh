@@ -9,18 +9,26 @@ enum MapKind : int {
     MAP_HENON = 1,      // q <- q + dq                                   python/functions/func.py:239-260
     MAP_STANDARD = 2,   // q <- mod(q + dq, 2pi), p <- mod(P, 2pi), pdiff python/04_standard_map/func.py:218-254
     MAP_TOKAMAK = 3,    // pendulum wrap + loss test (compute_r)         python/05_tokamak/SympGPR/func.py:182-211
+    MAP_STANDARD_EXPL = 4,  // p <- mod(P, 2pi), pdiff, q <- q + dq (no wrap): applymap_expl python/04_standard_map/func.py:256-285
+    MAP_TOKAMAK_SPLIT = 5,  // split map: model (step-1) mod nmodels, loss test at the NEW angle, lost orbits NaN in q and p:
+                            // applymap_tok python/05_tokamak/Split_SympGPR/func.py:184-219
 };
 
 constexpr int MAP_CHUNK = 64;        // training points per chunk (one bulk copy)
 constexpr int MAP_GF = 4;            // fields of a guess-GP chunk:      u, v, y, alpha
 constexpr int MAP_TF = 5;            // fields of a symplectic-GP chunk: u, v, y, alpha_q, alpha_P
 
-struct MapArgs {
-    // training sets in chunked structure-of-arrays form: chunk c = [field0(64) field1(64) ...], padded with
-    // neutral points (alpha = 0) to a whole number of chunks, at least two
+// One learned map on the device.  Training sets in chunked structure-of-arrays form: chunk c =
+// [field0(64) field1(64) ...], padded with neutral points (alpha = 0) to a whole number of chunks, at least two.
+struct MapModelDev {
     const double* gch; int nchg;     // ordinary GP (guess)
     const double* tch; int ncht;     // symplectic GP
     HypC h, hp;
+};
+
+struct MapArgs {
+    const MapModelDev* models;       // device table; step s uses models[(s - 1) % nmodels] (split maps cycle, others have one)
+    int nmodels;
     int kind;
     long E, nsteps;
     const double *q0, *p0;

@@ -97,6 +97,7 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     const int nt = (int)(n_pad / TILE);
     const int fam = job.fam;
     if (fam < 0 || fam > 2) { set_error("unknown kernel family %d", fam); return ST_BADARG; }
+    if (job.reg < 0 || job.reg > 3 || (job.reg > 1 && job.ngrad > 0)) { set_error("nll: reg must be 0..3 (gradient only for 0 and 1)"); return ST_BADARG; }
     if (!(job.hyp[0] > 0.0) || !(job.hyp[1] > 0.0)) { set_error("nll: length scales must be positive"); return ST_BADARG; }
     const bool need_inv = job.ngrad > 0 || job.d_kinv != nullptr;
 
@@ -127,7 +128,7 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     c.pev_valid = false;
     SGP_TRY(c.mark(0));
     SGP_TRY(make_points(c, fam, job.per, job.d_x, job.d_x + N, N, pts));
-    if (job.reg) SGP_TRY(fill_reg_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
+    if (job.reg) SGP_TRY(fill_reg_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad, job.reg - 1));
     else SGP_TRY(fill_hess_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
 
     SGP_CUDA(cudaMemsetAsync(yv, 0, (size_t)n_pad * sizeof(double), st));
@@ -135,21 +136,31 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), st));
     SGP_TRY(c.mark(1));
 
-    SGP_TRY(potrf(c, K, n_pad, n_pad, Dinv, logparts, info));
+    // factor + forward substitution L w = z in one kernel (potrf_ll.cu).  0.5 z'alpha = 0.5 w'w, so the value
+    // needs nothing else; alpha itself comes from the backward substitution, or -- when the inverse is formed
+    // anyway -- from one transposed matrix-vector product with the explicit inverse factor.
+    SGP_TRY(potrf(c, K, n_pad, n_pad, Dinv, logparts, info, yv, wv));
     SGP_TRY(c.mark(2));
     if (job.d_L) {
         tril_out_kernel<<<1024, 256, 0, st>>>(K, n_pad, job.d_L, n);
         SGP_CUDA(cudaGetLastError());
         count_launch();
     }
-    SGP_TRY(potrs(c, K, n_pad, n_pad, Dinv, yv, wv, av));
-    if (job.d_alpha) SGP_CUDA(cudaMemcpyAsync(job.d_alpha, av, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    const bool need_alpha = job.d_alpha != nullptr || job.ngrad > 0;
+    const double* dot_a = wv;                      // finalize: 0.5 * dot_a . dot_b
+    const double* dot_b = wv;
+    if (need_alpha && !need_inv) {
+        SGP_CUDA(cudaMemcpyAsync(yv, wv, (size_t)n_pad * sizeof(double), cudaMemcpyDeviceToDevice, st));   // trsv_bwd eats its input
+        SGP_TRY(trsv_bwd(c, K, n_pad, n_pad, Dinv, yv, av));
+    }
     SGP_TRY(c.mark(3));
 
     double* partial = c.partial.as<double>();
     if (need_inv) {
         double* W = c.Wmat.as<double>();
         SGP_TRY(trtri(c, K, n_pad, n_pad, Dinv, c.Tmat.as<double>()));
+        // K now holds X = L^-1: alpha = L^-T w = X^T w is one pass over its columns
+        if (need_alpha) SGP_TRY(gemv_t_lower(c, K, n_pad, n_pad, wv, av));
         SGP_TRY(c.mark(4));
         SGP_TRY(lauum(c, K, n_pad, n_pad, W, n_pad));
         SGP_TRY(c.mark(5));
@@ -163,8 +174,9 @@ int nll_enqueue(Ctx& c, const NllJob& job)
         SGP_TRY(c.mark(4));
         SGP_TRY(c.mark(5));
     }
+    if (job.d_alpha) SGP_CUDA(cudaMemcpyAsync(job.d_alpha, av, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
     SGP_TRY(c.mark(6));
-    finalize_kernel<<<1, 256, 0, st>>>(job.d_z, av, n, logparts, nt, info, partial, job.ngrad > 0 ? npart : 0, job.hyp[2],
+    finalize_kernel<<<1, 256, 0, st>>>(dot_a, dot_b, n, logparts, nt, info, partial, job.ngrad > 0 ? npart : 0, job.hyp[2],
                                        job.ngrad, job.d_res);
     SGP_CUDA(cudaGetLastError());
     count_launch();

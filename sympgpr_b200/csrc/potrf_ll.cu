@@ -37,6 +37,10 @@ struct LLArgs {
     int* info;
     int* ready;            // nt*nt, ready[i + j*nt] = 1 once L(i,j) (and Dinv_j for i == j) is final
     int* abort;
+    // optional fused forward substitution  L w = y  (potrs, first half): the diagonal task of column j also
+    // accumulates v_j = sum_{k<j} L(j,k) w_k from the slabs it streams anyway, then w_j = Dinv_j (y_j - v_j)
+    const double* y;       // n_pad (zero in the padding) or nullptr
+    double* w;             // n_pad
 };
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(LL_CONSUMERS) : "memory"); }
@@ -92,15 +96,25 @@ __device__ __forceinline__ void ll_produce(const double* pa, long lda, const dou
 }
 
 // consumers: acc += sum over nk slabs
+// MATVEC: additionally v += A_slab * wv[k] for the row (tid & 127) of the A slab, k-half (tid >> 7)
+template <bool MATVEC>
 __device__ __forceinline__ void ll_consume(double (&acc)[8][4][2], int nk, uint32_t& it, const double* smem, unsigned long long* full,
-                                           unsigned long long* empty, int wm, int wn, int g, int t, int lane, const volatile int* abort)
+                                           unsigned long long* empty, int wm, int wn, int g, int t, int lane, const volatile int* abort,
+                                           const double* wv = nullptr, int tid = 0, double* vout = nullptr)
 {
+    double v = 0.0;
     for (int kb = 0; kb < nk; kb++, it++) {
         const int s = (int)(it % WS_STAGES);
         const uint32_t ph = (it / WS_STAGES) & 1u;
         mbar_wait_ab(full + s, ph, abort);
         const double* sa = smem + (size_t)s * 2 * STAGE_DOUBLES;
         const double* sb = sa + STAGE_DOUBLES;
+        if (MATVEC) {
+            const int m = tid & (TILE - 1), kh = (tid >> 7) * (GK / 2);
+            const double* wk = wv + (long)kb * GK + kh;
+#pragma unroll
+            for (int kk = 0; kk < GK / 2; kk++) v = fma(sa[(kh + kk) * LDMN + m], __ldcg(wk + kk), v);
+        }
         double af[2][8], bf[2][4];
         load_frags_a<LAYOUT_MN>(sa, wm, g, t, 0, af[0]);
         load_frags_b<LAYOUT_MN>(sb, wn, g, t, 0, bf[0]);
@@ -119,6 +133,7 @@ __device__ __forceinline__ void ll_consume(double (&acc)[8][4][2], int nk, uint3
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + s);
     }
+    if (MATVEC) *vout = v;
 }
 
 // Cholesky factor and inverse of the 128 x 128 tile held in shared memory S[r*LL_LD + c] (lower part),
@@ -258,7 +273,10 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
         for (int ii = 0; ii < 8; ii++)
 #pragma unroll
             for (int jj = 0; jj < 4; jj++) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
-        ll_consume(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort);
+        const bool solve = (i == j) && a.y != nullptr;
+        double vpart = 0.0;
+        if (solve) ll_consume<true>(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort, a.w, tid, &vpart);
+        else ll_consume<false>(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort);
 
         double* tile = a.A + (long)i * TILE + (long)j * TILE * a.lda;
         if (i == j) {
@@ -291,6 +309,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             }
             consumer_bar();
             diag_tile_invert(S, tmp, tid);
+            if (solve) {
+                // w_j = L(j,j)^-1 (y_j - v_j); S holds L(j,j)^-1, the two k-halves of v_j are in vpart
+                tmp[tid] = vpart;
+                consumer_bar();
+                if (tid < TILE) tmp[2 * TILE + tid] = a.y[(long)j * TILE + tid] - (tmp[tid] + tmp[tid + TILE]);
+                consumer_bar();
+                if (tid < TILE) {
+                    double sacc = 0.0;
+                    for (int c = 0; c <= tid; c++) sacc = fma(S[tid * LL_LD + c], tmp[2 * TILE + c], sacc);
+                    a.w[(long)j * TILE + tid] = sacc;
+                }
+            }
             double* Dj = a.Dinv + (long)j * TILE * TILE;
             for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
                 const int rr = idx & (TILE - 1), c = idx >> 7;
@@ -322,7 +352,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             for (int ii = 0; ii < 8; ii++)
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
-            ll_consume(acc, TILE / GK, it, smem, full, empty, wm, wn, g, t, lane, vabort);
+            ll_consume<false>(acc, TILE / GK, it, smem, full, empty, wm, wn, g, t, lane, vabort);
 #pragma unroll
             for (int ii = 0; ii < 8; ii++) {
 #pragma unroll
@@ -351,14 +381,15 @@ size_t potrf_ll_flag_bytes(long n_pad)
 }
 
 // flags: potrf_ll_flag_bytes(n_pad) bytes of device scratch
-int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags)
+int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags, const double* y,
+             double* w)
 {
     static bool configured = false;
     if (!configured) {
         SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
         configured = true;
     }
-    static_assert((size_t)TILE * LL_LD * sizeof(double) + 2 * LL_CONSUMERS * sizeof(double) <= (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double),
+    static_assert((size_t)TILE * LL_LD * sizeof(double) + 3 * LL_CONSUMERS * sizeof(double) <= (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double),
                   "diagonal tile scratch must fit in the operand ring");
     const int nt = (int)(n_pad / TILE);
     const size_t nflags = (size_t)nt * nt;
@@ -366,6 +397,7 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
     LLArgs a;
     a.A = A; a.lda = lda; a.nt = nt; a.Dinv = Dinv; a.logparts = logparts; a.info = info;
     a.ready = flags; a.abort = flags + nflags;
+    a.y = (y && w) ? y : nullptr; a.w = w;
     const long ntasks = (long)nt * (nt + 1) / 2;
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     const unsigned grid = (unsigned)(ntasks < sms ? ntasks : sms);

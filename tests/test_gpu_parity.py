@@ -458,3 +458,91 @@ def test_nan_and_empty_inputs(api, O):
     q, p = api.applymap(3, 0, m["hyp"], m["hypp"], np.zeros(0), np.zeros(0), m["xtp"], m["ztp"], m["Kyinvp"], m["xt"],
                         m["zt"], m["Kyinv"])
     assert q.shape == (3, 0)
+
+
+# ------------------------------------------------------------------------------- explicit maps
+def test_explicit_map_matches_reference_python_layer(api, O):
+    """applymap_expl / calcP_expl / nll_expl (python/04_standard_map/func.py:126-141,174-179,256-285) and the
+    explicit pendulum loop (python/01_pendulum/explicit/func_expl.py:114-128): the GPU path against the
+    reference's own Python functions (tests/golden/path_expl.npz) and against the oracle at a larger size."""
+    g = np.load(os.path.join(G, "path_expl.npz"))
+    N = int(g["N"][0])
+    xt, zt, hyp, Kyinv = g["xtrain"], g["ztrain"], g["hyp"], g["Kyinv"]
+    sig2n = float(g["sig2n"][0])
+    for k, l in enumerate((0.9, 0.5)):
+        assert np.isclose(api.nll_expl([l, hyp[2], sig2n], xt, zt[:N], 2 * N, 0), g["nll_expl_0"][k], rtol=1e-9)
+    for k, l in enumerate((0.6, 0.35)):
+        assert np.isclose(api.nll_expl([l, hyp[2], sig2n], xt, zt[N:], 2 * N, 1), g["nll_expl_1"][k], rtol=1e-9)
+    q0, p0 = g["q0"], g["p0"]
+    for k in range(len(q0)):
+        assert np.isclose(api.calcP_expl(q0[k], p0[k], hyp, xt, zt, Kyinv), g["calcp_expl"][k], rtol=1e-11, atol=1e-11)
+    nm = g["std_q"].shape[0]
+    q, p, pd = api.applymap_expl(nm, len(q0), hyp, q0, p0, xt, zt, Kyinv)
+    assert np.allclose(q, g["std_q"], rtol=1e-9, atol=1e-9) and np.allclose(p, g["std_p"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(pd, g["std_pdiff"], rtol=1e-9, atol=1e-9)
+    q, p = api.applymap_expl_pendulum(hyp, q0, p0, xt, zt, Kyinv, len(q0), nm)
+    assert np.allclose(q, g["pen_q"], rtol=1e-9, atol=1e-9) and np.allclose(p, g["pen_p"], rtol=1e-9, atol=1e-9)
+
+
+@pytest.mark.parametrize("family", ["sum", "product"])
+def test_explicit_map_matches_oracle(api, O, family):
+    """Explicit step with either kernel family, ensemble larger than one warp, training set of several chunks."""
+    Nt = 150
+    d = O.standard_map_training(Nt)
+    xt = np.hstack((d["q"], d["p"]))              # explicit variant: generating function of the OLD momentum
+    zt = d["ztrain"]
+    hyp = np.array([0.4, 0.5, d["sig"]])
+    noise = 1e-2              # cond(Ky) ~ 3e5, |alpha| < 40: a rounding-level change of the sums moves an orbit by
+    #                           ~1e-13 in one step and ~20x more with every further step of this (rough) learned map
+    Kyinv = np.linalg.inv(O.build_k_vec(xt[:Nt], xt[Nt:], xt[:Nt], xt[Nt:], hyp, family) + noise * np.eye(2 * Nt))
+    E, nm = 45, 5
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 1.0 + O.halton(E, 7) * 4.0
+    qr, pr, pdr = O.applymap_expl("standard", nm, q0, p0, hyp, xt[:Nt], xt[Nt:], zt, Kyinv, family)
+    q, p, pd = api.applymap_expl(nm, E, hyp, q0, p0, xt, zt, Kyinv, family=family)
+    assert np.allclose(q[1], qr[1], rtol=1e-11, atol=1e-11) and np.allclose(pd[1], pdr[1], rtol=1e-11, atol=1e-11)
+    # every later step on its own, restarted from the oracle's state (no amplification of rounding differences)
+    for i in range(1, nm - 1):
+        qi, pi, _ = api.applymap_expl(2, E, hyp, qr[i], pr[i], xt, zt, Kyinv, family=family)
+        assert np.allclose(qi[1], qr[i + 1], rtol=1e-11, atol=1e-11) and np.max(_wrapdiff(pi[1], pr[i + 1], True)) < 1e-11
+    # whole trajectories: this rough learned map amplifies a rounding-level difference ~20x per step
+    assert np.allclose(q, qr, rtol=1e-6, atol=1e-6) and np.allclose(pd, pdr, rtol=1e-6, atol=1e-6)
+    assert np.max(_wrapdiff(p, pr, True)) < 1e-6
+    # nll_expl at a size with several tiles
+    for ind, l in ((0, 0.3), (1, 0.4)):
+        y = zt[:Nt] if ind == 0 else zt[Nt:]
+        assert np.isclose(api.nll_expl([l, d["sig"], 1e-3], xt, y, 2 * Nt, ind), O.nll_expl([l, d["sig"], 1e-3], xt, y, 2 * Nt, ind),
+                          rtol=1e-9)
+
+
+# ------------------------------------------------------------------------------- split map (SURVEY 8f row 1)
+def test_split_map_matches_oracle(api, O):
+    """applymap_tok of python/05_tokamak/Split_SympGPR/func.py:184-219: nphmap learned maps in turn, loss test at the
+    new angle, whole turns only.  Four sub-maps = four quarter-strength standard-map kicks, so one turn is a map
+    with regular orbits; training sets / hyper-parameters differ per sub-map."""
+    nph, N = 4, 60
+    xtp = np.zeros((2 * N, nph)); ztp = np.zeros((N, nph)); xt = np.zeros((2 * N, nph)); zt = np.zeros((2 * N, nph))
+    hyp = np.zeros((nph, 3)); hypp = np.zeros((nph, 3)); Kyinv = np.zeros((nph, 2 * N, 2 * N)); Kyinvp = np.zeros((nph, N, N))
+    for m in range(nph):
+        q = O.halton(N, 2, start=1 + 7 * m) * 2 * np.pi
+        p = 0.5 + O.halton(N, 3, start=1 + 5 * m) * 5.0
+        P = p + 0.1 * (1 + 0.2 * m) * np.sin(q)
+        Q = q + 0.25 * P
+        xt[:, m] = np.hstack((q, P)); zt[:, m] = np.concatenate((p - P, Q - q))
+        xtp[:, m] = np.hstack((q, p)); ztp[:, m] = P
+        l = 1.2 + 0.1 * m
+        hyp[m] = [l, l, 2 * np.max(np.abs(zt[:, m]))**2]
+        hypp[m] = [l, l, 2 * np.max(np.abs(ztp[:, m]))**2]
+        Kyinv[m] = np.linalg.inv(O.build_k_vec(q, P, q, P, hyp[m]) + 1e-6 * np.eye(2 * N))
+        Kyinvp[m] = np.linalg.inv(O.buildkreg_vec(q, p, q, p, hypp[m]) + 1e-6 * np.eye(N))
+    E, nm = 9, 14                       # 14 - 4 = 10 -> three whole turns = 12 steps, last row stays zero
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 0.3 + O.halton(E, 7) * 4.5     # some start below the loss boundary region, some get lost
+    qr, pr = O.applymap_tok_split(nph, nm, q0, p0, xtp, ztp, Kyinvp, hypp, xt, zt, Kyinv, hyp)
+    q, p = api.applymap_tok_split(nph, nm, E, q0, p0, xtp, ztp, Kyinvp, hypp, xt, zt, Kyinv, hyp)
+    assert q.shape == (nm, E)
+    assert np.array_equal(np.isnan(p), np.isnan(pr)) and np.array_equal(np.isnan(q), np.isnan(qr))
+    assert np.all(q[13] == 0.0) and np.all(p[13] == 0.0) and np.all(qr[13] == 0.0)
+    assert np.nanmax(_wrapdiff(q, qr, True)) < 1e-8 and np.nanmax(np.abs(p - pr)) < 1e-8
+    q2, p2 = api.applymap_tok_split(nph, nm, E, q0, p0, xtp, ztp, Kyinvp, hypp, xt, zt, Kyinv, hyp, solver="newton")
+    assert np.nanmax(_wrapdiff(q2, qr, True)) < 1e-8 and np.nanmax(np.abs(p2 - pr)) < 1e-8

@@ -193,3 +193,31 @@ def test_odd_dimensions_follow_integer_division():
     assert np.all(K[4, :] == 14.0)
     Kc = C.build_k(x, y, x, y, np.array([0.8, 0.9, 2.0]), rows=5, cols=4)
     assert np.allclose(Kc[:4], K[:4], rtol=1e-13, atol=1e-15)
+
+
+# ------------------------------------------------------------------------------- explicit maps
+def test_explicit_map_oracle_matches_reference_python_layer():
+    """oracle.applymap_expl / calcp_expl / nll_expl against the reference's own applymap_expl, calcP_expl,
+    nll_expl (python/04_standard_map/func.py:126-141,174-179,256-285) and applymap
+    (python/01_pendulum/explicit/func_expl.py:114-128), tests/golden/path_expl.npz."""
+    from oracle import oracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "path_expl.npz"))
+    N = int(g["N"][0])
+    xt, zt, hyp, Kyinv = g["xtrain"], g["ztrain"], g["hyp"], g["Kyinv"]
+    sig2n = float(g["sig2n"][0])
+    K = O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp, "sum")
+    assert np.allclose(K, g["K"], rtol=1e-12, atol=1e-12)
+    for k, l in enumerate((0.9, 0.5)):
+        assert np.isclose(O.nll_expl([l, hyp[2], sig2n], xt, zt[:N], 2 * N, 0), g["nll_expl_0"][k], rtol=1e-10)
+    for k, l in enumerate((0.6, 0.35)):
+        assert np.isclose(O.nll_expl([l, hyp[2], sig2n], xt, zt[N:], 2 * N, 1), g["nll_expl_1"][k], rtol=1e-10)
+    q0, p0 = g["q0"], g["p0"]
+    for k in range(len(q0)):
+        assert np.isclose(O.calcp_expl(q0[k], p0[k], hyp, xt[:N], xt[N:], zt, Kyinv, "sum"), g["calcp_expl"][k], rtol=1e-11,
+                          atol=1e-11)
+    nm = g["std_q"].shape[0]
+    q, p, pd = O.applymap_expl("standard", nm, q0, p0, hyp, xt[:N], xt[N:], zt, Kyinv, "sum")
+    assert np.allclose(q, g["std_q"], rtol=1e-9, atol=1e-9) and np.allclose(p, g["std_p"], rtol=1e-9, atol=1e-9)
+    assert np.allclose(pd, g["std_pdiff"], rtol=1e-9, atol=1e-9)
+    q, p = O.applymap_expl("pendulum", nm, q0, p0, hyp, xt[:N], xt[N:], zt, Kyinv, "sum")
+    assert np.allclose(q, g["pen_q"], rtol=1e-9, atol=1e-9) and np.allclose(p, g["pen_p"], rtol=1e-9, atol=1e-9)

@@ -126,8 +126,15 @@ def run_reference(a):
     if rank != 0:
         return
     steps, warm = max(1, a.steps), max(1, min(a.warmup, 1))
-    v, t_s = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
-    cores = blas_threads()
+    ncpu = os.cpu_count() or 1
+    try:                                    # torchrun exports OMP_NUM_THREADS=1: lift the BLAS/OpenMP limit again
+        from threadpoolctl import threadpool_limits
+        with threadpool_limits(limits=ncpu):
+            v, t_s = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
+            cores = blas_threads()
+    except ImportError:
+        v, t_s = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
+        cores = blas_threads()
     sample = (f"oracle nll_grad (C/NumPy fill, SciPy potrf+potri, elementwise contraction) at N={a.cpu_sample} "
               f"(n={2 * a.cpu_sample}): {t_s:.3f} s/eval, scaled by (n/n_s)^3 to N={a.n_train}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
@@ -317,9 +324,12 @@ def main():
         sync_all()
         stats.zero_()
         m0, m1 = ev(), ev()
+        t_mwall0 = time.time()
         m0.record(stream); map_run(1, a.map_steps); m1.record(stream)
         sync_all()
-        t_map = max_over_ranks(m0.elapsed_time(m1) * 1e-3)
+        t_mwall1 = time.time()
+        t_map_local = m0.elapsed_time(m1) * 1e-3
+        t_map = max_over_ranks(t_map_local)
         st = stats.clone()
         cks = torch.stack([torch.nansum(qf), torch.nansum(pf)])
         if world > 1:                                   # the only collectives of the path: gather statistics
@@ -356,6 +366,7 @@ def main():
                             "h2d_bytes_per_step": int(16 * E + 8 * (3 * Nt + 4 * Nt)), "d2h_bytes_per_step": int(16 * E)},
                     "hybrd_value": float(E) * world * hsteps / t_map_h, "hybrd_steps": hsteps,
                     "unconverged": int(st[1].item()),
+                    "clocks": sampler.summary(t_mwall0, t_mwall1), "rank0_s": t_map_local,
                     "checksum": [float(cks[0].item()), float(cks[1].item())]}
         L.sgp_model_destroy(model)
 

@@ -70,6 +70,61 @@ def test_sharded_ensemble_and_restarts_world2(E, T):
     assert list(out) == [1] * world
 
 
+def _ishigami(X, a=7.0, b=0.1):
+    return np.sin(X[:, 0]) + a * np.sin(X[:, 1])**2 + b * X[:, 2]**4 * np.sin(X[:, 0])
+
+
+def _sobol_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sympgpr_b200 import ensemble as ens
+    calls = []
+
+    def model(X):
+        calls.append(len(X))
+        y = _ishigami(X)
+        y[(X[:, 0] > 3.0) & (X[:, 1] > 3.0)] = np.nan          # "lost orbits" are dropped consistently
+        return y
+    res = ens.sobol_indices_sharded(model, [(-np.pi, np.pi)] * 3, 20001, block=4096)
+    for k, v in (("S1", res["S1"]), ("ST", res["ST"])):
+        out[rank * 8 + (0 if k == "S1" else 3):rank * 8 + (3 if k == "S1" else 6)] = list(v)
+    out[rank * 8 + 6] = res["var"]
+    out[rank * 8 + 7] = float(sum(calls))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sobol_sample_sets_world2():
+    """sample sets split over the ranks, one all-reduce of the estimator sums."""
+    from sympgpr_b200 import ensemble as ens
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("d", [0.0] * (8 * world))
+    procs = [ctx.Process(target=_sobol_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    o = np.array(out[:]).reshape(world, 8)
+    assert np.array_equal(o[0, :7], o[1, :7])                   # every rank holds the same result
+    assert o[0, 7] + o[1, 7] == 20001 * 5                       # rows split, d + 2 runs per row
+    # the same computation in one process
+
+    def model(X):
+        y = _ishigami(X)
+        y[(X[:, 0] > 3.0) & (X[:, 1] > 3.0)] = np.nan
+        return y
+    ref = ens.sobol_indices_sharded(model, [(-np.pi, np.pi)] * 3, 20001, block=100000)
+    assert np.allclose(o[0, :3], ref["S1"], rtol=1e-10, atol=1e-12) and np.allclose(o[0, 3:6], ref["ST"], rtol=1e-10, atol=1e-12)
+    # analytic Ishigami indices (a = 7, b = 0.1): S = (0.3139, 0.4424, 0), ST = (0.5576, 0.4424, 0.2437)
+    clean = ens.sobol_indices_sharded(_ishigami, [(-np.pi, np.pi)] * 3, 60000)
+    assert np.allclose(clean["S1"], [0.3139, 0.4424, 0.0], atol=0.02)
+    assert np.allclose(clean["ST"], [0.5576, 0.4424, 0.2437], atol=0.02)
+
+
 def test_single_process_paths():
     from sympgpr_b200 import ensemble as ens
     q0, p0 = np.linspace(0, 6, 7), np.linspace(1, 2, 7)

@@ -101,6 +101,11 @@ int sgp_build_k(sgp_ctx* ctx, int fam, double per, const double* x, const double
 /* sympgpr.f90:40-60  buildkreg(x,y,x0,y0,hyp,k): (N x N0). */
 int sgp_buildkreg(sgp_ctx* ctx, int fam, double per, const double* x, const double* y, long N,
                   const double* x0, const double* y0, long N0, const double* hyp3, double* K, long ldk);
+/* 2-DOF generalisation of build_k (NOT in the reference; BASELINE config 3): x = [q1; q2; P1; P2]
+ * (4 arrays of N), x0 likewise (N0), hyp3 = [lq, lP, sig]; fills the (4N x 4N0) matrix of the mixed second
+ * derivatives of the SE kernel in (q1, q2, P1, P2), blocks ordered like x.  csrc/dof2.cu. */
+int sgp_build_k4(sgp_ctx* ctx, const double* x, long N, const double* x0, long N0, const double* hyp3,
+                 double* K, long ldk);
 /* sympgpr.f90:62-73  guessp(x,y,hypp,xtrainp,ytrainp,ztrainp,kyinvp) */
 int sgp_guessp(sgp_ctx* ctx, int fam, double per, double x, double y, const double* hypp3,
                const double* xtrainp, const double* ytrainp, const double* ztrainp,
@@ -128,7 +133,9 @@ int sgp_applymap_tok(sgp_ctx* ctx, int fam, double per, int solver, int kind, lo
  * python/02_pert_pendulum/func.py:132-162.  xin = [x(0:N); y(0:N)], z = observations (n),
  * hyp4 = [lx, ly, sig, sig2n]; reg = 0: derivative kernel, n = 2N; reg = 1: plain kernel, n = N;
  * reg = 2 / 3: the (q,q) / (P,P) Hessian block alone, n = N, value only -- nll_expl
- * python/04_standard_map/func.py:126-141 (the sum kernel's matrix is block diagonal and is fitted per block).
+ * python/04_standard_map/func.py:126-141 (the sum kernel's matrix is block diagonal and is fitted per block);
+ * reg = 4: the 2-DOF 4x4-block kernel of sgp_build_k4, n = 4N, xin = [q1; q2; P1; P2], hyp4 = [lq, lP, sig, sig2n],
+ * gradient w.r.t. (lq, lP[, sig]) as for reg = 0.
  * ngrad = 0 value only, 2 or 3 also the gradient.  res: SGP_RES_LEN doubles. */
 int sgp_nll(sgp_ctx* ctx, int fam, double per, int reg, const double* hyp4, const double* xin,
             const double* z, long n, int ngrad, double* res);

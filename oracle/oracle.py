@@ -393,6 +393,79 @@ def nll_expl(hyp, x, y, n, ind, p=0.5):
     return float(0.5 * np.asarray(y, float).dot(alpha) + np.sum(np.log(np.diag(L))))
 
 
+# ------------------------------------------------- X1: 2-DOF 4x4-block kernel (NOT in the reference; parity unpinned)
+def build_k4(x, x0, hyp):
+    """Direct generalisation of build_K (sympgpr.f90:12-38) to F(q1, q2, P1, P2) with the SE kernel of
+    python/03_henon_heiles/init_func.py:24-28 in all four variables, l = (lq, lq, lP, lP):
+    K[aN+i, bN0+j] = sig (delta_ab/l_a^2 - D_a D_b/(l_a^2 l_b^2)) exp(-sum_c D_c^2/(2 l_c^2)), D = u(x_i) - u(x0_j).
+    x = [q1; q2; P1; P2].  Validated by finite differences of the kernel and by its 2x2 sub-blocks
+    reproducing the SE x SE matrix of the reference (tests/test_oracle.py)."""
+    x = np.asarray(x, float); x0 = np.asarray(x0, float)
+    N, N0 = len(x) // 4, len(x0) // 4
+    l = np.array([hyp[0], hyp[0], hyp[1], hyp[1]], float)
+    U = x.reshape(4, N); U0 = x0.reshape(4, N0)
+    D = U[:, :, None] - U0[:, None, :]                          # (4, N, N0)
+    E = np.exp(-0.5 * np.sum(D**2 / l[:, None, None]**2, axis=0))
+    K = np.empty((4 * N, 4 * N0), order="F")
+    for a in range(4):
+        for b in range(4):
+            blk = -D[a] * D[b] / (l[a]**2 * l[b]**2)
+            if a == b:
+                blk = blk + 1.0 / l[a]**2
+            K[a * N:(a + 1) * N, b * N0:(b + 1) * N0] = hyp[2] * blk * E
+    return K
+
+
+def nll_grad4(hyp, x, y, n, with_sig=False):
+    """NLL and its gradient w.r.t. (lq, lP[, sig]) for the 2-DOF kernel, the way nll_grad does it for the 2x2 case
+    (python/02_pert_pendulum/func.py:148-162: -0.5 a' dK a + 0.5 tr(Kyinv dK)); dK by central differences of
+    build_k4 in the length scales is NOT used -- the derivative blocks are written out analytically here and
+    checked against differences in the tests."""
+    x = np.asarray(x, float); y = np.asarray(y, float)
+    N = n // 4
+    lq, lP, sig, noise = float(hyp[0]), float(hyp[1]), float(hyp[2]), abs(float(hyp[3]))
+    K = build_k4(x, x, [lq, lP, sig])
+    Ky = K + noise * np.eye(n)
+    L = scipy.linalg.cholesky(Ky, lower=True)
+    alpha = solve_cholesky(L, y)
+    val = float(0.5 * y.dot(alpha) + np.sum(np.log(np.diag(L))))
+    Kinv = scipy.linalg.cho_solve((L, True), np.eye(n))
+    l = np.array([lq, lq, lP, lP])
+    U = x.reshape(4, N)
+    D = U[:, :, None] - U[:, None, :]
+    E = np.exp(-0.5 * np.sum(D**2 / l[:, None, None]**2, axis=0))
+    grads = []
+    for grp, lg in (((0, 1), lq), ((2, 3), lP)):
+        S = sum(D[c]**2 for c in grp) / lg**3
+        dK = np.empty((n, n))
+        for a in range(4):
+            for b in range(4):
+                ga, gb = 1.0 / l[a]**2, 1.0 / l[b]**2
+                ww = D[a] * D[b] * ga * gb
+                base = (ga if a == b else 0.0) - ww
+                d = base * S + 2.0 * ((a in grp) + (b in grp)) * ww / lg
+                if a == b and a in grp:
+                    d = d - 2.0 * ga / lg
+                dK[a * N:(a + 1) * N, b * N:(b + 1) * N] = sig * d * E
+        grads.append(-0.5 * alpha.dot(dK.dot(alpha)) + 0.5 * np.sum(Kinv * dK))
+    if with_sig:
+        grads.append(-0.5 * alpha.dot(K.dot(alpha)) / sig + 0.5 * np.sum(Kinv * K) / sig)
+    return val, np.array(grads)
+
+
+def henon_like_training(N, seed=3):
+    """Synthetic 2-DOF symplectic map for the X1 tests: one kick-drift step of a Henon-Heiles-like potential,
+    P = p - dt dV/dq(q), Q = q + dt P, V = (q1^2 + q2^2)/2 + q1^2 q2 - q2^3/3; Halton points in [-0.4, 0.4]^4."""
+    dt = 0.3
+    q1 = -0.4 + 0.8 * halton(N, 2, start=seed); q2 = -0.4 + 0.8 * halton(N, 3, start=seed)
+    p1 = -0.4 + 0.8 * halton(N, 5, start=seed); p2 = -0.4 + 0.8 * halton(N, 7, start=seed)
+    P1 = p1 - dt * (q1 + 2 * q1 * q2); P2 = p2 - dt * (q2 + q1**2 - q2**2)
+    Q1 = q1 + dt * P1; Q2 = q2 + dt * P2
+    x = np.concatenate((q1, q2, P1, P2))
+    z = np.concatenate((p1 - P1, p2 - P2, Q1 - q1, Q2 - q2))
+    return x, z
+
+
 # ------------------------------------------------------------------- M5 tokamak
 def compute_r(z, rstart=0.3):
     """fieldlines.f90:94-107 with f_r :82-91, Ath :34-39, dAthdr :42-47

@@ -46,6 +46,7 @@ _PROTOS = {
     "sgp_stage_times": (c_i, [c_vp, c_dp]),
     "sgp_kernel_scalar": (c_d, [c_i, c_i, c_d, c_d, c_d, c_d, c_d, c_d, c_d]),
     "sgp_build_k": (c_i, [c_vp, c_i, c_d, c_dp, c_dp, c_l, c_dp, c_dp, c_l, c_dp, c_dp, c_l]),
+    "sgp_build_k4": (c_i, [c_vp, c_dp, c_l, c_dp, c_l, c_dp, c_dp, c_l]),
     "sgp_buildkreg": (c_i, [c_vp, c_i, c_d, c_dp, c_dp, c_l, c_dp, c_dp, c_l, c_dp, c_dp, c_l]),
     "sgp_guessp": (c_i, [c_vp, c_i, c_d, c_d, c_d, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp]),
     "sgp_calcq": (c_i, [c_vp, c_i, c_d, c_d, c_d, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp]),

@@ -119,11 +119,11 @@ def _nll(hyp, x, y, n, reg, ngrad, family, per):
     if hyp.size != 4:
         raise ValueError("hyp must be [lx, ly, sig, sig2n]")
     n = int(n)
-    N = n if reg else n // 2
+    nx = n if int(reg) in (0, 4) else 2 * n          # coordinates: [x; y] (2N values) or [q1; q2; P1; P2] (reg = 4)
     x = as_f64(x).ravel()
     y = as_f64(y).ravel()
-    if x.size < 2 * N or y.size < n:
-        raise ValueError("nll: x must hold 2N values and y n values")
+    if x.size < nx or y.size < n:
+        raise ValueError("nll: x must hold the coordinates of all points and y n values")
     res = np.zeros(RES_LEN)
     st = _lib.lib().sgp_nll(_lib.context().handle, _fam(family), per, int(reg), dptr(hyp), dptr(x), dptr(y), n, ngrad,
                             dptr(res))
@@ -161,6 +161,32 @@ def nll_grad_reg(hyp, x, y, N, family="product", per=0.5):
     """python/02_pert_pendulum/func.py:132-146."""
     r = _nll(hyp, x, y, N, True, 2, family, per)
     return float(r[RES_NLL]), np.array([r[RES_DLX], r[RES_DLX + 1]])
+
+
+# --------------------------------------------------------------------------- 2-DOF 4x4-block kernel (not in the reference)
+def build_k4(x, x0, hyp, K):
+    """2-DOF generalisation of build_K (BASELINE config 3; csrc/dof2.cu): x = [q1; q2; P1; P2]
+    (4N values), x0 likewise, hyp = [lq, lP, sig]; fills the Fortran-ordered (4N, 4N0) array K in place."""
+    K = _inout_matrix(K)
+    if not K.flags.f_contiguous:
+        raise ValueError("failed to initialize intent(inout) array -- input not Fortran contiguous")
+    x, x0, hyp = as_f64(x).ravel(), as_f64(x0).ravel(), _hyp3(hyp)
+    N, N0 = K.shape[0] // 4, K.shape[1] // 4
+    if x.size < 4 * N or x0.size < 4 * N0:
+        raise ValueError("build_k4: point arrays shorter than the matrix dimensions require")
+    check(_lib.lib().sgp_build_k4(_lib.context().handle, dptr(x), N, dptr(x0), N0, dptr(hyp), dptr(K), max(K.shape[0], 1)), "build_k4")
+
+
+def nll_chol4(hyp, x, y, n):
+    """NLL of the 2-DOF derivative-kernel GP: hyp = [lq, lP, sig, sig2n], x = [q1; q2; P1; P2], y the n = 4N observations
+    [p1 - P1; p2 - P2; Q1 - q1; Q2 - q2]."""
+    return float(_nll(hyp, x, y, n, 4, 0, "sq", 0.5)[RES_NLL])
+
+
+def nll_grad4(hyp, x, y, n, with_sig=False):
+    """(value, gradient w.r.t. [lq, lP(, sig)]) of the 2-DOF derivative-kernel NLL."""
+    r = _nll(hyp, x, y, n, 4, 3 if with_sig else 2, "sq", 0.5)
+    return float(r[RES_NLL]), np.array(r[RES_DLX:RES_DLX + (3 if with_sig else 2)])
 
 
 def nll_expl(hyp, x, y, N, ind, family="sum", per=0.5):

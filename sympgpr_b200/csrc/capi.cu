@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "chol.cuh"
+#include "dof2.cuh"
 #include "fill.cuh"
 #include "grad.cuh"
 #include "map.cuh"
@@ -336,6 +337,24 @@ int sgp_build_k(sgp_ctx* ctx, int fam, double per, const double* x, const double
                 long N0, const double* hyp3, double* K, long ldk)
 {
     return fill_host(ctx, 0, fam, per, x, y, N, x0, y0, N0, hyp3, K, ldk);
+}
+
+int sgp_build_k4(sgp_ctx* ctx, const double* x, long N, const double* x0, long N0, const double* hyp3, double* K, long ldk)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (N < 0 || N0 < 0 || !hyp3 || (N > 0 && N0 > 0 && (!K || ldk < 4 * N))) { set_error("build_k4: bad arguments"); return ST_BADARG; }
+    if (N == 0 || N0 == 0) return ST_OK;
+    const size_t rows = 4 * (size_t)N, cols = 4 * (size_t)N0;
+    SGP_TRY(c.io.reserve((rows + cols + 8) * sizeof(double)));
+    SGP_TRY(c.Kmat.reserve(rows * cols * sizeof(double)));
+    double* dx = c.io.as<double>(); double* dx0 = dx + rows;
+    SGP_TRY(upload(c, dx, x, rows));
+    SGP_TRY(upload(c, dx0, x0, cols));
+    SGP_TRY(fill4(c, dx, N, dx0, N0, hyp3[0], hyp3[1], hyp3[2], c.Kmat.as<double>(), (long)rows));
+    SGP_CUDA(cudaMemcpy2DAsync(K, (size_t)ldk * sizeof(double), c.Kmat.p, rows * sizeof(double), rows * sizeof(double), cols,
+                               cudaMemcpyDeviceToHost, c.stream));
+    return sync(c);
 }
 
 int sgp_buildkreg(sgp_ctx* ctx, int fam, double per, const double* x, const double* y, long N, const double* x0, const double* y0,
@@ -713,12 +732,12 @@ static int nll_host(sgp_ctx* ctx, int fam, double per, int reg, const double* hy
     SGP_TRY(check_ctx(ctx));
     Ctx& c = ctx->c;
     if (!hyp4 || !xin || !z || n <= 0 || (ngrad != 0 && ngrad != 2 && ngrad != 3)) { set_error("nll: bad arguments"); return ST_BADARG; }
-    const long N = reg ? n : n / 2;
+    const long nx = (reg == 4) ? n : (reg ? 2 * n : n);      // coordinates in xin: [x; y] or [q1; q2; P1; P2]
     const size_t out_mats = (kyinv ? (size_t)n * n : 0) + (L ? (size_t)n * n : 0);
-    SGP_TRY(c.io.reserve(((size_t)(2 * N + 2 * n) + RES_DOUBLES + out_mats + 8) * sizeof(double)));
+    SGP_TRY(c.io.reserve(((size_t)(nx + 2 * n) + RES_DOUBLES + out_mats + 8) * sizeof(double)));
     double* d = c.io.as<double>();
-    double *dx = d, *dz = dx + 2 * N, *dres = dz + n, *dal = dres + RES_DOUBLES, *dki = dal + n, *dL = dki + (kyinv ? (size_t)n * n : 0);
-    SGP_TRY(upload(c, dx, xin, 2 * N));
+    double *dx = d, *dz = dx + nx, *dres = dz + n, *dal = dres + RES_DOUBLES, *dki = dal + n, *dL = dki + (kyinv ? (size_t)n * n : 0);
+    SGP_TRY(upload(c, dx, xin, nx));
     SGP_TRY(upload(c, dz, z, n));
     NllJob j;
     j.fam = fam; j.per = per; j.reg = reg;

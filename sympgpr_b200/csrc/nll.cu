@@ -10,6 +10,7 @@
 
 #include "chol.cuh"
 #include "fill.cuh"
+#include "dof2.cuh"
 #include "grad.cuh"
 
 namespace sgp {
@@ -92,12 +93,14 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     const long n = job.n;
     if (n <= 0) { set_error("nll: empty problem (n = %ld)", n); return ST_BADARG; }
     if (!job.reg && (n % 2)) { set_error("nll: derivative-kernel order must be even, got %ld", n); return ST_BADARG; }
-    const long N = job.reg ? n : n / 2;
+    if (job.reg == 4 && (n % 4)) { set_error("nll: the order of the 2-DOF derivative kernel must be a multiple of 4, got %ld", n); return ST_BADARG; }
+    const bool dof2 = job.reg == 4;
+    const long N = dof2 ? n / 4 : (job.reg ? n : n / 2);
     const long n_pad = round_up(n, TILE);
     const int nt = (int)(n_pad / TILE);
     const int fam = job.fam;
     if (fam < 0 || fam > 2) { set_error("unknown kernel family %d", fam); return ST_BADARG; }
-    if (job.reg < 0 || job.reg > 3 || (job.reg > 1 && job.ngrad > 0)) { set_error("nll: reg must be 0..3 (gradient only for 0 and 1)"); return ST_BADARG; }
+    if (job.reg < 0 || job.reg > 4 || ((job.reg == 2 || job.reg == 3) && job.ngrad > 0)) { set_error("nll: reg must be 0..4 (no gradient for 2 and 3)"); return ST_BADARG; }
     if (!(job.hyp[0] > 0.0) || !(job.hyp[1] > 0.0)) { set_error("nll: length scales must be positive"); return ST_BADARG; }
     const bool need_inv = job.ngrad > 0 || job.d_kinv != nullptr;
 
@@ -105,7 +108,7 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     SGP_TRY(c.Dinv.reserve((size_t)nt * TILE * TILE * sizeof(double)));
     SGP_TRY(c.vecs.reserve((size_t)4 * n_pad * sizeof(double)));
     SGP_TRY(c.pts.reserve((size_t)N * sizeof(Pt)));
-    const long npart = need_inv ? grad_num_partials(N) : 0;
+    const long npart = need_inv ? (dof2 ? grad4_num_partials(N) : grad_num_partials(N)) : 0;
     SGP_TRY(c.partial.reserve((size_t)(npart * 6 + 8) * sizeof(double)));
     SGP_TRY(c.small.reserve((size_t)(nt + 8) * sizeof(double)));
     if (need_inv) {
@@ -127,9 +130,14 @@ int nll_enqueue(Ctx& c, const NllJob& job)
 
     c.pev_valid = false;
     SGP_TRY(c.mark(0));
-    SGP_TRY(make_points(c, fam, job.per, job.d_x, job.d_x + N, N, pts));
-    if (job.reg) SGP_TRY(fill_reg_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad, job.reg - 1));
-    else SGP_TRY(fill_hess_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
+    if (dof2) {
+        // 2-DOF 4x4-block kernel (dof2.cu; not in the reference): coordinates are used as they are
+        SGP_TRY(fill4_sym(c, job.d_x, N, job.hyp[0], job.hyp[1], job.hyp[2], noise, K, n_pad, n_pad));
+    } else {
+        SGP_TRY(make_points(c, fam, job.per, job.d_x, job.d_x + N, N, pts));
+        if (job.reg) SGP_TRY(fill_reg_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad, job.reg - 1));
+        else SGP_TRY(fill_hess_sym(c, fam, pts, N, h, noise, K, n_pad, n_pad));
+    }
 
     SGP_CUDA(cudaMemsetAsync(yv, 0, (size_t)n_pad * sizeof(double), st));
     SGP_CUDA(cudaMemcpyAsync(yv, job.d_z, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -164,7 +172,10 @@ int nll_enqueue(Ctx& c, const NllJob& job)
         SGP_TRY(c.mark(4));
         SGP_TRY(lauum(c, K, n_pad, n_pad, W, n_pad));
         SGP_TRY(c.mark(5));
-        if (job.ngrad > 0) SGP_TRY(grad_contract(c, fam, job.reg, pts, N, h, W, n_pad, av, partial));
+        if (job.ngrad > 0) {
+            if (dof2) SGP_TRY(grad4_contract(c, job.d_x, N, job.hyp[0], job.hyp[1], job.hyp[2], W, n_pad, av, partial));
+            else SGP_TRY(grad_contract(c, fam, job.reg, pts, N, h, W, n_pad, av, partial));
+        }
         if (job.d_kinv) {
             sym_out_kernel<<<1024, 256, 0, st>>>(W, n_pad, job.d_kinv, n);
             SGP_CUDA(cudaGetLastError());

@@ -221,3 +221,45 @@ def test_explicit_map_oracle_matches_reference_python_layer():
     assert np.allclose(pd, g["std_pdiff"], rtol=1e-9, atol=1e-9)
     q, p = O.applymap_expl("pendulum", nm, q0, p0, hyp, xt[:N], xt[N:], zt, Kyinv, "sum")
     assert np.allclose(q, g["pen_q"], rtol=1e-9, atol=1e-9) and np.allclose(p, g["pen_p"], rtol=1e-9, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------- X1: 2-DOF 4x4-block kernel
+def test_dof2_kernel_oracle_is_self_consistent():
+    """No reference code exists for the 4x4-block kernel (parity unpinned).  The oracle is
+    validated instead: (i) its (q1,P1) sub-blocks reproduce the reference's SE x SE Hessian-block matrix when the
+    second degree of freedom is frozen, (ii) blocks are the mixed second differences of the kernel, (iii) the
+    analytic NLL gradient matches central differences, (iv) the matrix is symmetric positive definite."""
+    from oracle import oracle as O
+    N = 7
+    q = np.linspace(0, 1, N); P = np.linspace(0.3, 1.1, N)
+    x4 = np.concatenate((q, np.full(N, 0.2), P, np.full(N, -0.1)))
+    K4 = O.build_k4(x4, x4, [0.6, 0.7, 1.3])
+    K2 = O.build_k_vec(q, P, q, P, [0.6, 0.7, 1.3], "sq")
+    sel = np.r_[0:N, 2 * N:3 * N]
+    assert np.allclose(K4[np.ix_(sel, sel)], K2, rtol=1e-13, atol=1e-14)
+    # (ii) finite differences of k(u, u') = sig exp(-sum (u-u')^2 / 2 l^2)
+    l = np.array([0.6, 0.6, 0.7, 0.7]); sig = 1.3
+    rng = np.random.default_rng(1)
+    u, v = rng.uniform(-1, 1, 4), rng.uniform(-1, 1, 4)
+
+    def k(a, b):
+        return sig * np.exp(-0.5 * np.sum((a - b)**2 / l**2))
+    Kuv = O.build_k4(u, v, [0.6, 0.7, sig])               # N = N0 = 1: a 4 x 4 matrix
+    h = 1e-4
+    for a in range(4):
+        for b in range(4):
+            ea, eb = np.eye(4)[a] * h, np.eye(4)[b] * h
+            fd = (k(u + ea, v + eb) - k(u + ea, v - eb) - k(u - ea, v + eb) + k(u - ea, v - eb)) / (4 * h * h)
+            assert abs(Kuv[a, b] - fd) < 1e-6 * max(1.0, abs(fd)), (a, b, Kuv[a, b], fd)
+    # (iii), (iv)
+    x, z = O.henon_like_training(25)
+    hyp = np.array([0.6, 0.7, 2 * np.max(np.abs(z))**2, 1e-6])
+    K = O.build_k4(x, x, hyp[:3])
+    assert np.allclose(K, K.T, rtol=0, atol=1e-12) and np.linalg.eigvalsh(K + 1e-6 * np.eye(100)).min() > 0
+    v0, g = O.nll_grad4(hyp, x, z, 100, with_sig=True)
+    for kk in range(3):
+        e = 1e-5 * hyp[kk]
+        hp_, hm_ = hyp.copy(), hyp.copy()
+        hp_[kk] += e; hm_[kk] -= e
+        fd = (O.nll_grad4(hp_, x, z, 100)[0] - O.nll_grad4(hm_, x, z, 100)[0]) / (2 * e)
+        assert np.isclose(g[kk], fd, rtol=1e-6), (kk, g[kk], fd)

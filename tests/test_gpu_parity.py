@@ -519,6 +519,19 @@ def test_explicit_map_matches_oracle(api, O, family):
 
 
 # ------------------------------------------------------------------------------- split map
+def test_split_map_matches_reference_loop(api):
+    """The GPU split map against the reference's own applymap_tok loop (Split_SympGPR/func.py:184-219) run in the
+    build container with oracle-backed f2py adapters (tests/golden/make_golden_split.py)."""
+    g = np.load(os.path.join(G, "path_split.npz"))
+    nm, E = g["qmap"].shape
+    for solver in ("hybrd", "newton"):
+        q, p = api.applymap_tok_split(int(g["nph"][0]), nm, E, g["q0"], g["p0"], g["xtp"], g["ztp"], g["Kyinvp"], g["hypp"],
+                                      g["xt"], g["zt"], g["Kyinv"], g["hyp"], solver=solver)
+        assert np.array_equal(np.isnan(p), np.isnan(g["pmap"])) and np.array_equal(np.isnan(q), np.isnan(g["qmap"]))
+        assert np.nanmax(_wrapdiff(q, g["qmap"], True)) < 1e-8 and np.nanmax(np.abs(p - g["pmap"])) < 1e-8
+        assert np.all(q[-1] == 0.0) and np.all(p[-1] == 0.0)
+
+
 def test_split_map_matches_oracle(api, O):
     """applymap_tok of python/05_tokamak/Split_SympGPR/func.py:184-219: nphmap learned maps in turn, loss test at the
     new angle, whole turns only.  Four sub-maps = four quarter-strength standard-map kicks, so one turn is a map

@@ -263,3 +263,17 @@ def test_dof2_kernel_oracle_is_self_consistent():
         hp_[kk] += e; hm_[kk] -= e
         fd = (O.nll_grad4(hp_, x, z, 100)[0] - O.nll_grad4(hm_, x, z, 100)[0]) / (2 * e)
         assert np.isclose(g[kk], fd, rtol=1e-6), (kk, g[kk], fd)
+
+
+def test_split_map_oracle_matches_reference_loop():
+    """oracle.applymap_tok_split against the reference's own applymap_tok loop
+    (python/05_tokamak/Split_SympGPR/func.py:184-219, tests/golden/make_golden_split.py)."""
+    from oracle import oracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "path_split.npz"))
+    nm = g["qmap"].shape[0]
+    q, p = O.applymap_tok_split(int(g["nph"][0]), nm, g["q0"], g["p0"], g["xtp"], g["ztp"], g["Kyinvp"], g["hypp"], g["xt"],
+                                g["zt"], g["Kyinv"], g["hyp"])
+    assert np.array_equal(np.isnan(p), np.isnan(g["pmap"])) and np.isnan(g["pmap"]).any()
+    assert np.allclose(q, g["qmap"], rtol=1e-10, atol=1e-10, equal_nan=True)
+    assert np.allclose(p, g["pmap"], rtol=1e-10, atol=1e-10, equal_nan=True)
+    assert np.all(g["qmap"][-1] == 0.0)          # whole turns only: the last row was never written

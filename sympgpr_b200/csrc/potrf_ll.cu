@@ -23,6 +23,9 @@
 // is set and the launcher reports an error -- the kernel cannot hang the device.
 #include "chol.cuh"
 
+#include <stdlib.h>
+#include <vector>
+
 namespace sgp {
 
 namespace {
@@ -41,6 +44,7 @@ struct LLArgs {
     // accumulates v_j = sum_{k<j} L(j,k) w_k from the slabs it streams anyway, then w_j = Dinv_j (y_j - v_j)
     const double* y;       // n_pad (zero in the padding) or nullptr
     double* w;             // n_pad
+    unsigned long long* dbg;   // optional (SGP_LL_TRACE=1): 8 globaltimer stamps per task [task*8 + k], else nullptr
 };
 
 __device__ __forceinline__ void consumer_bar() { asm volatile("bar.sync 1, %0;\n" ::"n"(LL_CONSUMERS) : "memory"); }
@@ -268,6 +272,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
 
         int i, j;
         ll_ticket(task, nt, i, j);
+        unsigned long long* dbg = a.dbg ? a.dbg + task * 8 : nullptr;
+        if (dbg && tid == 0) { dbg[0] = globaltimer(); dbg[7] = ((unsigned long long)i << 32) | (unsigned)j; }
         double acc[8][4][2];
 #pragma unroll
         for (int ii = 0; ii < 8; ii++)
@@ -278,6 +284,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
         if (solve) ll_consume<true>(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort, a.w, tid, &vpart);
         else ll_consume<false>(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort);
 
+        if (dbg && tid == 0) dbg[1] = globaltimer();           // main loop done
         double* tile = a.A + (long)i * TILE + (long)j * TILE * a.lda;
         if (i == j) {
             // ---- diagonal tile: S = A(j,j) - acc in shared memory (ring is idle: the producer waits on c2p)
@@ -295,7 +302,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             }
             consumer_bar();
             double mylog;
+            if (dbg && tid == 0) dbg[2] = globaltimer();       // S built
             diag_tile_factor(S, tmp, tid, a.info, j * TILE, mylog);
+            if (dbg && tid == 0) dbg[3] = globaltimer();       // factored
             for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
                 const int rr = idx & (TILE - 1), c = idx >> 7;
                 tile[rr + (long)c * a.lda] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
@@ -309,6 +318,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             }
             consumer_bar();
             diag_tile_invert(S, tmp, tid);
+            if (dbg && tid == 0) dbg[4] = globaltimer();       // inverted
             if (solve) {
                 // w_j = L(j,j)^-1 (y_j - v_j); S holds L(j,j)^-1, the two k-halves of v_j are in vpart
                 tmp[tid] = vpart;
@@ -331,6 +341,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             if (tid == 0) {
                 st_release(a.ready + j + (long)j * nt, 1);
                 mbar_arrive(c2p);                            // the producer may refill the ring
+                if (dbg) dbg[5] = globaltimer();
             }
         } else {
             // ---- off-diagonal tile: C' = A(i,j) - acc, in place; then L(i,j) = C' Dinv_j^T through the ring
@@ -348,6 +359,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             fence_proxy_async();
             consumer_bar();
             if (tid == 0) mbar_arrive(c2p);                  // producer: C' is in global memory
+            if (dbg && tid == 0) dbg[2] = globaltimer();
 #pragma unroll
             for (int ii = 0; ii < 8; ii++)
 #pragma unroll
@@ -366,6 +378,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             __threadfence();
             consumer_bar();
             if (tid == 0) st_release(a.ready + i + (long)j * nt, 1);
+            if (dbg && tid == 0) dbg[5] = globaltimer();
         }
     }
 }
@@ -398,12 +411,39 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
     a.A = A; a.lda = lda; a.nt = nt; a.Dinv = Dinv; a.logparts = logparts; a.info = info;
     a.ready = flags; a.abort = flags + nflags;
     a.y = (y && w) ? y : nullptr; a.w = w;
+    a.dbg = nullptr;
+    // SGP_LL_TRACE=1: per-task time stamps (tools/ll_trace.py), dumped to $SGP_LL_TRACE_FILE after the launch
+    static const int trace = [] { const char* v = getenv("SGP_LL_TRACE"); return (v && v[0] == '1') ? 1 : 0; }();
+    static DBuf tracebuf;
+    const long ntasks_all = (long)nt * (nt + 1) / 2;
+    if (trace) {
+        SGP_TRY(tracebuf.reserve((size_t)ntasks_all * 8 * sizeof(unsigned long long)));
+        SGP_CUDA(cudaMemsetAsync(tracebuf.p, 0, (size_t)ntasks_all * 8 * sizeof(unsigned long long), c.stream));
+        a.dbg = tracebuf.as<unsigned long long>();
+    }
     const long ntasks = (long)nt * (nt + 1) / 2;
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     const unsigned grid = (unsigned)(ntasks < sms ? ntasks : sms);
     void* args[] = {&a};
     SGP_CUDA(cudaLaunchCooperativeKernel((const void*)potrf_ll_kernel, dim3(grid), dim3(WS_THREADS), args, LL_SMEM, c.stream));
     count_launch();
+    if (trace) {
+        std::vector<unsigned long long> h((size_t)ntasks_all * 8);
+        SGP_CUDA(cudaStreamSynchronize(c.stream));
+        SGP_CUDA(cudaMemcpy(h.data(), tracebuf.p, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        const char* fn = getenv("SGP_LL_TRACE_FILE");
+        FILE* f = fopen(fn ? fn : "potrf_ll_trace.txt", "w");
+        if (f) {
+            unsigned long long t0 = ~0ull;
+            for (long t = 0; t < ntasks_all; t++) if (h[t * 8] && h[t * 8] < t0) t0 = h[t * 8];
+            for (long t = 0; t < ntasks_all; t++) {
+                fprintf(f, "%ld %d %d", t, (int)(h[t * 8 + 7] >> 32), (int)(h[t * 8 + 7] & 0xffffffffu));
+                for (int k = 0; k < 6; k++) fprintf(f, " %lld", h[t * 8 + k] ? (long long)(h[t * 8 + k] - t0) : -1ll);
+                fprintf(f, "\n");
+            }
+            fclose(f);
+        }
+    }
     return ST_OK;
 }
 

@@ -512,9 +512,9 @@ def test_explicit_map_matches_oracle(api, O, family):
     assert np.allclose(q, qr, rtol=1e-6, atol=1e-6) and np.allclose(pd, pdr, rtol=1e-6, atol=1e-6)
     assert np.max(_wrapdiff(p, pr, True)) < 1e-6
     # nll_expl at a size with several tiles
-    for ind, l in ((0, 0.3), (1, 0.4)):
+    for ind, l in ((0, 0.1), (1, 0.1)):           # cond ~ 2e5 / 4e5 with this noise (1e7 at l = 0.4, noise 1e-3)
         y = zt[:Nt] if ind == 0 else zt[Nt:]
-        assert np.isclose(api.nll_expl([l, d["sig"], 1e-3], xt, y, 2 * Nt, ind), O.nll_expl([l, d["sig"], 1e-3], xt, y, 2 * Nt, ind),
+        assert np.isclose(api.nll_expl([l, d["sig"], 0.1], xt, y, 2 * Nt, ind), O.nll_expl([l, d["sig"], 0.1], xt, y, 2 * Nt, ind),
                           rtol=1e-9)
 
 

@@ -140,6 +140,7 @@ __device__ __forceinline__ void ll_consume(double (&acc)[8][4][2], int nk, uint3
     if (MATVEC) *vout = v;
 }
 
+// (unblocked variant, used by the kernel instantiation for large matrices)
 // Cholesky factor and inverse of the 128 x 128 tile held in shared memory S[r*LL_LD + c] (lower part),
 // by the 256 consumer threads.  Unblocked right-looking factorisation, then the unblocked inverse of
 // the triangular factor (last column first).  Returns this thread's share of sum(log diag L).
@@ -204,6 +205,189 @@ __device__ void diag_tile_invert(double* S, double* tmp, int tid)
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Diagonal tile: Cholesky factor L and inverse X = L^-1 of a 128 x 128 block in shared memory, blocked 4 x 4
+// with 32 x 32 blocks so that block-wide barriers are per PHASE (about 30), not per column (the unblocked
+// version took 123 us + 138 us and paced the whole factorisation for n <= 16k; tools/ll_trace.py).
+//   layout: S[r*LL_LD + c]; lower triangle (r >= c): the matrix, then L.  The inverse is kept TRANSPOSED in the
+//   strict upper triangle: X(r,c) = S[c*LL_LD + r] for r > c, diagonal X(c,c) = xd[c].
+//   per block column kb:  warp 0 factors the 32 x 32 diagonal block and inverts it (warp-synchronous);
+//                         all: panel L(i, kb) = A(i, kb) X_kk^T; trailing A(i,c) -= L(i,kb) L(c,kb)^T
+//   then per block row bi = 1..3:  T = sum_k L(bi,k) X(k, 0..bi-1),  X(bi, 0..bi-1) = -X_bibi T.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int DB = 32;
+
+
+// warp 0 only.  Factor the diagonal block at k0 in place (lower), write its inverse transposed into the block's
+// strict upper triangle and 1/l_cc into xd[].  Warp-synchronous, operands in shared memory.  (Two register-
+// resident variants -- rows exchanged by shuffles, or broadcast through a line of shared memory -- were slower:
+// under the 168-register budget of a 288-thread CTA they spill, also into the DMMA main loop.)
+__device__ __forceinline__ void warp_potrf32(double* S, int k0, double* xd, int* info, int col0, int lane)
+{
+    double* Sr = S + (k0 + lane) * LL_LD + k0;              // row `lane` of the block
+    for (int j = 0; j < DB; j++) {
+        double d = S[(k0 + j) * LL_LD + k0 + j];
+        if (!(d > 0.0)) {                                    // also NaN
+            if (lane == 0) atomicCAS(info, 0, col0 + k0 + j + 1);
+            d = 1.0;
+        }
+        // 1/sqrt(d) by rsqrt (1 ulp) and l_jj = d * rsqrt(d): the correctly rounded sqrt + divide sequences cost
+        // ~800 cycles per column on the critical path of the whole factorisation; log(l_jj) is taken later, in parallel
+        const double inv = rsqrt(d), dj = d * inv;
+        __syncwarp();                                        // every lane has read the pivot
+        if (lane > j) Sr[j] *= inv;
+        else if (lane == j) { Sr[j] = dj; xd[k0 + j] = inv; }
+        __syncwarp();
+        if (lane > j) {
+            const double l = Sr[j];
+            const double* Cj = S + k0 * LL_LD + k0 + j;      // Cj[c*LL_LD] = L(c, j)
+            int c = j + 1;
+            for (; c + 3 <= lane; c += 4) {
+                const double l0 = Cj[c * LL_LD], l1 = Cj[(c + 1) * LL_LD], l2 = Cj[(c + 2) * LL_LD], l3 = Cj[(c + 3) * LL_LD];
+                const double a0 = Sr[c], a1 = Sr[c + 1], a2 = Sr[c + 2], a3 = Sr[c + 3];
+                Sr[c] = fma(-l, l0, a0); Sr[c + 1] = fma(-l, l1, a1); Sr[c + 2] = fma(-l, l2, a2); Sr[c + 3] = fma(-l, l3, a3);
+            }
+            for (; c <= lane; c++) Sr[c] = fma(-l, Cj[c * LL_LD], Sr[c]);
+        }
+        __syncwarp();
+    }
+    // inverse of the block: lane = column c, forward substitution down the column; X(r,c) -> S[(k0+c)][k0+r]
+    {
+        const int c = lane;
+        double* Xc = S + (k0 + c) * LL_LD + k0;             // Xc[r] = X(r, c) for r > c
+        for (int r = c + 1; r < DB; r++) {
+            const double* Lr = S + (k0 + r) * LL_LD + k0;   // row r of L
+            double s0 = Lr[c] * xd[k0 + c], s1 = 0.0;
+            int k = c + 1;
+            for (; k + 1 < r; k += 2) {
+                s0 = fma(Lr[k], Xc[k], s0);
+                s1 = fma(Lr[k + 1], Xc[k + 1], s1);
+            }
+            if (k < r) s0 = fma(Lr[k], Xc[k], s0);
+            Xc[r] = -(s0 + s1) * xd[k0 + r];
+        }
+    }
+    __syncwarp();
+}
+
+// all 256 consumer threads; S lower = matrix on entry, L on exit; upper/xd = X^T; scratch: >= 32*96 doubles
+__device__ void diag_tile_factor_invert(double* S, double* xd, double* scratch, int tid, int* info, int col0, double* logout,
+                                        unsigned long long* stamp)
+{
+    const int lane = tid & 31;
+    for (int kb = 0; kb < TILE / DB; kb++) {
+        const int k0 = kb * DB, R0 = k0 + DB, nrows = TILE - R0;
+        unsigned long long tw0 = 0ull;
+        if (stamp && tid == 0) tw0 = globaltimer();
+        if (tid < 32) warp_potrf32(S, k0, xd, info, col0, lane);
+        if (stamp && tid == 0) stamp[3] += globaltimer() - tw0;      // trace: time in the warp-level block factorisations
+        consumer_bar();
+        if (nrows > 0) {
+            // panel: L(i, k0+c) = sum_{k<=c} A(i, k0+k) X_kk(c, k); results held back until every thread has read A
+            double out[12];
+#pragma unroll
+            for (int u = 0; u < 12; u++) {
+                const int idx = tid + u * LL_CONSUMERS;
+                out[u] = 0.0;
+                if (idx < nrows * DB) {
+                    const int i = R0 + idx % nrows, c = idx / nrows;
+                    const double* Ai = S + i * LL_LD + k0;
+                    double s0 = Ai[c] * xd[k0 + c], s1 = 0.0;
+                    int k = 0;
+                    for (; k + 1 < c; k += 2) {
+                        s0 = fma(Ai[k], S[(k0 + k) * LL_LD + k0 + c], s0);
+                        s1 = fma(Ai[k + 1], S[(k0 + k + 1) * LL_LD + k0 + c], s1);
+                    }
+                    if (k < c) s0 = fma(Ai[k], S[(k0 + k) * LL_LD + k0 + c], s0);
+                    out[u] = s0 + s1;
+                }
+            }
+            consumer_bar();
+#pragma unroll
+            for (int u = 0; u < 12; u++) {
+                const int idx = tid + u * LL_CONSUMERS;
+                if (idx < nrows * DB) S[(R0 + idx % nrows) * LL_LD + k0 + idx / nrows] = out[u];
+            }
+            consumer_bar();
+            // trailing update: A(i, c) -= sum_k L(i, k0+k) L(c, k0+k) for R0 <= c <= i; 1 row x 4 columns per item
+            const int ncg = nrows / 4;
+            for (int idx = tid; idx < nrows * ncg; idx += LL_CONSUMERS) {
+                const int i = R0 + idx % nrows, c0 = R0 + 4 * (idx / nrows);
+                if (c0 > i) continue;
+                const double* Li = S + i * LL_LD + k0;
+                const double* Lc = S + c0 * LL_LD + k0;
+                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+#pragma unroll 8
+                for (int k = 0; k < DB; k++) {
+                    const double l = Li[k];
+                    s0 = fma(l, Lc[k], s0);
+                    s1 = fma(l, Lc[LL_LD + k], s1);
+                    s2 = fma(l, Lc[2 * LL_LD + k], s2);
+                    s3 = fma(l, Lc[3 * LL_LD + k], s3);
+                }
+                double* Ai = S + i * LL_LD + c0;
+                // (entries above the diagonal belong to the X^T storage of finished blocks: only c <= i is written)
+                Ai[0] -= s0;
+                if (c0 + 1 <= i) Ai[1] -= s1;
+                if (c0 + 2 <= i) Ai[2] -= s2;
+                if (c0 + 3 <= i) Ai[3] -= s3;
+            }
+            consumer_bar();
+        }
+    }
+    // sum(log diag L) = -sum(log xd): one log per thread, fixed-order reduction
+    if (tid < TILE) scratch[tid] = -log(xd[tid]);
+    consumer_bar();
+    if (tid == 0) {
+        double sl = 0.0;
+        for (int k = 0; k < TILE; k++) sl += scratch[k];
+        *logout = sl;
+    }
+    consumer_bar();
+    if (stamp && tid == 0) *stamp = globaltimer();           // factor done (trace only)
+    // off-diagonal blocks of the inverse, block row by block row
+    for (int bi = 1; bi < TILE / DB; bi++) {
+        const int r0 = bi * DB, ncols = r0;                  // X(bi, 0..bi-1): 32 x ncols
+        // T(rr, c) = sum_{k = c .. r0-1} L(r0+rr, k) X(k, c)
+        for (int idx = tid; idx < DB * ncols; idx += LL_CONSUMERS) {
+            const int rr = idx % DB, c = idx / DB;
+            const double* Lr = S + (r0 + rr) * LL_LD;
+            double s0 = Lr[c] * xd[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+            const double* Xc = S + c * LL_LD;                // Xc[k] = X(k, c), k > c
+            int k = c + 1;
+            for (; k + 3 < r0; k += 4) {
+                s0 = fma(Lr[k], Xc[k], s0);
+                s1 = fma(Lr[k + 1], Xc[k + 1], s1);
+                s2 = fma(Lr[k + 2], Xc[k + 2], s2);
+                s3 = fma(Lr[k + 3], Xc[k + 3], s3);
+            }
+            for (; k < r0; k++) s0 = fma(Lr[k], Xc[k], s0);
+            scratch[c * DB + rr] = (s0 + s1) + (s2 + s3);
+        }
+        consumer_bar();
+        // X(r0+rr, c) = - sum_{q <= rr} X_bibi(rr, q) T(q, c)
+        for (int idx = tid; idx < DB * ncols; idx += LL_CONSUMERS) {
+            const int rr = idx % DB, c = idx / DB;
+            const double* Tc = scratch + c * DB;
+            double s0 = xd[r0 + rr] * Tc[rr], s1 = 0.0;
+            int q = 0;
+            for (; q + 1 < rr; q += 2) {
+                s0 = fma(S[(r0 + q) * LL_LD + r0 + rr], Tc[q], s0);
+                s1 = fma(S[(r0 + q + 1) * LL_LD + r0 + rr], Tc[q + 1], s1);
+            }
+            if (q < rr) s0 = fma(S[(r0 + q) * LL_LD + r0 + rr], Tc[q], s0);
+            S[c * LL_LD + r0 + rr] = -(s0 + s1);
+        }
+        consumer_bar();
+    }
+}
+
+// TRACE: record per-task time stamps (tools/ll_trace.py); a separate instantiation so that the production
+// kernel carries no trace state through the register-tight main loop
+// BLOCKED: diagonal tiles by the blocked routine (4x faster per tile, which is what paces matrices up to
+// n ~ 16k) or by the unblocked one.  The blocked code costs the kernel a few spilled registers that also show up in the
+// DMMA main loop (-2 % at n = 32 768, where the diagonal tiles are off the critical path), hence two instantiations.
+template <bool TRACE, bool BLOCKED>
 __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -272,8 +456,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
 
         int i, j;
         ll_ticket(task, nt, i, j);
-        unsigned long long* dbg = a.dbg ? a.dbg + task * 8 : nullptr;
-        if (dbg && tid == 0) { dbg[0] = globaltimer(); dbg[7] = ((unsigned long long)i << 32) | (unsigned)j; }
+        unsigned long long* dbg = (TRACE && a.dbg) ? a.dbg + task * 8 : nullptr;
+        if (TRACE && dbg && tid == 0) { dbg[0] = globaltimer(); dbg[7] = ((unsigned long long)i << 32) | (unsigned)j; }
         double acc[8][4][2];
 #pragma unroll
         for (int ii = 0; ii < 8; ii++)
@@ -284,7 +468,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
         if (solve) ll_consume<true>(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort, a.w, tid, &vpart);
         else ll_consume<false>(acc, j * (TILE / GK), it, smem, full, empty, wm, wn, g, t, lane, vabort);
 
-        if (dbg && tid == 0) dbg[1] = globaltimer();           // main loop done
+        if (TRACE && dbg && tid == 0) dbg[1] = globaltimer();           // main loop done
         double* tile = a.A + (long)i * TILE + (long)j * TILE * a.lda;
         if (i == j) {
             // ---- diagonal tile: S = A(j,j) - acc in shared memory (ring is idle: the producer waits on c2p)
@@ -301,10 +485,38 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
                 }
             }
             consumer_bar();
+            if (BLOCKED) {
+            double* xd = tmp + 3 * TILE;                     // diagonal of the inverse
+            double* scratch = tmp + 4 * TILE;                // 32 x 96 doubles
+            if (TRACE && dbg && tid == 0) dbg[2] = globaltimer();       // S built
+            diag_tile_factor_invert(S, xd, scratch, tid, a.info, j * TILE, a.logparts + j, (TRACE && dbg) ? dbg + 3 : nullptr);
+            if (TRACE && dbg && tid == 0) dbg[4] = globaltimer();       // factored and inverted
+            for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
+                const int rr = idx & (TILE - 1), c = idx >> 7;
+                tile[rr + (long)c * a.lda] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
+            }
+            if (solve) {
+                // w_j = X (y_j - v_j); the two k-halves of v_j are in vpart
+                tmp[tid] = vpart;
+                consumer_bar();
+                if (tid < TILE) tmp[2 * TILE + tid] = a.y[(long)j * TILE + tid] - (tmp[tid] + tmp[tid + TILE]);
+                consumer_bar();
+                if (tid < TILE) {
+                    double sacc = xd[tid] * tmp[2 * TILE + tid];
+                    for (int c = 0; c < tid; c++) sacc = fma(S[c * LL_LD + tid], tmp[2 * TILE + c], sacc);
+                    a.w[(long)j * TILE + tid] = sacc;
+                }
+            }
+            double* Dj = a.Dinv + (long)j * TILE * TILE;
+            for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
+                const int rr = idx & (TILE - 1), c = idx >> 7;
+                Dj[rr + c * TILE] = (rr > c) ? S[c * LL_LD + rr] : (rr == c ? xd[c] : 0.0);
+            }
+            } else {
             double mylog;
-            if (dbg && tid == 0) dbg[2] = globaltimer();       // S built
+            if (TRACE && dbg && tid == 0) dbg[2] = globaltimer();       // S built
             diag_tile_factor(S, tmp, tid, a.info, j * TILE, mylog);
-            if (dbg && tid == 0) dbg[3] = globaltimer();       // factored
+            if (TRACE && dbg && tid == 0) dbg[3] = globaltimer();       // factored
             for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
                 const int rr = idx & (TILE - 1), c = idx >> 7;
                 tile[rr + (long)c * a.lda] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
@@ -318,7 +530,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             }
             consumer_bar();
             diag_tile_invert(S, tmp, tid);
-            if (dbg && tid == 0) dbg[4] = globaltimer();       // inverted
+            if (TRACE && dbg && tid == 0) dbg[4] = globaltimer();       // inverted
             if (solve) {
                 // w_j = L(j,j)^-1 (y_j - v_j); S holds L(j,j)^-1, the two k-halves of v_j are in vpart
                 tmp[tid] = vpart;
@@ -336,12 +548,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
                 const int rr = idx & (TILE - 1), c = idx >> 7;
                 Dj[rr + c * TILE] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
             }
+            }
             __threadfence();
             consumer_bar();                                  // all stores issued and fenced; S no longer used
             if (tid == 0) {
                 st_release(a.ready + j + (long)j * nt, 1);
                 mbar_arrive(c2p);                            // the producer may refill the ring
-                if (dbg) dbg[5] = globaltimer();
+                if (TRACE && dbg) dbg[5] = globaltimer();
             }
         } else {
             // ---- off-diagonal tile: C' = A(i,j) - acc, in place; then L(i,j) = C' Dinv_j^T through the ring
@@ -359,7 +572,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             fence_proxy_async();
             consumer_bar();
             if (tid == 0) mbar_arrive(c2p);                  // producer: C' is in global memory
-            if (dbg && tid == 0) dbg[2] = globaltimer();
+            if (TRACE && dbg && tid == 0) dbg[2] = globaltimer();
 #pragma unroll
             for (int ii = 0; ii < 8; ii++)
 #pragma unroll
@@ -378,7 +591,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             __threadfence();
             consumer_bar();
             if (tid == 0) st_release(a.ready + i + (long)j * nt, 1);
-            if (dbg && tid == 0) dbg[5] = globaltimer();
+            if (TRACE && dbg && tid == 0) dbg[5] = globaltimer();
         }
     }
 }
@@ -399,10 +612,13 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
 {
     static bool configured = false;
     if (!configured) {
-        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
         configured = true;
     }
-    static_assert((size_t)TILE * LL_LD * sizeof(double) + 3 * LL_CONSUMERS * sizeof(double) <= (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double),
+    static_assert((size_t)TILE * LL_LD * sizeof(double) + (4 * TILE + 32 * 96) * sizeof(double) <= (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double),
                   "diagonal tile scratch must fit in the operand ring");
     const int nt = (int)(n_pad / TILE);
     const size_t nflags = (size_t)nt * nt;
@@ -425,7 +641,10 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     const unsigned grid = (unsigned)(ntasks < sms ? ntasks : sms);
     void* args[] = {&a};
-    SGP_CUDA(cudaLaunchCooperativeKernel((const void*)potrf_ll_kernel, dim3(grid), dim3(WS_THREADS), args, LL_SMEM, c.stream));
+    const bool blocked = nt < 192;                       // n < 24 576: the chain of diagonal tiles paces the factorisation
+    const void* kern = trace ? (blocked ? (const void*)potrf_ll_kernel<true, true> : (const void*)potrf_ll_kernel<true, false>)
+                             : (blocked ? (const void*)potrf_ll_kernel<false, true> : (const void*)potrf_ll_kernel<false, false>);
+    SGP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(WS_THREADS), args, LL_SMEM, c.stream));
     count_launch();
     if (trace) {
         std::vector<unsigned long long> h((size_t)ntasks_all * 8);
@@ -439,7 +658,7 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
             for (long t = 0; t < ntasks_all; t++) {
                 fprintf(f, "%ld %d %d", t, (int)(h[t * 8 + 7] >> 32), (int)(h[t * 8 + 7] & 0xffffffffu));
                 for (int k = 0; k < 6; k++) fprintf(f, " %lld", h[t * 8 + k] ? (long long)(h[t * 8 + k] - t0) : -1ll);
-                fprintf(f, "\n");
+                fprintf(f, " %lld\n", (long long)h[t * 8 + 6]);       // accumulated ns in the 32 x 32 block factorisations
             }
             fclose(f);
         }

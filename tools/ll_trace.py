@@ -15,7 +15,7 @@ diag = diag[np.argsort(diag[:, 1])]
 print("diag tasks: j, start, mainloop_end-start, Sbuilt-ml, factor, invert, rest, end   (us)")
 for r in diag[:: max(1, len(diag) // 16)]:
     j = int(r[1]); s = r[3:9] / 1e3
-    print(f"{j:4d} start {s[0]:9.1f}  ml {s[1]-s[0]:8.1f}  S {s[2]-s[1]:6.1f}  fac {s[3]-s[2]:6.1f}  inv {s[4]-s[3]:6.1f}  out {s[5]-s[4]:6.1f}  end {s[5]:9.1f}")
+    print(f"{j:4d} start {s[0]:9.1f}  ml {s[1]-s[0]:8.1f}  S {s[2]-s[1]:6.1f}  fac {s[3]-s[2]:6.1f}  inv {s[4]-s[3]:6.1f}  out {s[5]-s[4]:6.1f}  end {s[5]:9.1f}  warp32 {r[9]/1e3:6.1f}")
 ends = diag[:, 8] / 1e3
 print("diag-to-diag interval (us): mean %.1f  min %.1f  max %.1f" % (np.diff(ends).mean(), np.diff(ends).min(), np.diff(ends).max()))
 off = t[t[:, 1] == t[:, 2] + 1]

@@ -18,6 +18,7 @@ baseline (oracle = port of the reference maths, SciPy LAPACK on the host cores).
 import argparse
 import ctypes
 import json
+import math
 import os
 import subprocess
 import sys
@@ -320,12 +321,15 @@ def main():
             _lib.check(L.sgp_model_applymap_dev(ctx.handle, model, 2, solver, steps, E, q0.data_ptr(), p0.data_ptr(),
                                                 qf.data_ptr(), pf.data_ptr(), None, None, 0, stats.data_ptr()),
                        "sgp_model_applymap_dev")
-        map_run(1, 8)                                   # warm-up
+        # solver 3 = Newton started at p + guess: the guess GP of this workload is trained on P - p as
+        # python/04_standard_map/main.py:89-90 does (the reference starts hybrd1 at the bare difference)
+        MAP_SOLVER, MAP_SOLVER_NAME = 3, "newton_delta"
+        map_run(MAP_SOLVER, 8)                          # warm-up
         sync_all()
         stats.zero_()
         m0, m1 = ev(), ev()
         t_mwall0 = time.time()
-        m0.record(stream); map_run(1, a.map_steps); m1.record(stream)
+        m0.record(stream); map_run(MAP_SOLVER, a.map_steps); m1.record(stream)
         sync_all()
         t_mwall1 = time.time()
         t_map_local = m0.elapsed_time(m1) * 1e-3
@@ -344,27 +348,46 @@ def main():
         h0.record(stream); map_run(0, hsteps); h1.record(stream)
         sync_all()
         t_map_h = max_over_ranks(h0.elapsed_time(h1) * 1e-3)
+        qh, ph = qf.clone(), pf.clone()
+        # Newton from the reference's start (solver 1) on the same short run, and the headline solver again: how many
+        # orbits end within 1e-8 of the hybrd1 trajectories after hsteps steps (full-size parity property)
+        n0, n1 = ev(), ev()
+        n0.record(stream); map_run(1, hsteps); n1.record(stream)
+        sync_all()
+        t_map_n = max_over_ranks(n0.elapsed_time(n1) * 1e-3)
+        map_run(MAP_SOLVER, hsteps)
+        sync_all()
+        def wrapd(x, y):
+            d = (x - y).abs()
+            return torch.minimum(d, (d - 2 * math.pi).abs())
+        both = torch.isfinite(qh) & torch.isfinite(qf)
+        same = both & (wrapd(qf, qh) < 1e-8) & (wrapd(pf, ph) < 1e-8)
+        agree = torch.stack([same.sum(), both.sum()]).to(torch.int64)
+        if world > 1:
+            dist.all_reduce(agree, op=dist.ReduceOp.SUM)
         # end to end through the public API: host arrays in, final states out (model staging, H2D of the
         # initial conditions and D2H of the result inside the timed region)
         q0_h, p0_h = q0_all[rank::world].copy(), p0_all[rank::world].copy()
         sync_all()
         t0 = time.perf_counter()
         out = api.applymap_standard(a.map_steps + 1, E, hm[:3], hpm[:3], q0_h, p0_h, xtp, None, None, xt, None, None,
-                                    solver="newton", alphap=fpm["alpha"], alpha=fm["alpha"], out_every=0, want_pdiff=False)
+                                    solver=MAP_SOLVER_NAME, alphap=fpm["alpha"], alpha=fm["alpha"], out_every=0, want_pdiff=False)
         t_map_e2e = max_over_ranks(time.perf_counter() - t0)
         pair_evals = (Nt + evals / orbit_steps * Nt)      # per orbit-step: guess sweep + solver/dq sweeps
         dp_instr = 34.0                                   # DP instructions per pair evaluation (SASS of the F/dF sweep)
         fp64_peak = 148 * 64 * 1.965e9                    # thread-level DP instructions/s: SMs x FP64 lanes x max SM clock
         map_info = {"metric": "orbit_map_steps_per_s", "value": orbit_steps / t_map, "unit": "orbit-steps/s",
-                    "solver": "newton", "n_train": Nt, "orbits_total": E * world, "steps": a.map_steps,
+                    "solver": MAP_SOLVER_NAME, "n_train": Nt, "orbits_total": E * world, "steps": a.map_steps,
                     "sweeps_per_orbit_step": 1 + evals / orbit_steps,
                     "pair_evals_per_s": orbit_steps * pair_evals / t_map,
-                    "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe",
+                    "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe", "note": "useful (per-orbit) pair evaluations x 34 DP instr; lanes of a warp that wait for a slower neighbour's Newton iteration are not counted",
                                  "achieved": orbit_steps * pair_evals * dp_instr / t_map / world, "peak": fp64_peak,
                                  "unit": "DP instr/s per GPU", "frac": orbit_steps * pair_evals * dp_instr / t_map / world / fp64_peak},
                     "e2e": {"value": orbit_steps / t_map_e2e, "unit": "orbit-steps/s",
                             "h2d_bytes_per_step": int(16 * E + 8 * (3 * Nt + 4 * Nt)), "d2h_bytes_per_step": int(16 * E)},
                     "hybrd_value": float(E) * world * hsteps / t_map_h, "hybrd_steps": hsteps,
+                    "newton_refstart_value": float(E) * world * hsteps / t_map_n,
+                    "same_as_hybrd_after_hsteps": {"within_1e-8": int(agree[0].item()), "compared": int(agree[1].item())},
                     "unconverged": int(st[1].item()),
                     "clocks": sampler.summary(t_mwall0, t_mwall1), "rank0_s": t_map_local,
                     "checksum": [float(cks[0].item()), float(cks[1].item())]}

@@ -48,6 +48,9 @@ extern "C" {
 /* root solver of the implicit equation (argument `solver`) */
 #define SGP_SOLVER_HYBRD  0 /* MINPACK hybrd1, n = 1, tol 1e-13 (sympgpr.f90:107)     */
 #define SGP_SOLVER_NEWTON 1 /* Newton with the analytic derivative, same tolerance   */
+#define SGP_SOLVER_NEWTON_DELTA 3 /* Newton started at p + guess: for guess GPs trained on P - p (ztrainp = P - p,
+                               * python/04_standard_map/main.py:89-90, 03, 05), where the reference starts hybrd1 at the
+                               * bare difference.  Same root wherever the residual has one root; about half the sweeps */
 #define SGP_SOLVER_EXPLICIT 2 /* no root solve: P = p - F_q(q, p); the explicit maps calcP_expl
                                * python/04_standard_map/func.py:174-179, python/01_pendulum/explicit/func_expl.py:107-127
                                * (the guess-GP arguments are ignored and may be empty) */
@@ -159,6 +162,27 @@ int sgp_applymap(sgp_ctx* ctx, int kind, int fam, double per, int solver, long n
                  double* qmap, double* pmap, double* pdiff, long out_every,
                  double* qfinal, double* pfinal, unsigned long long* stats);
 
+/* energy function of the fused quality metric (argument `ekind`) */
+#define SGP_ENERGY_PENDULUM 1 /* H = p^2/2 + U0 (1 - cos(q + pi)); epar4 = {U0}: energy() python/01_pendulum/implicit/func.py:116-117 */
+#define SGP_ENERGY_TOKAMAK  2 /* H = -Aph(r, q, 0), r = compute_r([p 1e-2, q, 0], 0.3); epar4 = {eps, m, phase}:
+                               * energy() python/05_tokamak/Split_SympGPR/func.py:234-246, Aph fieldlines.f90:58-64 */
+/* Ensemble map application with the quality metrics of `quality` (python/functions/func.py:262-272,
+ * python/05_tokamak/Split_SympGPR/func.py:221-232) accumulated inside the map kernel, so that no history is
+ * written: eosc[k] = std(H[:, k]) / mean(H[:, k]) and hmean[k] = mean(H[:, k]) over the rows 0, e_every,
+ * 2 e_every, ... of the (nm, E) history the reference would hold (numpy.std: population standard deviation);
+ * q1/p1 = row e_every (the first mapped state that `quality` compares with the reference orbit, `gd`).
+ * Other arguments as sgp_applymap.  Any output pointer may be NULL. */
+int sgp_applymap_quality(sgp_ctx* ctx, int kind, int fam, double per, int solver, long nm, long E,
+                         const double* q0, const double* p0, const double* hyp3, const double* hypp3,
+                         const double* xtrainp, const double* ytrainp, const double* alphap, long np,
+                         const double* xtrain, const double* ytrain, const double* alpha, long nt,
+                         int ekind, const double* epar4, long e_every, double* q1, double* p1,
+                         double* qfinal, double* pfinal, double* eosc, double* hmean,
+                         unsigned long long* stats);
+/* StandardMapIterate(k, nm, N, X0) python/04_standard_map/main.py:27-39: X0 (2, N) -> f (2, N, nm), C order,
+ * J' = J + k sin(th), th' = th + J' (no wrap); the generator of the standard-map training and reference orbits. */
+int sgp_standard_map_iterate(sgp_ctx* ctx, double k, long nm, long N, const double* X0, double* f);
+
 /* Split map: nmodels learned maps (one per toroidal section) applied in turn, step s with map (s-1) mod nmodels;
  * loss test at the new angle, lost orbits NaN in q and p -- applymap_tok
  * python/05_tokamak/Split_SympGPR/func.py:184-219.  All sub-maps have np / nt training pairs; every model
@@ -180,6 +204,14 @@ int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solve
                            const double* d_q0, const double* d_p0, double* d_qfinal, double* d_pfinal,
                            double* d_qhist, double* d_phist, long out_every,
                            unsigned long long* d_stats);             /* async on ctx stream   */
+
+/* sgp_model_applymap_dev with the fused quality metrics of sgp_applymap_quality; d_work3: 3 E doubles of scratch
+ * (carried between work items); d_q1/d_p1 may be NULL. */
+int sgp_model_applymap_quality_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solver, long nsteps, long E,
+                                   const double* d_q0, const double* d_p0, double* d_qfinal, double* d_pfinal,
+                                   int ekind, const double* epar4, long e_every, double* d_work3,
+                                   double* d_q1, double* d_p1, double* d_eosc, double* d_hmean,
+                                   unsigned long long* d_stats);     /* async on ctx stream   */
 
 /* ---- fieldlines module (tokamak loss test) ------------------------------------------------ */
 /* fieldlines.f90:94-107 compute_r(z(3), rstart): z = (pth, th, ph); host arithmetic. */

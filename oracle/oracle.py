@@ -520,6 +520,45 @@ def applymap(kind, nm, q0, p0, hyp, hypp, xtrainp, ytrainp, ztrainp, kyinvp,
     return qmap, pmap
 
 
+# ------------------------------------------------------ quality metrics
+def energy_pendulum(q, p, U0):
+    """energy(x, U0) python/01_pendulum/implicit/func.py:116-117."""
+    return np.asarray(p)**2 / 2 + U0 * (1 - np.cos(np.asarray(q) + np.pi))
+
+
+def aph(r, th, ph, eps, m, n, phase):
+    """fieldlines.f90:58-64 (B0 = iota0 = 1, a = 0.5)."""
+    return -(r**2 / 2.0 - r**4 / (4.0 * 0.5**2)) * (1.0 + eps * np.cos(m * th + n * ph + phase))
+
+
+def energy_tok(qmap, pmap, eps, m, phase):
+    """energy(qmap, pmap, nm) python/05_tokamak/Split_SympGPR/func.py:234-246 (ph = 0): H (N, nm)."""
+    nm, N = qmap.shape
+    H = np.zeros((N, nm))
+    for i in range(N):
+        for k in range(nm):
+            r = compute_r(np.array([pmap[k, i] * 1e-2, qmap[k, i], 0.0]), 0.3)
+            H[i, k] = -aph(r, qmap[k, i], 0.0, eps, m, 0, phase)
+    return H
+
+
+def quality_eosc(H):
+    """Energy oscillation of `quality` python/functions/func.py:268-271: H (nm, Ntest) -> std/mean per orbit."""
+    H = np.asarray(H)
+    return np.array([np.std(H[:, k]) / np.mean(H[:, k]) for k in range(H.shape[1])])
+
+
+def standard_map_iterate(k, nm, N, X0):
+    """StandardMap / StandardMapIterate python/04_standard_map/main.py:27-39."""
+    f = np.zeros((2, N, nm))
+    f[:, :, 0] = X0
+    for i in range(N):
+        for l in range(nm - 1):
+            J = f[1, i, l] + k * np.sin(f[0, i, l])
+            f[:, i, l + 1] = [f[0, i, l] + J, J]
+    return f
+
+
 # -------------------------------------------------- synthetic workload (SURVEY 8d)
 def halton(n, base, start=1):
     """Unscrambled van der Corput sequence, indices start..start+n-1."""

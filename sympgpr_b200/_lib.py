@@ -26,7 +26,8 @@ E_BADARG, E_CUDA, E_NOMEM, E_NODEV = -1, -2, -3, -4
 
 FAMILIES = {"product": 0, "sq": 1, "sum": 2, "period": 0}
 MAP_KINDS = {"pendulum": 0, "henon": 1, "standard": 2, "tokamak": 3, "standard_expl": 4}
-SOLVERS = {"hybrd": 0, "newton": 1, "explicit": 2}
+SOLVERS = {"hybrd": 0, "newton": 1, "explicit": 2, "newton_delta": 3}
+ENERGIES = {"pendulum": 1, "tokamak": 2}
 
 _lib = None
 _lock = threading.Lock()
@@ -65,6 +66,11 @@ _PROTOS = {
                                ctypes.POINTER(c_vp)]),
     "sgp_model_destroy": (c_i, [c_vp]),
     "sgp_model_applymap_dev": (c_i, [c_vp, c_vp, c_i, c_i, c_l, c_l, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_l, c_vp]),
+    "sgp_applymap_quality": (c_i, [c_vp, c_i, c_i, c_d, c_i, c_l, c_l, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp,
+                                   c_dp, c_dp, c_l, c_i, c_dp, c_l, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ullp]),
+    "sgp_standard_map_iterate": (c_i, [c_vp, c_d, c_l, c_l, c_dp, c_dp]),
+    "sgp_model_applymap_quality_dev": (c_i, [c_vp, c_vp, c_i, c_i, c_l, c_l, c_vp, c_vp, c_vp, c_vp, c_i, c_dp, c_l, c_vp,
+                                             c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sgp_compute_r": (c_d, [c_d, c_d, c_d, c_d]),
     "sgp_ath": (c_d, [c_d, c_d, c_d]),
     "sgp_spd_factor": (c_i, [c_vp, c_dp, c_l, c_dp, c_dp, c_dp]),

@@ -19,7 +19,7 @@ import ctypes
 import numpy as np
 
 from . import _lib
-from ._lib import (FAMILIES, MAP_KINDS, RES_A, RES_B, RES_DLX, RES_INFO, RES_LEN, RES_LOGD, RES_NLL, RES_QUAD, SOLVERS,
+from ._lib import (ENERGIES, FAMILIES, MAP_KINDS, RES_A, RES_B, RES_DLX, RES_INFO, RES_LEN, RES_LOGD, RES_NLL, RES_QUAD, SOLVERS,
                    as_f64, as_f64_fortran, check, dptr)
 
 _NULL = ctypes.POINTER(ctypes.c_double)()
@@ -428,6 +428,72 @@ def applymap_tok_split(nphmap, nm, Ntest, Q0map, P0map, xtrainp, ztrainp, Kyinvp
     if return_stats:
         return qmap, pmap, dict(evaluations=int(stats[0]), unconverged=int(stats[1]))
     return qmap, pmap
+
+
+def applymap_quality(kind, nm, Ntest, l, hypp, Q0map, P0map, xtrainp, ztrainp, Kyinvp, xtrain, ztrain, Kyinv,
+                     energy="pendulum", energy_par=(1.0,), e_every=1, family="product", per=0.5, solver="hybrd",
+                     alphap=None, alpha=None):
+    """Map an ensemble nm - 1 steps and return the ingredients of the reference's `quality`
+    (python/functions/func.py:262-272; python/05_tokamak/Split_SympGPR/func.py:221-232) without any history:
+    dict(q1, p1, qfinal, pfinal, Eosc, Hmean, evaluations, unconverged) with Eosc = std(H)/mean(H) per orbit over
+    the rows 0, e_every, ... of the history the reference would hold, accumulated inside the map kernel.
+    energy="pendulum": H = p^2/2 + U0 (1 - cos(q + pi)), energy_par = (U0,)  (01_pendulum/implicit/func.py:116-117);
+    energy="tokamak":  H = -Aph(compute_r([p 1e-2, q, 0], 0.3), q, 0), energy_par = (eps, m, phase)
+    (Split_SympGPR/func.py:234-246)."""
+    hyp, hypp = _hyp3(l), _hyp3(hypp, "hypp")
+    E = int(Ntest)
+    q0, p0 = as_f64(Q0map).ravel()[:E], as_f64(P0map).ravel()[:E]
+    if q0.size < E or p0.size < E:
+        raise ValueError("applymap_quality: fewer initial conditions than Ntest")
+    xtrainp, xtrain = as_f64(xtrainp).ravel(), as_f64(xtrain).ravel()
+    np_, nt = xtrainp.size // 2, xtrain.size // 2
+    if alphap is None:
+        alphap = as_f64(Kyinvp).dot(as_f64(ztrainp).ravel())
+    if alpha is None:
+        alpha = as_f64(Kyinv).dot(as_f64(ztrain).ravel())
+    alphap, alpha = as_f64(alphap).ravel(), as_f64(alpha).ravel()
+    if alphap.size != np_ or alpha.size != 2 * nt:
+        raise ValueError("applymap_quality: alpha vectors do not match the training sets")
+    epar = np.zeros(4)
+    ep = as_f64(energy_par).ravel()
+    epar[:ep.size] = ep
+    ek = ENERGIES[energy] if isinstance(energy, str) else int(energy)
+    q1, p1, qf, pf, eosc, hmean = (np.zeros(E) for _ in range(6))
+    stats = (ctypes.c_ulonglong * 2)()
+    st = _lib.lib().sgp_applymap_quality(
+        _lib.context().handle, _kind(kind), _fam(family), per, _solver(solver), int(nm), E, dptr(q0), dptr(p0), dptr(hyp),
+        dptr(hypp), dptr(xtrainp[:np_]), dptr(np.ascontiguousarray(xtrainp[np_:2 * np_])), dptr(alphap), np_,
+        dptr(xtrain[:nt]), dptr(np.ascontiguousarray(xtrain[nt:2 * nt])), dptr(alpha), nt, ek, dptr(epar), int(e_every),
+        dptr(q1), dptr(p1), dptr(qf), dptr(pf), dptr(eosc), dptr(hmean), stats)
+    check(st, "applymap_quality")
+    return dict(q1=q1, p1=p1, qfinal=qf, pfinal=pf, Eosc=eosc, Hmean=hmean, evaluations=int(stats[0]),
+                unconverged=int(stats[1]))
+
+
+def quality(q1, p1, Eosc, ysint, Nm, order="qp"):
+    """(Eosc, gd, stdgd) as `quality` returns them (python/functions/func.py:262-272): gd[k] = mean squared distance of
+    the first mapped state from the reference orbit ysint[Nm, :, k]; order="pq" for the tokamak variant, which compares
+    (p, q) with ysint[Nm, 0:2, k] after wrapping the angle (Split_SympGPR/func.py:221-232)."""
+    ys = np.asarray(ysint, float)
+    if order == "pq":
+        ref = np.array([ys[Nm, 0], np.mod(ys[Nm, 1], 2 * np.pi)])
+        mine = np.array([p1, q1])
+    else:
+        ref = np.array([ys[Nm, 0], ys[Nm, 1]])
+        mine = np.array([q1, p1])
+    gd = np.mean((mine - ref)**2, axis=0)
+    return np.asarray(Eosc), gd, float(np.std(gd))
+
+
+def StandardMapIterate(k, nm, N, X0):
+    """StandardMapIterate(k, nm, N, X0) -> f (2, N, nm) -- python/04_standard_map/main.py:32-39, on the device."""
+    X0 = as_f64(X0)
+    if X0.shape != (2, int(N)):
+        raise ValueError("StandardMapIterate: X0 must have shape (2, N)")
+    f = np.zeros((2, int(N), int(nm)))
+    check(_lib.lib().sgp_standard_map_iterate(_lib.context().handle, float(k), int(nm), int(N), dptr(X0), dptr(f)),
+          "StandardMapIterate")
+    return f
 
 
 def applymap_expl(nm, Ntest, l, Q0map, P0map, xtrain, ztrain, Kyinv, family="sum", per=0.5, **kw):

@@ -431,6 +431,8 @@ static void model_args(const sgp_model* m, MapArgs& a)
 {
     a.models = m->tab.as<MapModelDev>(); a.nmodels = m->nmodels;
     a.pdstate = nullptr; a.ticket = nullptr; a.slots = nullptr; a.progress = nullptr; a.slice_steps = 1;
+    a.ekind = ENERGY_NONE; a.e_every = 1; a.epar[0] = a.epar[1] = a.epar[2] = a.epar[3] = 0.0;
+    a.ek = a.emean = a.em2 = a.q1 = a.p1 = a.eosc = a.ehmean = nullptr;
 }
 
 int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solver, long nsteps, long E, const double* d_q0,
@@ -438,7 +440,7 @@ int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solve
                            long out_every, unsigned long long* d_stats)
 {
     SGP_TRY(check_ctx(ctx));
-    if (!m || E < 0 || nsteps < 0 || kind < 0 || kind > 5 || solver < 0 || solver > 2 || !d_qfinal || !d_pfinal || !d_stats) {
+    if (!m || E < 0 || nsteps < 0 || kind < 0 || kind > 5 || solver < 0 || solver > 3 || !d_qfinal || !d_pfinal || !d_stats) {
         set_error("model_applymap_dev: bad arguments"); return ST_BADARG;
     }
     MapArgs a;
@@ -452,12 +454,18 @@ int sgp_model_applymap_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solve
     return map_launch(ctx->c, m->fam, solver, a, ctx->c.flags.p);
 }
 
+// fused quality metrics requested through the host-buffer entry points (all outputs E doubles, any may be NULL)
+struct QualHost {
+    int ekind; long e_every; const double* epar;
+    double *q1, *p1, *eosc, *hmean;
+};
+
 // shared implementation of the host-buffer map entry points
 static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver, int nmodels, long nm, long E, const double* q0,
                          const double* p0, const double* hyp3, const double* hypp3, const double* d_xtp, const double* d_ytp,
                          const double* d_alphap, long np, const double* d_xt, const double* d_yt, const double* d_alpha, long nt,
                          double* qmap, double* pmap, double* pdiff, long out_every,
-                         double* qfinal, double* pfinal, unsigned long long* stats)
+                         double* qfinal, double* pfinal, unsigned long long* stats, const QualHost* qual = nullptr)
 {
     Ctx& c = ctx->c;
     if (nm < 1) { set_error("applymap: nm must be >= 1"); return ST_BADARG; }
@@ -467,7 +475,7 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
     const bool hist = (qmap && pmap && out_every > 0);
     const long rows = hist ? 1 + (nm - 1) / out_every : 0;
     const size_t hsz = (size_t)rows * (size_t)E;
-    const size_t need = (size_t)(5 * E) + hsz * (pdiff ? 3 : 2) + 4;
+    const size_t need = (size_t)(5 * E) + hsz * (pdiff ? 3 : 2) + 4 + (qual ? (size_t)(7 * E) : 0);
     if (!st) st = c.mapbuf.reserve(need * sizeof(double));
     if (!st) st = c.flags.reserve(map_sched_bytes(E > 0 ? E : 1));
     if (st) { m.buf.release(); m.tab.release(); return st; }
@@ -483,6 +491,12 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
     a.step_stride = E; a.orbit_stride = 1; a.out_every = hist ? out_every : 0;
     a.qfinal = dqf; a.pfinal = dpf; a.stats = dstats;
     a.pdstate = a.pdiff ? dpds : nullptr;
+    if (qual) {
+        double* dq = dpd + (pdiff ? hsz : 0);
+        a.ekind = qual->ekind; a.e_every = qual->e_every;
+        for (int i = 0; i < 4; i++) a.epar[i] = qual->epar ? qual->epar[i] : 0.0;
+        a.ek = dq; a.emean = dq + E; a.em2 = dq + 2 * E; a.q1 = dq + 3 * E; a.p1 = dq + 4 * E; a.eosc = dq + 5 * E; a.ehmean = dq + 6 * E;
+    }
     auto run = [&]() -> int {
         SGP_CUDA(cudaMemsetAsync(dstats, 0, 2 * sizeof(unsigned long long), c.stream));
         SGP_TRY(upload(c, dq0, q0, E));
@@ -496,6 +510,12 @@ static int applymap_host(sgp_ctx* ctx, int kind, int fam, double per, int solver
         }
         if (qfinal) SGP_TRY(download(c, qfinal, dqf, E));
         if (pfinal) SGP_TRY(download(c, pfinal, dpf, E));
+        if (qual) {
+            if (qual->q1) SGP_TRY(download(c, qual->q1, a.q1, E));
+            if (qual->p1) SGP_TRY(download(c, qual->p1, a.p1, E));
+            if (qual->eosc) SGP_TRY(download(c, qual->eosc, a.eosc, E));
+            if (qual->hmean) SGP_TRY(download(c, qual->hmean, a.ehmean, E));
+        }
         if (stats) SGP_CUDA(cudaMemcpyAsync(stats, dstats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
         SGP_TRY(sync(c));
         if (E > 0) {
@@ -518,7 +538,7 @@ int sgp_applymap(sgp_ctx* ctx, int kind, int fam, double per, int solver, long n
 {
     SGP_TRY(check_ctx(ctx));
     Ctx& c = ctx->c;
-    if (E < 0 || np < 0 || nt < 0 || kind < 0 || kind > 4 || solver < 0 || solver > 2 || fam < 0 || fam > 2) { set_error("applymap: bad arguments"); return ST_BADARG; }
+    if (E < 0 || np < 0 || nt < 0 || kind < 0 || kind > 4 || solver < 0 || solver > 3 || fam < 0 || fam > 2) { set_error("applymap: bad arguments"); return ST_BADARG; }
     const size_t tot = (size_t)(3 * np + 4 * nt);
     SGP_TRY(c.io.reserve((tot + 8) * sizeof(double)));
     double* d = c.io.as<double>();
@@ -529,6 +549,68 @@ int sgp_applymap(sgp_ctx* ctx, int kind, int fam, double per, int solver, long n
                          pdiff, out_every, qfinal, pfinal, stats);
 }
 
+int sgp_applymap_quality(sgp_ctx* ctx, int kind, int fam, double per, int solver, long nm, long E, const double* q0, const double* p0,
+                         const double* hyp3, const double* hypp3, const double* xtrainp, const double* ytrainp, const double* alphap,
+                         long np, const double* xtrain, const double* ytrain, const double* alpha, long nt, int ekind,
+                         const double* epar4, long e_every, double* q1, double* p1, double* qfinal, double* pfinal, double* eosc,
+                         double* hmean, unsigned long long* stats)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (E < 0 || np < 0 || nt < 0 || kind < 0 || kind > 4 || solver < 0 || solver > 3 || fam < 0 || fam > 2 || ekind < 1 || ekind > 2 ||
+        e_every < 1 || !epar4) {
+        set_error("applymap_quality: bad arguments"); return ST_BADARG;
+    }
+    const size_t tot = (size_t)(3 * np + 4 * nt);
+    SGP_TRY(c.io.reserve((tot + 8) * sizeof(double)));
+    double* d = c.io.as<double>();
+    double *dxp = d, *dyp = dxp + np, *dap = dyp + np, *dx = dap + np, *dy = dx + nt, *da = dy + nt;
+    SGP_TRY(upload(c, dxp, xtrainp, np)); SGP_TRY(upload(c, dyp, ytrainp, np)); SGP_TRY(upload(c, dap, alphap, np));
+    SGP_TRY(upload(c, dx, xtrain, nt)); SGP_TRY(upload(c, dy, ytrain, nt)); SGP_TRY(upload(c, da, alpha, 2 * nt));
+    QualHost qh{ekind, e_every, epar4, q1, p1, eosc, hmean};
+    return applymap_host(ctx, kind, fam, per, solver, 1, nm, E, q0, p0, hyp3, hypp3, dxp, dyp, dap, np, dx, dy, da, nt, nullptr, nullptr,
+                         nullptr, 0, qfinal, pfinal, stats, &qh);
+}
+
+int sgp_model_applymap_quality_dev(sgp_ctx* ctx, const sgp_model* m, int kind, int solver, long nsteps, long E, const double* d_q0,
+                                   const double* d_p0, double* d_qfinal, double* d_pfinal, int ekind, const double* epar4,
+                                   long e_every, double* d_work3, double* d_q1, double* d_p1, double* d_eosc, double* d_hmean,
+                                   unsigned long long* d_stats)
+{
+    SGP_TRY(check_ctx(ctx));
+    if (!m || E < 0 || nsteps < 0 || kind < 0 || kind > 5 || solver < 0 || solver > 3 || !d_qfinal || !d_pfinal || !d_stats ||
+        ekind < 1 || ekind > 2 || e_every < 1 || !epar4 || !d_work3 || !d_eosc || !d_hmean) {
+        set_error("model_applymap_quality_dev: bad arguments"); return ST_BADARG;
+    }
+    MapArgs a;
+    model_args(m, a);
+    a.kind = kind; a.E = E; a.nsteps = nsteps; a.q0 = d_q0; a.p0 = d_p0;
+    a.qout = nullptr; a.pout = nullptr; a.pdiff = nullptr;
+    a.step_stride = E; a.orbit_stride = 1; a.out_every = 0;
+    a.qfinal = d_qfinal; a.pfinal = d_pfinal; a.stats = d_stats;
+    a.ekind = ekind; a.e_every = e_every;
+    for (int i = 0; i < 4; i++) a.epar[i] = epar4[i];
+    a.ek = d_work3; a.emean = d_work3 + E; a.em2 = d_work3 + 2 * E;
+    a.q1 = d_q1; a.p1 = d_q1 ? d_p1 : nullptr; a.eosc = d_eosc; a.ehmean = d_hmean;
+    if (E == 0) return ST_OK;
+    SGP_TRY(ctx->c.flags.reserve(map_sched_bytes(E)));
+    return map_launch(ctx->c, m->fam, solver, a, ctx->c.flags.p);
+}
+
+int sgp_standard_map_iterate(sgp_ctx* ctx, double k, long nm, long N, const double* X0, double* f)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (nm < 1 || N < 0 || !X0 || !f) { set_error("standard_map_iterate: bad arguments"); return ST_BADARG; }
+    if (N == 0) return ST_OK;
+    SGP_TRY(c.mapbuf.reserve((size_t)(2 * N) * (size_t)(nm + 1) * sizeof(double)));
+    double* d = c.mapbuf.as<double>();
+    SGP_TRY(upload(c, d, X0, 2 * N));
+    SGP_TRY(standard_map_iterate(c, k, nm, N, d, d + 2 * N));
+    SGP_TRY(download(c, f, d + 2 * N, (size_t)(2 * N) * (size_t)nm));
+    return sync(c);
+}
+
 int sgp_applymap_split(sgp_ctx* ctx, int fam, double per, int solver, int nmodels, long nsteps, long E, const double* q0,
                        const double* p0, const double* hyp3, const double* hypp3, const double* xtrainp, const double* ytrainp,
                        const double* alphap, long np, const double* xtrain, const double* ytrain, const double* alpha, long nt,
@@ -536,7 +618,7 @@ int sgp_applymap_split(sgp_ctx* ctx, int fam, double per, int solver, int nmodel
 {
     SGP_TRY(check_ctx(ctx));
     Ctx& c = ctx->c;
-    if (E < 0 || np < 0 || nt < 0 || nmodels < 1 || nsteps < 0 || solver < 0 || solver > 1 || fam < 0 || fam > 2 || !qmap || !pmap) {
+    if (E < 0 || np < 0 || nt < 0 || nmodels < 1 || nsteps < 0 || solver < 0 || solver == 2 || solver > 3 || fam < 0 || fam > 2 || !qmap || !pmap) {
         set_error("applymap_split: bad arguments"); return ST_BADARG;
     }
     const size_t M = (size_t)nmodels;

@@ -64,6 +64,20 @@ __host__ __device__ inline double compute_r_dev(double pth, double th, double rs
     return r;
 }
 
+// fieldlines.f90:58-64 at ph = 0 (B0 = iota0 = 1, a = 0.5): Aph = -(r^2/2 - r^4/(4 a^2)) (1 + eps cos(m th + phase))
+__host__ __device__ inline double aph_dev(double r, double th, double eps, double m, double phase)
+{
+    const double r2 = r * r;
+    return -(r2 / 2.0 - r2 * r2 / (4.0 * 0.25)) * (1.0 + eps * cos(m * th + phase));
+}
+
+__device__ __forceinline__ double orbit_energy(int ekind, double e0, double e1, double e2, double q, double p)
+{
+    if (ekind == ENERGY_PENDULUM) return p * p / 2.0 + e0 * (1.0 - cos(q + 3.141592653589793));
+    const double r = compute_r_dev(p * 1e-2, q, 0.3);
+    return -aph_dev(r, q, e0, e1, e2);
+}
+
 enum SweepMode : int { SW_GUESS = 0, SW_F_DF = 1, SW_F = 2, SW_DQ = 3 };
 
 // 2^(j/64), j = 0..63, correctly rounded (filled by the host on first launch; copied to shared memory per block)
@@ -317,6 +331,12 @@ map_kernel(MapArgs a)
             if (slice == 0) { q = a.q0[k]; p = a.p0[k]; pd = p; }
             else { q = a.qfinal[k]; p = a.pfinal[k]; pd = a.pdstate ? a.pdstate[k] : 0.0; }
         }
+        if (slice == 0 && mine && a.ekind != ENERGY_NONE) {
+            a.ek[k] = orbit_energy(a.ekind, a.epar[0], a.epar[1], a.epar[2], q, p);
+            a.emean[k] = 0.0;
+            a.em2[k] = 0.0;
+            if (a.nsteps < a.e_every) { a.eosc[k] = 0.0 / a.ek[k]; a.ehmean[k] = a.ek[k]; }     // a single sample
+        }
         if (slice == 0 && mine && a.out_every > 0) {
             a.qout[k * a.orbit_stride] = q;
             a.pout[k * a.orbit_stride] = p;
@@ -381,7 +401,9 @@ map_kernel(MapArgs a)
                 if (alive && sv.info != 1) fails++;
             } else {
                 Newton1 sv;
-                sv.start(alive ? pg : 0.0);
+                // the reference starts at the guess GP's prediction as it is (sympgpr.f90:104-107) even where that GP was
+                // trained on P - p (scripts 03/04/05); start_delta adds p, which is the consistent start for such a model
+                sv.start(alive ? (a.start_delta ? p + pg : pg) : 0.0);
                 if (!alive) sv.phase = 3;
                 while (__any_sync(0xffffffffu, !sv.done())) {
                     const bool run = !sv.done();
@@ -425,6 +447,24 @@ map_kernel(MapArgs a)
             q = qn;
             p = Pst;
 
+            if (mine && a.ekind != ENERGY_NONE && (step % a.e_every) == 0) {
+                // Welford update with the sample H - H(0); the accumulators live in global memory (L2) between steps:
+                // 40 bytes per orbit-step against ~1e5 pair evaluations, and no registers held across the sweeps
+                const double x = orbit_energy(a.ekind, a.epar[0], a.epar[1], a.epar[2], q, p) - a.ek[k];
+                const double n = (double)(step / a.e_every + 1);
+                double mean = a.emean[k];
+                const double dl = x - mean;
+                mean += dl / n;
+                const double m2 = a.em2[k] + dl * (x - mean);
+                a.emean[k] = mean;
+                a.em2[k] = m2;
+                if (step == a.e_every && a.q1) { a.q1[k] = q; a.p1[k] = p; }
+                if (step + a.e_every > a.nsteps) {           // last sampled row
+                    const double hm = a.ek[k] + mean;
+                    a.ehmean[k] = hm;
+                    a.eosc[k] = sqrt(m2 / n) / hm;
+                }
+            }
             if (mine && a.out_every > 0 && (step % a.out_every) == 0) {
                 const long row = step / a.out_every;
                 a.qout[row * a.step_stride + k * a.orbit_stride] = q;
@@ -532,6 +572,32 @@ int map_prepare_sympl(Ctx& c, int fam, double per, const double* x, const double
     return ST_OK;
 }
 
+// StandardMapIterate python/04_standard_map/main.py:27-39 (training / reference orbits of the standard map, no wrap):
+// f (2, N, nm) C order, f[:, i, 0] = X0[:, i], J' = J + k sin(th), th' = th + J'.  One thread per orbit.
+__global__ void standard_map_iterate_kernel(double kk, long nm, long N, const double* __restrict__ X0, double* __restrict__ f)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    double th = X0[i], J = X0[N + i];
+    double* fth = f + i * nm;
+    double* fJ = f + (N + i) * nm;
+    fth[0] = th; fJ[0] = J;
+    for (long l = 1; l < nm; l++) {
+        J = J + kk * sin(th);
+        th = th + J;
+        fth[l] = th; fJ[l] = J;
+    }
+}
+
+int standard_map_iterate(Ctx& c, double kk, long nm, long N, const double* d_X0, double* d_f)
+{
+    if (N <= 0 || nm <= 0) return ST_OK;
+    standard_map_iterate_kernel<<<(unsigned)((N + 127) / 128), 128, 0, c.stream>>>(kk, nm, N, d_X0, d_f);
+    SGP_CUDA(cudaGetLastError());
+    count_launch();
+    return ST_OK;
+}
+
 static int init_exp_table()
 {
     static bool done[64] = {};
@@ -560,6 +626,7 @@ int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched)
     if (ss > 16) ss = 16;
     if (a.nmodels > 1) ss = (ss + a.nmodels - 1) / a.nmodels * a.nmodels;      // work items start at a turn boundary of a split map
     a.slice_steps = ss;
+    a.start_delta = (solver == 3) ? 1 : 0;
     const long warps_needed = nbatches;
     long blocks = (warps_needed + MAP_WARPS - 1) / MAP_WARPS;
     const long cap = (long)(c.sm_count > 0 ? c.sm_count : 148) * MAP_BLOCKS_PER_SM;
@@ -580,13 +647,15 @@ int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched)
         case FAM_SUM: ML(FAM_SUM, 2); break;
         default: set_error("unknown kernel family %d", fam); return ST_BADARG;
         }
-    } else {
+    } else if (solver == 1 || solver == 3) {
         switch (fam) {
         case FAM_PRODUCT: ML(FAM_PRODUCT, 1); break;
         case FAM_SQ: ML(FAM_SQ, 1); break;
         case FAM_SUM: ML(FAM_SUM, 1); break;
         default: set_error("unknown kernel family %d", fam); return ST_BADARG;
         }
+    } else {
+        set_error("unknown solver %d", solver); return ST_BADARG;
     }
 #undef ML
     SGP_CUDA(cudaGetLastError());

@@ -14,6 +14,14 @@ enum MapKind : int {
                             // applymap_tok python/05_tokamak/Split_SympGPR/func.py:184-219
 };
 
+// energy function of the fused quality metric (python/functions/func.py:262-272 `quality`: Eosc = std(H)/mean(H) per orbit)
+enum EnergyKind : int {
+    ENERGY_NONE = 0,
+    ENERGY_PENDULUM = 1,   // H = p^2/2 + U0 (1 - cos(q + pi)), epar[0] = U0: energy() python/01_pendulum/implicit/func.py:116-117
+    ENERGY_TOKAMAK = 2,    // H = -Aph(r, q, 0), r = compute_r([p 1e-2, q, 0], 0.3), epar = {eps, m, phase}:
+                           // energy() python/05_tokamak/Split_SympGPR/func.py:234-246, Aph fieldlines.f90:58-64
+};
+
 constexpr int MAP_CHUNK = 64;        // training points per chunk (one bulk copy)
 constexpr int MAP_GF = 4;            // fields of a guess-GP chunk:      u, v, y, alpha
 constexpr int MAP_TF = 5;            // fields of a symplectic-GP chunk: u, v, y, alpha_q, alpha_P
@@ -31,6 +39,7 @@ struct MapArgs {
     int nmodels;
     int kind;
     long E, nsteps;
+    int start_delta;                 // 1: the guess GP predicts P - p (SGP_SOLVER_NEWTON_DELTA): the solver starts at p + guess
     const double *q0, *p0;
     // history: row r (= step / out_every) of orbit k at [r*step_stride + k*orbit_stride]; out_every = 0: none
     double *qout, *pout, *pdiff;
@@ -38,6 +47,14 @@ struct MapArgs {
     double *qfinal, *pfinal;         // last state; also carries the state from one work item to the next
     double* pdstate;                 // running pdiff between work items (only when pdiff != nullptr)
     unsigned long long* stats;       // [0] residual evaluations, [1] solver exits without convergence
+    // fused quality metrics (ekind != ENERGY_NONE): running mean / sum of squares of H - H(0) per orbit over the rows
+    // 0, e_every, 2 e_every, ... (Welford), so that no history has to be written; first mapped state for `gd`
+    int ekind;
+    long e_every;
+    double epar[4];
+    double *ek, *emean, *em2;        // E each: H(0), mean of H - H(0), sum of squared deviations
+    double *q1, *p1;                 // state after e_every steps (row 1 of the sampled history) or nullptr
+    double *eosc, *ehmean;           // E each, written with the last step: std(H)/mean(H) and mean(H)
     // work distribution: a work item is slice_steps steps of one batch of 32 orbits; runnable batches wait
     // in a FIFO (map.cu).  All of it is zeroed before launch.
     long slice_steps;
@@ -54,5 +71,7 @@ int map_prepare_guess(Ctx& c, int fam, double per, const double* x, const double
 int map_prepare_sympl(Ctx& c, int fam, double per, const double* x, const double* y, const double* alpha, long n, double* tch);
 // a.ticket / a.slots / a.progress / a.slice_steps are filled in by map_launch from `sched` (map_sched_bytes(E) bytes)
 int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched);
+// StandardMapIterate (python/04_standard_map/main.py:32-39) on device arrays: X0 (2, N), f (2, N, nm)
+int standard_map_iterate(Ctx& c, double kk, long nm, long N, const double* d_X0, double* d_f);
 
 }  // namespace sgp

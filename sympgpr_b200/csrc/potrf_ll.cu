@@ -218,68 +218,88 @@ __device__ void diag_tile_invert(double* S, double* tmp, int tid)
 constexpr int DB = 32;
 
 
-// warp 0 only.  Factor the diagonal block at k0 in place (lower), write its inverse transposed into the block's
-// strict upper triangle and 1/l_cc into xd[].  Warp-synchronous, operands in shared memory.  (Two register-
-// resident variants -- rows exchanged by shuffles, or broadcast through a line of shared memory -- were slower:
-// under the 168-register budget of a 288-thread CTA they spill, also into the DMMA main loop.)
-__device__ __forceinline__ void warp_potrf32(double* S, int k0, double* xd, int* info, int col0, int lane)
+// warp 0 only.  Factor the diagonal block at k0 in place (lower), write its inverse transposed into the block's strict
+// upper triangle and 1/l_cc into xd[].  Register-resident: lane = row, the row lives in 32 registers, columns
+// travel by shuffles; no shared-memory round trip on the dependent chain.  Compact code (two rolled loops of 32
+// steps; a fully unrolled triangular version is 25 000 instructions and runs at instruction-fetch speed) and
+// branch-free (selects, so the shuffles need no re-convergence).  __noinline__: own register allocation.
+//   factor : the register array is shifted by one per column, so the current column is always row[0]:
+//            d = row_j[0]; l = row[0] / sqrt(d); row[c-1] = row[c] - l * L(j+c, j)
+//   inverse: lane r accumulates row r of X = L^-1 in x[0..31] (x = e_r at the start);
+//            step k: lane k scales its finished row by 1/l_kk; lanes r > k: x[c] -= L(r,k) X(k,c)
+__device__ __noinline__ void warp_potrf32_reg(double* S, int k0, double* xd, int* info, int col0)
 {
-    double* Sr = S + (k0 + lane) * LL_LD + k0;              // row `lane` of the block
-    for (int j = 0; j < DB; j++) {
-        double d = S[(k0 + j) * LL_LD + k0 + j];
-        if (!(d > 0.0)) {                                    // also NaN
-            if (lane == 0) atomicCAS(info, 0, col0 + k0 + j + 1);
-            d = 1.0;
-        }
-        // 1/sqrt(d) by rsqrt (1 ulp) and l_jj = d * rsqrt(d): the correctly rounded sqrt + divide sequences cost
-        // ~800 cycles per column on the critical path of the whole factorisation; log(l_jj) is taken later, in parallel
-        const double inv = rsqrt(d), dj = d * inv;
-        __syncwarp();                                        // every lane has read the pivot
-        if (lane > j) Sr[j] *= inv;
-        else if (lane == j) { Sr[j] = dj; xd[k0 + j] = inv; }
-        __syncwarp();
-        if (lane > j) {
-            const double l = Sr[j];
-            const double* Cj = S + k0 * LL_LD + k0 + j;      // Cj[c*LL_LD] = L(c, j)
-            int c = j + 1;
-            for (; c + 3 <= lane; c += 4) {
-                const double l0 = Cj[c * LL_LD], l1 = Cj[(c + 1) * LL_LD], l2 = Cj[(c + 2) * LL_LD], l3 = Cj[(c + 3) * LL_LD];
-                const double a0 = Sr[c], a1 = Sr[c + 1], a2 = Sr[c + 2], a3 = Sr[c + 3];
-                Sr[c] = fma(-l, l0, a0); Sr[c + 1] = fma(-l, l1, a1); Sr[c + 2] = fma(-l, l2, a2); Sr[c + 3] = fma(-l, l3, a3);
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double* Sr = S + (k0 + lane) * LL_LD + k0;
+    double row[DB];
+#pragma unroll
+    for (int c = 0; c < DB; c++) row[c] = (c <= lane) ? Sr[c] : 0.0;
+    double myinv = 1.0;
+    int bad = 0;
+    // two halves: after 16 shifts only 15 live columns remain, so the second half moves half the data
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int NC = half == 0 ? DB : DB / 2;              // live register slots in this half
+#pragma unroll 1
+        for (int j = half * (DB / 2); j < (half + 1) * (DB / 2); j++) {
+            double d = __shfl_sync(FULL, row[0], j);
+            const bool neg = !(d > 0.0);                     // also NaN
+            bad = (neg && bad == 0) ? j + 1 : bad;
+            d = neg ? 1.0 : d;
+            const double inv = rsqrt(d);
+            const double lj = (lane == j) ? d * inv : row[0] * inv;
+            myinv = (lane == j) ? inv : myinv;
+            Sr[j] = (lane >= j) ? lj : Sr[j];                // (plain select + store: no divergent branch)
+#pragma unroll
+            for (int c = 1; c < NC; c++) {
+                const double lc = __shfl_sync(FULL, lj, (j + c) & 31);   // L(j + c, j); wrapped lanes give garbage in dead slots
+                row[c - 1] = fma(-lj, lc, row[c]);
             }
-            for (; c <= lane; c++) Sr[c] = fma(-l, Cj[c * LL_LD], Sr[c]);
-        }
-        __syncwarp();
-    }
-    // inverse of the block: lane = column c, forward substitution down the column; X(r,c) -> S[(k0+c)][k0+r]
-    {
-        const int c = lane;
-        double* Xc = S + (k0 + c) * LL_LD + k0;             // Xc[r] = X(r, c) for r > c
-        for (int r = c + 1; r < DB; r++) {
-            const double* Lr = S + (k0 + r) * LL_LD + k0;   // row r of L
-            double s0 = Lr[c] * xd[k0 + c], s1 = 0.0;
-            int k = c + 1;
-            for (; k + 1 < r; k += 2) {
-                s0 = fma(Lr[k], Xc[k], s0);
-                s1 = fma(Lr[k + 1], Xc[k + 1], s1);
-            }
-            if (k < r) s0 = fma(Lr[k], Xc[k], s0);
-            Xc[r] = -(s0 + s1) * xd[k0 + r];
+            row[NC - 1] = 0.0;
         }
     }
+    if (bad != 0 && lane == 0) atomicCAS(info, 0, col0 + k0 + bad);
+    xd[k0 + lane] = myinv;
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < DB; c++) row[c] = (c == lane) ? 1.0 : 0.0;
+    double lk = Sr[0];
+    // two halves: rows k < 16 of X have no entries beyond column 15
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int NC = half == 0 ? DB / 2 : DB;
+#pragma unroll 1
+        for (int k = half * (DB / 2); k < (half + 1) * (DB / 2); k++) {
+            const double lnext = Sr[(k + 1) & 31];           // L(r, k+1): off the dependent chain
+            const double sc = (lane == k) ? myinv : 1.0;
+            const double ml = (lane > k) ? -lk : 0.0;
+#pragma unroll
+            for (int c = 0; c < NC; c++) {
+                const double xs = row[c] * sc;
+                const double xkc = __shfl_sync(FULL, xs, k); // X(k, c), final
+                row[c] = fma(ml, xkc, xs);
+            }
+            lk = lnext;
+        }
+    }
+    // X(r, c), r > c, transposed into the strict upper triangle of the block
+#pragma unroll
+    for (int c = 0; c < DB; c++)
+        if (c < lane) S[(k0 + c) * LL_LD + k0 + lane] = row[c];
     __syncwarp();
 }
 
 // all 256 consumer threads; S lower = matrix on entry, L on exit; upper/xd = X^T; scratch: >= 32*96 doubles
-__device__ void diag_tile_factor_invert(double* S, double* xd, double* scratch, int tid, int* info, int col0, double* logout,
+__device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, double* scratch, int tid, int* info, int col0, double* logout,
                                         unsigned long long* stamp)
 {
-    const int lane = tid & 31;
     for (int kb = 0; kb < TILE / DB; kb++) {
         const int k0 = kb * DB, R0 = k0 + DB, nrows = TILE - R0;
         unsigned long long tw0 = 0ull;
         if (stamp && tid == 0) tw0 = globaltimer();
-        if (tid < 32) warp_potrf32(S, k0, xd, info, col0, lane);
+        __syncwarp();                                        // (trace only diverges lane 0: re-converge, or the shuffles take their slow path)
+        if (tid < 32) warp_potrf32_reg(S, k0, xd, info, col0);
         if (stamp && tid == 0) stamp[3] += globaltimer() - tw0;      // trace: time in the warp-level block factorisations
         consumer_bar();
         if (nrows > 0) {
@@ -384,9 +404,8 @@ __device__ void diag_tile_factor_invert(double* S, double* xd, double* scratch, 
 
 // TRACE: record per-task time stamps (tools/ll_trace.py); a separate instantiation so that the production
 // kernel carries no trace state through the register-tight main loop
-// BLOCKED: diagonal tiles by the blocked routine (4x faster per tile, which is what paces matrices up to
-// n ~ 16k) or by the unblocked one.  The blocked code costs the kernel a few spilled registers that also show up in the
-// DMMA main loop (-2 % at n = 32 768, where the diagonal tiles are off the critical path), hence two instantiations.
+// BLOCKED: diagonal tiles by the blocked routine (default; its two helpers are __noinline__ so that their register
+// allocation stays out of the DMMA main loop: 0 bytes spilled) or by the unblocked one (kept for comparison).
 template <bool TRACE, bool BLOCKED>
 __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
 {
@@ -641,7 +660,11 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     const unsigned grid = (unsigned)(ntasks < sms ? ntasks : sms);
     void* args[] = {&a};
-    const bool blocked = nt < 192;                       // n < 24 576: the chain of diagonal tiles paces the factorisation
+    // diagonal tiles by the blocked routine: the chain of diagonal tiles paces the factorisation up to n ~ 16k
+    // (n = 8192: 12.0 ms against 18.7 ms unblocked; n = 32 768: 344 against 348 ms).  SGP_LL_BLOCKED=0 selects the
+    // unblocked routine (measurements only).
+    static const char* force_blocked = getenv("SGP_LL_BLOCKED");
+    const bool blocked = force_blocked ? force_blocked[0] != '0' : true;
     const void* kern = trace ? (blocked ? (const void*)potrf_ll_kernel<true, true> : (const void*)potrf_ll_kernel<true, false>)
                              : (blocked ? (const void*)potrf_ll_kernel<false, true> : (const void*)potrf_ll_kernel<false, false>);
     SGP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(WS_THREADS), args, LL_SMEM, c.stream));

@@ -334,6 +334,28 @@ def test_applymap_matches_oracle(api, O, C, kind, kname, solver):
         assert np.isnan(pr).any() and not np.isnan(pr[:, :]).all()
 
 
+def test_newton_delta_start(api, O, C):
+    """SGP_SOLVER_NEWTON_DELTA: Newton started at p + guess for a guess GP trained on P - p (scripts 03/04/05).  Same
+    trajectories as the oracle's hybrd1 from the reference's far start wherever both land on the root next to p
+    (the far start may pick another genuine root), in fewer residual evaluations than Newton from the far start."""
+    m = _model(O, 150, guess="dP")
+    E, nm = 64, 12
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 1.0 + O.halton(E, 7) * 4.0
+    ref, good = _oracle_map(C, 2, nm, q0, p0, m, True)
+    assert good.sum() >= 0.7 * E
+    outs = {}
+    for solver in ("newton", "newton_delta"):
+        outs[solver] = api.applymap_standard(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"],
+                                             m["Kyinv"], solver=solver, alphap=m["alphap"], alpha=m["alpha"], return_stats=True)
+    q, p, pd, st = outs["newton_delta"]
+    _check_orbits(C, m, q, p, ref[0], ref[1], good, True, True, max_other_root=0.3)
+    agree = (_wrapdiff(q[-1], ref[0][-1], True) < 1e-8) & (_wrapdiff(p[-1], ref[1][-1], True) < 1e-8)
+    assert agree[good].mean() > 0.7
+    assert st["unconverged"] == 0
+    assert st["evaluations"] < outs["newton"][-1]["evaluations"]
+
+
 def test_applymap_first_step_matches_reference_python_layer(api):
     """One map step against tests/golden/path_product.npz (reference calcQ / Pnewton root)."""
     g = np.load(os.path.join(G, "path_product.npz"))
@@ -585,3 +607,58 @@ def test_dof2_nll_and_gradient_match_oracle(api, O, N):
     assert np.isclose(v, vr, rtol=1e-9), (v, vr)
     assert np.allclose(g, gr, rtol=1e-8, atol=1e-8 * np.abs(gr).max()), (g, gr)
     assert np.isclose(api.nll_chol4(hyp, x, z, 4 * N), vr, rtol=1e-9)
+
+
+# ------------------------------------------------------------------- quality metrics, generators
+@pytest.mark.parametrize("energy", ["pendulum", "tokamak"])
+def test_fused_quality_matches_history_based_quality(api, O, energy):
+    """Eosc = std(H)/mean(H) accumulated inside the map kernel against `quality` evaluated on the full history the
+    reference would hold (python/functions/func.py:262-272; energy: 01_pendulum/implicit/func.py:116-117 and
+    Split_SympGPR/func.py:234-246)."""
+    m = _model(O, 120, guess="P")
+    E, nm = 70, 41
+    q0 = O.halton(E, 5) * 2 * np.pi
+    if energy == "pendulum":
+        kind, fn, par, e_every = "pendulum", api.applymap, (0.7,), 1
+        p0 = 1.0 + O.halton(E, 7) * 4.0
+    else:
+        kind, fn, par, e_every = "tokamak", api.applymap_tok, (0.001, 3.0, 0.2), 4
+        p0 = (1.0 + O.halton(E, 7) * 4.0) * 0.8          # some orbits are lost: NaN energy, NaN Eosc
+    args = (m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"], m["Kyinv"])
+    q, p = fn(nm, E, *args, solver="newton", alphap=m["alphap"], alpha=m["alpha"])[:2]
+    out = api.applymap_quality(kind, nm, E, *args, energy=energy, energy_par=par, e_every=e_every, solver="newton",
+                               alphap=m["alphap"], alpha=m["alpha"])
+    qs, ps = q[::e_every], p[::e_every]
+    if energy == "pendulum":
+        H = O.energy_pendulum(qs, ps, par[0])
+    else:
+        H = O.energy_tok(qs, ps, par[0], par[1], par[2]).T
+    with np.errstate(invalid="ignore"):
+        ref = O.quality_eosc(H)
+        hm = H.mean(axis=0)
+    assert np.array_equal(np.isnan(out["Eosc"]), np.isnan(ref))
+    ok = ~np.isnan(ref)
+    assert ok.sum() > E // 2
+    if energy == "tokamak":
+        assert (~ok).any()
+    assert np.allclose(out["Eosc"][ok], ref[ok], rtol=1e-7, atol=1e-13), np.abs(out["Eosc"][ok] / ref[ok] - 1).max()
+    assert np.allclose(out["Hmean"][ok], hm[ok], rtol=1e-12)
+    assert np.array_equal(out["q1"], qs[1], equal_nan=True) and np.array_equal(out["p1"], ps[1], equal_nan=True)
+    assert np.array_equal(out["qfinal"][ok], q[-1][ok])
+    # the reference's quality() on the same numbers: gd against a shifted "reference orbit"
+    ys = np.zeros((3, 2, E)); ys[2, 0] = qs[1] + 1e-3; ys[2, 1] = ps[1] - 2e-3
+    Eosc, gd, stdgd = api.quality(out["q1"], out["p1"], out["Eosc"], ys, 2)
+    assert np.allclose(gd[ok], 0.5 * (1e-6 + 4e-6), rtol=1e-6)
+
+
+def test_standard_map_iterate_matches_reference_loop(api, O):
+    N, nm, k = 50, 25, 0.9
+    X0 = np.vstack((O.halton(N, 2) * 2 * np.pi, O.halton(N, 3) * 2 * np.pi))
+    f = api.StandardMapIterate(k, nm, N, X0)
+    fr = O.standard_map_iterate(k, nm, N, X0)
+    assert f.shape == (2, N, nm)
+    assert np.array_equal(f[:, :, 0], X0)
+    assert np.allclose(f, fr, rtol=1e-11, atol=1e-11)
+    assert np.allclose(f[:, :, 1], fr[:, :, 1], rtol=1e-15, atol=1e-15)
+    with pytest.raises(ValueError):
+        api.StandardMapIterate(k, nm, N, X0.T)

@@ -277,3 +277,25 @@ def test_split_map_oracle_matches_reference_loop():
     assert np.allclose(q, g["qmap"], rtol=1e-10, atol=1e-10, equal_nan=True)
     assert np.allclose(p, g["pmap"], rtol=1e-10, atol=1e-10, equal_nan=True)
     assert np.all(g["qmap"][-1] == 0.0)          # whole turns only: the last row was never written
+
+
+def test_quality_and_generator_restatements():
+    """Oracle twins of `quality` / `energy` / StandardMapIterate on closed-form cases."""
+    from oracle import oracle as O
+    # standard map, one step by hand (python/04_standard_map/main.py:27-30)
+    X0 = np.array([[0.3, 1.0], [0.5, 2.0]])
+    f = O.standard_map_iterate(0.9, 3, 2, X0)
+    J1 = 0.5 + 0.9 * np.sin(0.3)
+    assert np.isclose(f[1, 0, 1], J1) and np.isclose(f[0, 0, 1], 0.3 + J1)
+    J2 = J1 + 0.9 * np.sin(0.3 + J1)
+    assert np.isclose(f[1, 0, 2], J2)
+    # energy oscillation: constant energy -> 0; pendulum energy at the stable point q = pi (x + pi convention)
+    H = np.ones((5, 3)) * np.array([1.0, 2.0, 3.0])
+    assert np.allclose(O.quality_eosc(H), 0.0)
+    assert np.isclose(O.energy_pendulum(np.pi, 0.0, 2.0), 0.0)
+    assert np.isclose(O.energy_pendulum(0.0, 1.0, 2.0), 0.5 + 4.0)
+    # Aph at eps = 0: -(r^2/2 - r^4)
+    assert np.isclose(O.aph(0.3, 1.0, 0.0, 0.0, 2, 1, 0.0), -(0.045 - 0.0081))
+    Ht = O.energy_tok(np.array([[0.5]]), np.array([[2.0]]), 0.0, 2, 0.0)
+    r = O.compute_r(np.array([2.0e-2, 0.5, 0.0]), 0.3)
+    assert np.isclose(Ht[0, 0], r**2 / 2 - r**4)

@@ -1,6 +1,6 @@
 """BASELINE config 5: NLL+gradient size sweep N = 2k..32k (n up to 65 536) and a 10^7-orbit map launch.
     python tools/sweep.py > gpurun_out/sweep.jsonl"""
-import ctypes, json, sys, time
+import ctypes, json, os, sys, time
 import numpy as np
 sys.path.insert(0, ".")
 import torch
@@ -10,7 +10,9 @@ L = _lib.lib(); ctx = _lib.context(0)
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream); ctx.set_stream(stream.cuda_stream)
 _lib.check(L.sgp_set_profiling(ctx.handle, 1), "prof")
-for N in (2048, 4096, 8192, 16384, 32768):
+MAXN = int(os.environ.get("SWEEP_MAX_N", "32768"))
+MINN = int(os.environ.get("SWEEP_MIN_N", "0"))
+for N in [v for v in (1024, 2048, 4096, 8192, 16384, 32768) if MINN <= v <= MAXN]:
     n = 2 * N
     d = W.standard_map_training(N)
     hyp = W.timing_hyp(N, d["sig"], 1e-8)
@@ -38,6 +40,8 @@ for N in (2048, 4096, 8192, 16384, 32768):
     ctx.release_workspace(); torch.cuda.empty_cache()
 
 # 10^7 orbits, 16 steps, Nt = 4096
+if os.environ.get("SWEEP_NO_MAP"):
+    sys.exit(0)
 Nt, E, steps = 4096, 10_000_000, 16
 dm = W.standard_map_training(Nt)
 hm = W.timing_hyp(Nt, dm["sig"], 1e-8, factor=1.0); hpm = W.timing_hyp(Nt, dm["sigp"], 1e-8, factor=1.0)

@@ -335,6 +335,11 @@ def main():
         t_map_local = m0.elapsed_time(m1) * 1e-3
         t_map = max_over_ranks(t_map_local)
         st = stats.clone()
+        npass = ctypes.c_ulonglong(0)
+        _lib.check(L.sgp_map_last_passes(ctx.handle, ctypes.byref(npass)), "sgp_map_last_passes")
+        passes = torch.tensor([npass.value], dtype=torch.int64, device=dev)
+        if world > 1:
+            dist.all_reduce(passes, op=dist.ReduceOp.SUM)
         cks = torch.stack([torch.nansum(qf), torch.nansum(pf)])
         if world > 1:                                   # the only collectives of the path: gather statistics
             dist.all_reduce(st, op=dist.ReduceOp.SUM)
@@ -348,21 +353,26 @@ def main():
         h0.record(stream); map_run(0, hsteps); h1.record(stream)
         sync_all()
         t_map_h = max_over_ranks(h0.elapsed_time(h1) * 1e-3)
-        qh, ph = qf.clone(), pf.clone()
-        # Newton from the reference's start (solver 1) on the same short run, and the headline solver again: how many
-        # orbits end within 1e-8 of the hybrd1 trajectories after hsteps steps (full-size parity property)
+        # Newton from the reference's start (solver 1) on the same short run
         n0, n1 = ev(), ev()
         n0.record(stream); map_run(1, hsteps); n1.record(stream)
         sync_all()
         t_map_n = max_over_ranks(n0.elapsed_time(n1) * 1e-3)
+        # full-size sanity property: the learned map follows the map it was trained on (standard map, K = 0.9);
+        # distance of the headline solver's orbits from the exact map after hsteps steps
         map_run(MAP_SOLVER, hsteps)
         sync_all()
+        qt, pt = q0.clone(), p0.clone()
+        for _ in range(hsteps):
+            Pn = pt + 0.9 * torch.sin(qt)
+            qt = torch.remainder(qt + Pn, 2 * math.pi)
+            pt = torch.remainder(Pn, 2 * math.pi)
         def wrapd(x, y):
             d = (x - y).abs()
             return torch.minimum(d, (d - 2 * math.pi).abs())
-        both = torch.isfinite(qh) & torch.isfinite(qf)
-        same = both & (wrapd(qf, qh) < 1e-8) & (wrapd(pf, ph) < 1e-8)
-        agree = torch.stack([same.sum(), both.sum()]).to(torch.int64)
+        err = torch.maximum(wrapd(qf, qt), wrapd(pf, pt))
+        fin = torch.isfinite(err)
+        agree = torch.stack([(fin & (err < 1e-2)).sum(), fin.sum()]).to(torch.int64)
         if world > 1:
             dist.all_reduce(agree, op=dist.ReduceOp.SUM)
         # end to end through the public API: host arrays in, final states out (model staging, H2D of the
@@ -379,15 +389,16 @@ def main():
         map_info = {"metric": "orbit_map_steps_per_s", "value": orbit_steps / t_map, "unit": "orbit-steps/s",
                     "solver": MAP_SOLVER_NAME, "n_train": Nt, "orbits_total": E * world, "steps": a.map_steps,
                     "sweeps_per_orbit_step": 1 + evals / orbit_steps,
+                    "lane_utilisation": (orbit_steps + evals) / (32.0 * max(1, int(passes.item()))),
                     "pair_evals_per_s": orbit_steps * pair_evals / t_map,
-                    "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe", "note": "useful (per-orbit) pair evaluations x 34 DP instr; lanes of a warp that wait for a slower neighbour's Newton iteration are not counted",
+                    "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe", "note": "useful (per-orbit) pair evaluations x 34 DP instr; lanes of a warp that idle during a pass (waiting for the other training set, or for the end of a work item) are not counted: achieved / lane_utilisation is the issued rate",
                                  "achieved": orbit_steps * pair_evals * dp_instr / t_map / world, "peak": fp64_peak,
                                  "unit": "DP instr/s per GPU", "frac": orbit_steps * pair_evals * dp_instr / t_map / world / fp64_peak},
                     "e2e": {"value": orbit_steps / t_map_e2e, "unit": "orbit-steps/s",
                             "h2d_bytes_per_step": int(16 * E + 8 * (3 * Nt + 4 * Nt)), "d2h_bytes_per_step": int(16 * E)},
                     "hybrd_value": float(E) * world * hsteps / t_map_h, "hybrd_steps": hsteps,
                     "newton_refstart_value": float(E) * world * hsteps / t_map_n,
-                    "same_as_hybrd_after_hsteps": {"within_1e-8": int(agree[0].item()), "compared": int(agree[1].item())},
+                    "follows_exact_map_after_hsteps": {"within_1e-2": int(agree[0].item()), "finite": int(agree[1].item())},
                     "unconverged": int(st[1].item()),
                     "clocks": sampler.summary(t_mwall0, t_mwall1), "rank0_s": t_map_local,
                     "checksum": [float(cks[0].item()), float(cks[1].item())]}

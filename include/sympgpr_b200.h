@@ -213,6 +213,11 @@ int sgp_model_applymap_quality_dev(sgp_ctx* ctx, const sgp_model* m, int kind, i
                                    double* d_q1, double* d_p1, double* d_eosc, double* d_hmean,
                                    unsigned long long* d_stats);     /* async on ctx stream   */
 
+/* Statistics of the last map launch of this context (synchronises): passes over a training set summed over all
+ * warps.  32 * passes against the lane-level evaluation count (stats[0] + one guess per orbit-step) tells how
+ * well the independently advancing orbits of a warp share their passes. */
+int sgp_map_last_passes(sgp_ctx* ctx, unsigned long long* passes);
+
 /* ---- fieldlines module (tokamak loss test) ------------------------------------------------ */
 /* fieldlines.f90:94-107 compute_r(z(3), rstart): z = (pth, th, ph); host arithmetic. */
 double sgp_compute_r(double pth, double th, double ph, double rstart);

@@ -71,6 +71,7 @@ _PROTOS = {
     "sgp_standard_map_iterate": (c_i, [c_vp, c_d, c_l, c_l, c_dp, c_dp]),
     "sgp_model_applymap_quality_dev": (c_i, [c_vp, c_vp, c_i, c_i, c_l, c_l, c_vp, c_vp, c_vp, c_vp, c_i, c_dp, c_l, c_vp,
                                              c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "sgp_map_last_passes": (c_i, [c_vp, c_ullp]),
     "sgp_compute_r": (c_d, [c_d, c_d, c_d, c_d]),
     "sgp_ath": (c_d, [c_d, c_d, c_d]),
     "sgp_spd_factor": (c_i, [c_vp, c_dp, c_l, c_dp, c_dp, c_dp]),

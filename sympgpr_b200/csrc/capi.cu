@@ -597,6 +597,18 @@ int sgp_model_applymap_quality_dev(sgp_ctx* ctx, const sgp_model* m, int kind, i
     return map_launch(ctx->c, m->fam, solver, a, ctx->c.flags.p);
 }
 
+int sgp_map_last_passes(sgp_ctx* ctx, unsigned long long* passes)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (!passes) { set_error("map_last_passes: null output"); return ST_BADARG; }
+    *passes = 0ull;
+    if (!c.flags.p) return ST_OK;
+    SGP_TRY(sync(c));
+    SGP_CUDA(cudaMemcpy(passes, (char*)c.flags.p + 24, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return ST_OK;
+}
+
 int sgp_standard_map_iterate(sgp_ctx* ctx, double k, long nm, long N, const double* X0, double* f)
 {
     SGP_TRY(check_ctx(ctx));

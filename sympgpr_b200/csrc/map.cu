@@ -118,6 +118,7 @@ struct Stream {
     double* buf;                 // 2 * MAP_BUF_DOUBLES
     unsigned long long* bar;     // 2
     uint32_t seq;
+    unsigned int passes;         // sweeps this warp has run (utilisation statistics)
     const double* primed;        // the set whose chunks 0 and 1 are in flight between sweeps
 };
 
@@ -190,6 +191,7 @@ __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set
     z.a0 = z.a1 = z.b0 = z.b1 = z.c0 = z.c1 = z.d0 = z.d1 = 0.0;
     const double nhx = -h.hx, nhy = -h.hy, lx2 = h.lx2, ly2 = h.ly2;
     const bool any = __any_sync(0xffffffffu, active);
+    st.passes++;
     for (int c = 0; c < nch; c++) {
         const uint32_t slot = st.seq & 1u, par = (st.seq >> 1) & 1u;
         mbar_wait(st.bar + slot, par);
@@ -267,6 +269,7 @@ map_kernel(MapArgs a)
     st.buf = s_buf[warp];
     st.bar = s_bar[warp];
     st.seq = 0;
+    st.passes = 0u;
     if (lane == 0) {
         mbar_init(st.bar + 0, 1);
         mbar_init(st.bar + 1, 1);
@@ -509,6 +512,7 @@ map_kernel(MapArgs a)
     if (lane == 0) {
         if (evals) atomicAdd(a.stats + 0, evals);
         if (fails) atomicAdd(a.stats + 1, (unsigned long long)fails);
+        if (st.passes) atomicAdd(a.ticket + 3, (unsigned long long)st.passes);  // passes over a training set, per warp (utilisation statistics)
     }
 }
 

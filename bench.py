@@ -439,12 +439,16 @@ def main():
                 "dtype": "f64", "data": "synthetic", "config": workload_config(a),
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches, "clocks": clocks,
-                "roofline": {"kernel": "gemm_f64_kernel (DMMA m8n8k4 structured GEMM: potrf/trtri/lauum updates)",
+                "roofline": {"kernel": "potrf_ll_kernel + gemm_f64_ws_kernel (DMMA m8n8k4: potrf, trtri, lauum; 512 launches per "
+                                       "evaluation taken together)",
                              "bound": "tensor", "achieved": achieved, "peak": dgemm_tflops, "unit": "TFLOP/s",
-                             "frac": achieved / dgemm_tflops, "traffic": None,
+                             "frac": achieved / dgemm_tflops, "traffic": read_traffic(n),
                              "note": "achieved = n^3 algorithmic flops / (potrf+trtri+lauum stage time of the last timed "
                                      "step, CUDA events on the launch stream); peak = cuBLAS DGEMM 8192^3 measured in "
-                                     "this run (MEASURED_PEAKS.json has no fp64 entry)"},
+                                     "this run (MEASURED_PEAKS.json has no fp64 entry; DMMA issue limit 37.2); traffic = "
+                                     "DRAM bytes read + written by those kernels in one evaluation (ncu, "
+                                     "profiles/r01_traffic_n32768.json), against 3 x 8 n^2 / 2 algorithmic matrix bytes: "
+                                     "operand panels are re-streamed per tile task, at 1.2 TB/s = 19 % of the HBM peak"},
                 "stages": stage_roof,
                 "roofline_fill": {"kernel": "fill_hess_kernel", "bound": "hbm", "achieved": fill_gbs,
                                   "peak": hbm, "unit": "GB/s", "frac": fill_gbs / hbm,
@@ -459,6 +463,15 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def read_traffic(n):
+    """DRAM bytes of the DMMA kernels per evaluation from the committed ncu capture of this matrix order, else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", f"r01_traffic_n{n}.json")) as f:
+            return float(json.load(f)["dmma_dram_bytes_per_evaluation"])
+    except Exception:
+        return None
 
 
 def read_hbm_peak():

@@ -47,6 +47,7 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2048, help="training pairs of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-map", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the small-size NLL+gradient sweep (N = 2048..8192)")
     return ap.parse_args()
 
 
@@ -294,6 +295,37 @@ def main():
     ctx.release_workspace()
     torch.cuda.empty_cache()
 
+    # ---- size sweep (BASELINE config 5), small sizes only: N = 2048 .. 8192 on rank 0 of a single-GPU run ------
+    sweep = None
+    if world == 1 and not a.no_sweep:
+        sweep = []
+        for Ns in (2048, 4096, 8192):
+            if Ns >= N:
+                continue
+            ds = W.standard_map_training(Ns)
+            hs = W.timing_hyp(Ns, ds["sig"], 1e-8)
+            hs_c = (ctypes.c_double * 4)(*hs)
+            xs_d = torch.from_numpy(ds["xtrain"].copy()).to(dev)
+            zs_d = torch.from_numpy(ds["ztrain"].copy()).to(dev)
+            rs_d = torch.zeros(16, dtype=torch.float64, device=dev)
+
+            def step_s():
+                _lib.check(L.sgp_nll_dev(ctx.handle, 0, 0.5, 0, hs_c, xs_d.data_ptr(), zs_d.data_ptr(), 2 * Ns, 2, rs_d.data_ptr()),
+                           "sgp_nll_dev")
+            for _ in range(3):
+                step_s()
+            torch.cuda.synchronize()
+            s0, s1 = ev(), ev()
+            s0.record(stream)
+            for _ in range(5):
+                step_s()
+            s1.record(stream); s1.synchronize()
+            ms = s0.elapsed_time(s1) / 5
+            sweep.append({"N": Ns, "n": 2 * Ns, "ms_per_eval": ms, "TFLOP/s": (2.0 * Ns) ** 3 / ms / 1e9,
+                          "nll": float(rs_d[0].item())})
+        ctx.release_workspace()
+        torch.cuda.empty_cache()
+
     # ---- map leg: ensemble sharded over the GPUs, model replicated -----------------------------
     map_info = None
     if not a.no_map:
@@ -455,6 +487,8 @@ def main():
                                   "bytes": 8.0 * n * n, "ms": t_fill * 1e3},
                 "result": {"nll": float(res[0]), "grad": [float(res[1]), float(res[2])]},
                 }
+        if sweep:
+            line["sweep"] = sweep
         if map_info:
             line["map"] = map_info
         if cpu:

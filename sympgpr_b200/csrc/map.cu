@@ -108,7 +108,7 @@ __device__ __forceinline__ double exp_neg_tab(double x, const double* __restrict
     q = fma(q, r, 0.5);
     q = fma(q, r, 1.0);
     q = q * r;
-    const double T = tab[N & 63];
+    const double T = tab[(N & 63) << 5];               // the table is replicated per lane (bank-conflict free), tab = base + lane
     double res = fma(T, q, T);
     return __hiloint2double(__double2hiint(res) + ((N >> 6) << 20), __double2loint(res));
 }
@@ -261,8 +261,11 @@ map_kernel(MapArgs a)
 {
     __shared__ __align__(16) double s_buf[MAP_WARPS][2 * MAP_BUF_DOUBLES];
     __shared__ unsigned long long s_bar[MAP_WARPS][2];
-    __shared__ double s_tab[64];
-    if (threadIdx.x < 64) s_tab[threadIdx.x] = c_exp2_tab[threadIdx.x];
+    // exp table, one copy per lane: entry j of lane l at [j*32 + l], so that the 32 random indices of a warp never
+    // meet in a bank (the single 512-byte table cost 28 % extra shared-memory wavefronts, profiles/r01_ncu_prof_map_e.txt)
+    __shared__ double s_tab_all[64 * 32];
+    for (int i = threadIdx.x; i < 64 * 32; i += MAP_THREADS) s_tab_all[i] = c_exp2_tab[i >> 5];
+    const double* s_tab = s_tab_all + (threadIdx.x & 31);
     __syncthreads();                                         // the only block-wide barrier: before any work
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     Stream st;

@@ -239,6 +239,30 @@ def test_nll_grad_medium_size(api, O):
     assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr)
 
 
+def test_nll_grad_full_size_against_cpu_golden(api, O):
+    """BASELINE's headline size, N = 16384 training pairs (n = 32768): NLL and gradient against the CPU oracle's value
+    (tests/golden/fullsize_nll_N16384.json, generated by tests/golden/make_golden_fullsize.py: the oracle's formulas
+    evaluated block by block with SciPy dpotrf/dpotri on the host cores), tolerance 1e-9 relative as north_star states;
+    plus a size-independent property: the gradient agrees with central differences of the NLL itself."""
+    import json, os
+    path = os.path.join(os.path.dirname(__file__), "golden", "fullsize_nll_N16384.json")
+    g = json.load(open(path))
+    N = g["N"]
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    assert np.allclose(hyp, g["hyp"], rtol=0, atol=0)
+    v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    assert abs(v - g["nll"]) <= 1e-9 * abs(g["nll"]), (v, g["nll"])
+    assert np.allclose(gr, g["grad"], rtol=1e-9, atol=1e-9 * np.abs(g["grad"]).max()), (gr, g["grad"])
+    for t in range(2):
+        h = 1e-5 * hyp[t]
+        hp, hm = hyp.copy(), hyp.copy()
+        hp[t] += h
+        hm[t] -= h
+        fd = (api.nll_chol(hp, d["xtrain"], d["ztrain"], 2 * N) - api.nll_chol(hm, d["xtrain"], d["ztrain"], 2 * N)) / (2 * h)
+        assert abs(fd - gr[t]) <= 2e-5 * abs(gr[t]), (t, fd, gr[t])
+
+
 # ------------------------------------------------------------------------------- map
 def _model(O, N, family="product", lfac=2.0, kch=0.9, guess="dP"):
     """Standard-map model.  guess="dP": ordinary GP trained on P - p as 03/04/05 do (the solver then

@@ -58,7 +58,7 @@ _lib.check(L.sgp_model_create(ctx.handle, 0, 0.5, dp(np.ascontiguousarray(hm[:3]
                               ctypes.byref(model)), "model_create")
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(stream)
-_lib.check(L.sgp_model_applymap_dev(ctx.handle, model, 2, 1, steps, E, q0.data_ptr(), p0.data_ptr(), qf.data_ptr(), pf.data_ptr(),
+_lib.check(L.sgp_model_applymap_dev(ctx.handle, model, 2, 3, steps, E, q0.data_ptr(), p0.data_ptr(), qf.data_ptr(), pf.data_ptr(),
                                     None, None, 0, stats.data_ptr()), "applymap")
 e1.record(stream); e1.synchronize()
 t = e0.elapsed_time(e1) * 1e-3

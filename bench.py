@@ -145,7 +145,7 @@ def run_reference(a):
             "config": workload_config(a),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(a):
@@ -157,8 +157,25 @@ def workload_config(a):
 
 
 # ------------------------------------------------------------------------------------------ b200 arm
+_JSON_FD = None
+
+
+def emit(line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else that writes to fd 1 while the bench
+    runs (NCCL's version banner, library chatter) has been sent to stderr by main()."""
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    global _JSON_FD
     a = parse()
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)                      # fd 1 -> stderr for the duration of the run
     if a.impl == "reference":
         run_reference(a)
         return
@@ -493,7 +510,7 @@ def main():
             line["map"] = map_info
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -179,6 +179,15 @@ int sgp_applymap_quality(sgp_ctx* ctx, int kind, int fam, double per, int solver
                          int ekind, const double* epar4, long e_every, double* q1, double* p1,
                          double* qfinal, double* pfinal, double* eosc, double* hmean,
                          unsigned long long* stats);
+/* 2-DOF map prediction with the 4 x 4-block kernel of sgp_build_k4 (BASELINE config 3; NOT in the reference, which
+ * reduces Henon-Heiles to a section map -- python/03_henon_heiles/main.py:91-106; parity unpinned, oracle twin
+ * oracle.applymap4).  Model: xtrain = [q1; q2; P1; P2] (4 N), alpha = (K4 + |sig2n| I)^-1 [p1-P1; p2-P2; Q1-q1; Q2-q2]
+ * (4 N, sgp_fit with reg = 4), hyp3 = [lq, lP, sig].  One step: Newton (2 x 2, analytic Jacobian, start P = p) on
+ * P = p - grad_q F(q, P), then Q = q + grad_P F(q, P).  q0, p0, qfinal, pfinal: (2, E); qmap, pmap: (rows, 2, E),
+ * rows = 1 + (nm-1)/out_every, or NULL.  stats[0] Newton + dQ evaluations, stats[1] exits without convergence. */
+int sgp_applymap4(sgp_ctx* ctx, long nm, long E, const double* q0, const double* p0, const double* hyp3,
+                  const double* xtrain, const double* alpha, long N, double* qmap, double* pmap, long out_every,
+                  double* qfinal, double* pfinal, unsigned long long* stats);
 /* StandardMapIterate(k, nm, N, X0) python/04_standard_map/main.py:27-39: X0 (2, N) -> f (2, N, nm), C order,
  * J' = J + k sin(th), th' = th + J' (no wrap); the generator of the standard-map training and reference orbits. */
 int sgp_standard_map_iterate(sgp_ctx* ctx, double k, long nm, long N, const double* X0, double* f);

@@ -453,6 +453,53 @@ def nll_grad4(hyp, x, y, n, with_sig=False):
     return val, np.array(grads)
 
 
+def grad_f4(xs, xtrain, alpha, hyp):
+    """grad F at the points xs (4, E) of the 2-DOF generating function: rows of build_k4(xs, xtrain) times alpha."""
+    xs = np.asarray(xs, float)
+    E = xs.shape[1]
+    K = build_k4(xs.reshape(-1), xtrain, hyp)
+    return (K @ np.asarray(alpha, float)).reshape(4, E)
+
+
+def applymap4(nm, q0, p0, hyp, xtrain, alpha):
+    """2-DOF map loop, the twin of csrc/map.cu map4_kernel (no reference code: SURVEY 8a row X1).  One step solves
+    P = p - grad_q F(q, P) by Newton started at P = p with the Jacobian I + d grad_q F / dP taken by central
+    differences of grad_f4 here (the kernel uses the closed form), then Q = q + grad_P F(q, P).  Stops as the kernel
+    does: step <= 1e-9 max(|P|, 1).  Returns qmap, pmap (nm, 2, E)."""
+    q0 = np.asarray(q0, float); p0 = np.asarray(p0, float)
+    E = q0.shape[1]
+    qmap = np.zeros((nm, 2, E)); pmap = np.zeros((nm, 2, E))
+    qmap[0], pmap[0] = q0, p0
+    h = 1e-6
+    for i in range(nm - 1):
+        q, p = qmap[i], pmap[i]
+        P = p.copy()
+        done = np.zeros(E, bool)
+        for it in range(40):
+            F = grad_f4(np.vstack((q, P)), xtrain, alpha, hyp)
+            J = np.zeros((2, 2, E))
+            for c in range(2):
+                dP = np.zeros((2, E)); dP[c] = h
+                Fp = grad_f4(np.vstack((q, P + dP)), xtrain, alpha, hyp)
+                Fm = grad_f4(np.vstack((q, P - dP)), xtrain, alpha, hyp)
+                J[:, c] = (Fp[:2] - Fm[:2]) / (2 * h)
+            r = P - p + F[:2]
+            j00, j01, j10, j11 = 1 + J[0, 0], J[0, 1], J[1, 0], 1 + J[1, 1]
+            det = j00 * j11 - j01 * j10
+            d0 = (j11 * r[0] - j01 * r[1]) / det
+            d1 = (j00 * r[1] - j10 * r[0]) / det
+            upd = ~done
+            P[0, upd] -= d0[upd]; P[1, upd] -= d1[upd]
+            ad = np.maximum(np.abs(d0), np.abs(d1))
+            done |= ad <= 1e-9 * np.maximum(np.abs(P).max(axis=0), 1.0)
+            if done.all():
+                break
+        F = grad_f4(np.vstack((q, P)), xtrain, alpha, hyp)
+        qmap[i + 1] = q + F[2:]
+        pmap[i + 1] = P
+    return qmap, pmap
+
+
 def henon_like_training(N, seed=3):
     """Synthetic 2-DOF symplectic map for the X1 tests: one kick-drift step of a Henon-Heiles-like potential,
     P = p - dt dV/dq(q), Q = q + dt P, V = (q1^2 + q2^2)/2 + q1^2 q2 - q2^3/3; Halton points in [-0.4, 0.4]^4."""

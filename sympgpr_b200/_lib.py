@@ -68,6 +68,7 @@ _PROTOS = {
     "sgp_model_applymap_dev": (c_i, [c_vp, c_vp, c_i, c_i, c_l, c_l, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_l, c_vp]),
     "sgp_applymap_quality": (c_i, [c_vp, c_i, c_i, c_d, c_i, c_l, c_l, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp,
                                    c_dp, c_dp, c_l, c_i, c_dp, c_l, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp, c_ullp]),
+    "sgp_applymap4": (c_i, [c_vp, c_l, c_l, c_dp, c_dp, c_dp, c_dp, c_dp, c_l, c_dp, c_dp, c_l, c_dp, c_dp, c_ullp]),
     "sgp_standard_map_iterate": (c_i, [c_vp, c_d, c_l, c_l, c_dp, c_dp]),
     "sgp_model_applymap_quality_dev": (c_i, [c_vp, c_vp, c_i, c_i, c_l, c_l, c_vp, c_vp, c_vp, c_vp, c_i, c_dp, c_l, c_vp,
                                              c_vp, c_vp, c_vp, c_vp, c_vp]),

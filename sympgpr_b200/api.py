@@ -208,6 +208,8 @@ def fit(hyp, x, z, n, reg=False, want_inverse=False, want_factor=False, family="
     N = n if reg else n // 2
     x = as_f64(x).ravel()
     z = as_f64(z).ravel()
+    if int(reg) == 4:                  # 2-DOF 4 x 4-block kernel: x = [q1; q2; P1; P2], n = 4 N coordinates in all
+        N = n // 2
     if hyp.size != 4 or x.size < 2 * N or z.size < n:
         raise ValueError("fit: bad argument sizes")
     alpha = np.zeros(n)
@@ -494,6 +496,32 @@ def StandardMapIterate(k, nm, N, X0):
     check(_lib.lib().sgp_standard_map_iterate(_lib.context().handle, float(k), int(nm), int(N), dptr(X0), dptr(f)),
           "StandardMapIterate")
     return f
+
+
+def applymap4(nm, Ntest, hyp, Q0map, P0map, xtrain, alpha, out_every=1, return_stats=False):
+    """2-DOF map prediction with the 4 x 4-block kernel (BASELINE config 3; not in the reference): Q0map, P0map (2, Ntest),
+    xtrain = [q1; q2; P1; P2], alpha from fit(hyp4, xtrain, z, 4 N, reg=4)["alpha"], hyp = [lq, lP, sig].
+    Returns (qmap, pmap) of shape (rows, 2, Ntest) -- or the final states (2, Ntest) with out_every=0."""
+    hyp = _hyp3(hyp)
+    E, nm = int(Ntest), int(nm)
+    q0, p0 = as_f64(Q0map), as_f64(P0map)
+    if q0.shape != (2, E) or p0.shape != (2, E):
+        raise ValueError("applymap4: Q0map and P0map must have shape (2, Ntest)")
+    xtrain, alpha = as_f64(xtrain).ravel(), as_f64(alpha).ravel()
+    N = xtrain.size // 4
+    if alpha.size != 4 * N:
+        raise ValueError("applymap4: alpha does not match the training set")
+    rows = 1 + (nm - 1) // out_every if out_every > 0 else 0
+    qmap, pmap = np.zeros((rows, 2, E)), np.zeros((rows, 2, E))
+    qf, pf = np.zeros((2, E)), np.zeros((2, E))
+    stats = (ctypes.c_ulonglong * 2)()
+    st = _lib.lib().sgp_applymap4(_lib.context().handle, nm, E, dptr(q0), dptr(p0), dptr(hyp), dptr(xtrain), dptr(alpha), N,
+                                  dptr(qmap) if rows else _NULL, dptr(pmap) if rows else _NULL, out_every, dptr(qf), dptr(pf), stats)
+    check(st, "applymap4")
+    out = [qmap, pmap] if rows else [qf, pf]
+    if return_stats:
+        out.append(dict(evaluations=int(stats[0]), unconverged=int(stats[1]), qfinal=qf, pfinal=pf))
+    return tuple(out)
 
 
 def applymap_expl(nm, Ntest, l, Q0map, P0map, xtrain, ztrain, Kyinv, family="sum", per=0.5, **kw):

@@ -609,6 +609,37 @@ int sgp_map_last_passes(sgp_ctx* ctx, unsigned long long* passes)
     return ST_OK;
 }
 
+int sgp_applymap4(sgp_ctx* ctx, long nm, long E, const double* q0, const double* p0, const double* hyp3, const double* xtrain,
+                  const double* alpha, long N, double* qmap, double* pmap, long out_every, double* qfinal, double* pfinal,
+                  unsigned long long* stats)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (nm < 1 || E < 0 || N < 0 || !hyp3 || (E > 0 && (!q0 || !p0)) || (N > 0 && (!xtrain || !alpha))) {
+        set_error("applymap4: bad arguments"); return ST_BADARG;
+    }
+    const bool hist = (qmap && pmap && out_every > 0);
+    const long rows = hist ? 1 + (nm - 1) / out_every : 0;
+    const size_t hsz = (size_t)rows * 2 * (size_t)E;
+    const size_t setsz = (size_t)map4_chunks(N) * 256;
+    SGP_TRY(c.io.reserve((8 * (size_t)N + setsz + 8) * sizeof(double)));
+    SGP_TRY(c.mapbuf.reserve((8 * (size_t)E + 2 * hsz + 4) * sizeof(double)));
+    double* dx = c.io.as<double>(); double* da = dx + 4 * N; double* dset = da + 4 * N;
+    double* d = c.mapbuf.as<double>();
+    unsigned long long* dstats = (unsigned long long*)d;
+    double *dq0 = d + 2, *dp0 = dq0 + 2 * E, *dqf = dp0 + 2 * E, *dpf = dqf + 2 * E, *dqh = dpf + 2 * E, *dph = dqh + hsz;
+    SGP_CUDA(cudaMemsetAsync(dstats, 0, 2 * sizeof(unsigned long long), c.stream));
+    SGP_TRY(upload(c, dx, xtrain, 4 * N)); SGP_TRY(upload(c, da, alpha, 4 * N));
+    SGP_TRY(upload(c, dq0, q0, 2 * E)); SGP_TRY(upload(c, dp0, p0, 2 * E));
+    SGP_TRY(map4_run(c, dx, da, N, hyp3[0], hyp3[1], hyp3[2], dset, E, nm - 1, dq0, dp0, hist ? dqh : nullptr, hist ? dph : nullptr,
+                     out_every, dqf, dpf, dstats));
+    if (hist) { SGP_TRY(download(c, qmap, dqh, hsz)); SGP_TRY(download(c, pmap, dph, hsz)); }
+    if (qfinal) SGP_TRY(download(c, qfinal, dqf, 2 * E));
+    if (pfinal) SGP_TRY(download(c, pfinal, dpf, 2 * E));
+    if (stats) SGP_CUDA(cudaMemcpyAsync(stats, dstats, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    return sync(c);
+}
+
 int sgp_standard_map_iterate(sgp_ctx* ctx, double k, long nm, long N, const double* X0, double* f)
 {
     SGP_TRY(check_ctx(ctx));

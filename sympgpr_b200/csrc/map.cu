@@ -579,6 +579,208 @@ int map_prepare_sympl(Ctx& c, int fam, double per, const double* x, const double
     return ST_OK;
 }
 
+static int init_exp_table();
+
+// ---------------------------------------------------------------------------------------------------------
+// 2-DOF map (BASELINE config 3): prediction side of the 4 x 4-block derivative kernel of dof2.cu.
+// NOT IN THE REFERENCE (it reduces Henon-Heiles to a section map with 2 x 2 blocks); parity unpinned, the oracle
+// twin is oracle.applymap4.  Generating function F(q1, q2, P1, P2), observations [p - P; Q - q] = grad F:
+//     grad_a F(x*) = sig sum_j E_j (at_ja - w_a s_j),   D = x* - x_j,  w_a = D_a / l_a^2,  at = alpha / l^2,
+//     s_j = sum_b D_b at_jb,  E_j = exp(-sum_b D_b w_b / 2)                       (row a of build_k4 times alpha)
+// One map step: solve  r(P) = P - p + grad_q F(q, P) = 0  (2 equations) by Newton with the analytic 2 x 2 Jacobian
+//     d grad_a F / dP_c = -sig sum_j E_j (w_c (at_ja - w_a s_j) + w_a at_jc),   a in q, c in P,
+// started at P = p, then  Q = q + grad_P F(q, P).  Warp = 32 orbits in lock step; the training set (8 doubles per
+// point: x and at) streams through the warp's double buffer in chunks of 32 points, one bulk copy each.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int M4_CHUNK = 32;
+constexpr int M4_F = 8;
+
+__global__ void map4_prep_kernel(const double* __restrict__ x, const double* __restrict__ alpha, long n, long npad, double gq,
+                                 double gP, double* __restrict__ out)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npad) return;
+    double* ch = out + (i / M4_CHUNK) * (long)(M4_F * M4_CHUNK) + (i % M4_CHUNK);
+#pragma unroll
+    for (int c = 0; c < 4; c++) {
+        ch[c * M4_CHUNK] = (i < n) ? x[c * n + i] : 0.0;
+        ch[(4 + c) * M4_CHUNK] = (i < n) ? alpha[c * n + i] * (c < 2 ? gq : gP) : 0.0;     // padding: alpha = 0
+    }
+}
+
+template <bool NEWTON>
+__device__ __forceinline__ void sweep4(Stream& st, const double* __restrict__ set, int nch, int lane, const double (&xs)[4],
+                                       const double (&g)[4], const double* __restrict__ tab, double (&F)[2], double (&J)[4])
+{
+    constexpr uint32_t bytes = M4_F * M4_CHUNK * sizeof(double);
+    F[0] = F[1] = 0.0;
+    J[0] = J[1] = J[2] = J[3] = 0.0;
+    if (lane == 0) {
+        stream_issue(st, st.seq & 1u, set, bytes);
+        stream_issue(st, (st.seq + 1u) & 1u, set + M4_F * M4_CHUNK, bytes);
+    }
+    for (int c = 0; c < nch; c++) {
+        const uint32_t slot = st.seq & 1u, par = (st.seq >> 1) & 1u;
+        mbar_wait(st.bar + slot, par);
+        const double* sm = st.buf + slot * MAP_BUF_DOUBLES;
+#pragma unroll 2
+        for (int j = 0; j < M4_CHUNK; j++) {
+            double D[4], at[4], w[4];
+#pragma unroll
+            for (int b = 0; b < 4; b++) { D[b] = xs[b] - sm[b * M4_CHUNK + j]; at[b] = sm[(4 + b) * M4_CHUNK + j]; w[b] = D[b] * g[b]; }
+            const double e = fma(D[0], w[0], fma(D[1], w[1], fma(D[2], w[2], D[3] * w[3])));
+            const double E = exp_neg_tab(-0.5 * e, tab);
+            const double sj = fma(D[0], at[0], fma(D[1], at[1], fma(D[2], at[2], D[3] * at[3])));
+            if (NEWTON) {
+                const double t0 = fma(-w[0], sj, at[0]), t1 = fma(-w[1], sj, at[1]);
+                F[0] = fma(E, t0, F[0]);
+                F[1] = fma(E, t1, F[1]);
+                J[0] = fma(E, fma(w[2], t0, w[0] * at[2]), J[0]);       // d F_0 / d P_1
+                J[1] = fma(E, fma(w[3], t0, w[0] * at[3]), J[1]);       // d F_0 / d P_2
+                J[2] = fma(E, fma(w[2], t1, w[1] * at[2]), J[2]);       // d F_1 / d P_1
+                J[3] = fma(E, fma(w[3], t1, w[1] * at[3]), J[3]);       // d F_1 / d P_2
+            } else {
+                F[0] = fma(E, fma(-w[2], sj, at[2]), F[0]);
+                F[1] = fma(E, fma(-w[3], sj, at[3]), F[1]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && c + 2 < nch) stream_issue(st, slot, set + (size_t)(c + 2) * M4_F * M4_CHUNK, bytes);
+        st.seq++;
+    }
+    st.passes++;
+}
+
+struct Map4Args {
+    const double* set; int nch;          // chunked training set
+    double g[4], sig;
+    long E, nsteps;
+    const double *q0, *p0;               // (2, E) each
+    double *qout, *pout;                 // history (rows, 2, E) or nullptr
+    long out_every;
+    double *qfinal, *pfinal;             // (2, E)
+    unsigned long long* stats;           // [0] Newton evaluations, [1] exits without convergence
+};
+
+__global__ void __launch_bounds__(MAP_THREADS, 3) map4_kernel(Map4Args a)
+{
+    __shared__ __align__(16) double s_buf[MAP_WARPS][2 * MAP_BUF_DOUBLES];
+    __shared__ unsigned long long s_bar[MAP_WARPS][2];
+    __shared__ double s_tab_all[64 * 32];
+    for (int i = threadIdx.x; i < 64 * 32; i += MAP_THREADS) s_tab_all[i] = c_exp2_tab[i >> 5];
+    const double* s_tab = s_tab_all + (threadIdx.x & 31);
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    Stream st;
+    st.buf = s_buf[warp]; st.bar = s_bar[warp]; st.seq = 0; st.passes = 0u; st.primed = nullptr;
+    if (lane == 0) { mbar_init(st.bar + 0, 1); mbar_init(st.bar + 1, 1); mbar_fence_init(); }
+    __syncwarp();
+    const double g[4] = {a.g[0], a.g[1], a.g[2], a.g[3]};
+    unsigned long long evals = 0ull;
+    unsigned int fails = 0u;
+    const long nbatches = (a.E + 31) / 32;
+    const long nwarps = (long)gridDim.x * MAP_WARPS;
+    for (long batch = (long)blockIdx.x * MAP_WARPS + warp; batch < nbatches; batch += nwarps) {
+        const long k = batch * 32 + lane;
+        const bool mine = k < a.E;
+        double q[2] = {0.0, 0.0}, p[2] = {0.0, 0.0};
+        if (mine) { q[0] = a.q0[k]; q[1] = a.q0[a.E + k]; p[0] = a.p0[k]; p[1] = a.p0[a.E + k]; }
+        if (mine && a.out_every > 0) {
+            a.qout[k] = q[0]; a.qout[a.E + k] = q[1]; a.pout[k] = p[0]; a.pout[a.E + k] = p[1];
+        }
+        for (long step = 1; step <= a.nsteps; step++) {
+            bool alive = mine && q[0] == q[0] && q[1] == q[1] && p[0] == p[0] && p[1] == p[1];
+            double P[2] = {p[0], p[1]};
+            bool done = !alive;
+            int it = 0;
+            while (__any_sync(0xffffffffu, !done)) {
+                const double xs[4] = {alive ? q[0] : 0.0, alive ? q[1] : 0.0, done ? 0.0 : P[0], done ? 0.0 : P[1]};
+                double F[2], J[4];
+                sweep4<true>(st, a.set, a.nch, lane, xs, g, s_tab, F, J);
+                if (!done) {
+                    evals++;
+                    it++;
+                    const double r0 = P[0] - p[0] + a.sig * F[0], r1 = P[1] - p[1] + a.sig * F[1];
+                    const double j00 = 1.0 - a.sig * J[0], j01 = -a.sig * J[1], j10 = -a.sig * J[2], j11 = 1.0 - a.sig * J[3];
+                    const double det = j00 * j11 - j01 * j10;
+                    const double d0 = (j11 * r0 - j01 * r1) / det, d1 = (j00 * r1 - j10 * r0) / det;
+                    if (!(fabs(d0) <= DBL_MAX) || !(fabs(d1) <= DBL_MAX)) {     // singular Jacobian / non-finite residual
+                        P[0] = P[1] = nan(""); done = true; fails++;
+                    } else {
+                        P[0] -= d0; P[1] -= d1;
+                        const double ad = fmax(fabs(d0), fabs(d1));
+                        if (ad <= 1e-9 * fmax(fmax(fabs(P[0]), fabs(P[1])), 1.0)) done = true;      // next error O(ad^2)
+                        else if (it >= 40) { done = true; fails++; }
+                    }
+                }
+            }
+            alive = alive && P[0] == P[0] && P[1] == P[1];
+            {
+                const double xs[4] = {alive ? q[0] : 0.0, alive ? q[1] : 0.0, alive ? P[0] : 0.0, alive ? P[1] : 0.0};
+                double F[2], J[4];
+                sweep4<false>(st, a.set, a.nch, lane, xs, g, s_tab, F, J);
+                if (alive) {
+                    evals++;
+                    q[0] += a.sig * F[0]; q[1] += a.sig * F[1];
+                    p[0] = P[0]; p[1] = P[1];
+                } else if (mine) {
+                    q[0] = q[1] = p[0] = p[1] = nan("");
+                }
+            }
+            if (mine && a.out_every > 0 && (step % a.out_every) == 0) {
+                const long row = step / a.out_every;
+                double* qo = a.qout + row * 2 * a.E;
+                double* po = a.pout + row * 2 * a.E;
+                qo[k] = q[0]; qo[a.E + k] = q[1]; po[k] = p[0]; po[a.E + k] = p[1];
+            }
+        }
+        if (mine) { a.qfinal[k] = q[0]; a.qfinal[a.E + k] = q[1]; a.pfinal[k] = p[0]; a.pfinal[a.E + k] = p[1]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        evals += __shfl_xor_sync(0xffffffffu, evals, o);
+        fails += __shfl_xor_sync(0xffffffffu, fails, o);
+    }
+    if (lane == 0) {
+        if (evals) atomicAdd(a.stats + 0, evals);
+        if (fails) atomicAdd(a.stats + 1, (unsigned long long)fails);
+    }
+}
+
+long map4_chunks(long n)
+{
+    long c = (n + M4_CHUNK - 1) / M4_CHUNK;
+    return c < 2 ? 2 : c;
+}
+
+// x (4, n), alpha (4, n) device arrays -> chunked set (map4_chunks(n) * 8 * 32 doubles) -> nm - 1 steps of E orbits
+int map4_run(Ctx& c, const double* d_x, const double* d_alpha, long n, double lq, double lP, double sig, double* d_set, long E,
+             long nsteps, const double* d_q0, const double* d_p0, double* d_qhist, double* d_phist, long out_every, double* d_qfinal,
+             double* d_pfinal, unsigned long long* d_stats)
+{
+    SGP_TRY(init_exp_table());
+    const long nch = map4_chunks(n), npad = nch * M4_CHUNK;
+    const double gq = 1.0 / (lq * lq), gP = 1.0 / (lP * lP);
+    map4_prep_kernel<<<(unsigned)((npad + 255) / 256), 256, 0, c.stream>>>(d_x, d_alpha, n, npad, gq, gP, d_set);
+    SGP_CUDA(cudaGetLastError());
+    count_launch();
+    if (E <= 0) return ST_OK;
+    Map4Args a;
+    a.set = d_set; a.nch = (int)nch;
+    a.g[0] = a.g[1] = gq; a.g[2] = a.g[3] = gP; a.sig = sig;
+    a.E = E; a.nsteps = nsteps; a.q0 = d_q0; a.p0 = d_p0;
+    a.qout = d_qhist; a.pout = d_phist; a.out_every = (d_qhist && d_phist) ? out_every : 0;
+    a.qfinal = d_qfinal; a.pfinal = d_pfinal; a.stats = d_stats;
+    const long nbatches = (E + 31) / 32;
+    long blocks = (nbatches + MAP_WARPS - 1) / MAP_WARPS;
+    const long cap = (long)(c.sm_count > 0 ? c.sm_count : 148) * 3;
+    if (blocks > cap) blocks = cap;
+    map4_kernel<<<(unsigned)blocks, MAP_THREADS, 0, c.stream>>>(a);
+    SGP_CUDA(cudaGetLastError());
+    count_launch();
+    return ST_OK;
+}
+
 // StandardMapIterate python/04_standard_map/main.py:27-39 (training / reference orbits of the standard map, no wrap):
 // f (2, N, nm) C order, f[:, i, 0] = X0[:, i], J' = J + k sin(th), th' = th + J'.  One thread per orbit.
 __global__ void standard_map_iterate_kernel(double kk, long nm, long N, const double* __restrict__ X0, double* __restrict__ f)

@@ -71,6 +71,12 @@ int map_prepare_guess(Ctx& c, int fam, double per, const double* x, const double
 int map_prepare_sympl(Ctx& c, int fam, double per, const double* x, const double* y, const double* alpha, long n, double* tch);
 // a.ticket / a.slots / a.progress / a.slice_steps are filled in by map_launch from `sched` (map_sched_bytes(E) bytes)
 int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched);
+// 2-DOF map (map.cu, "2-DOF map"): chunks the set needs, and the launch on device arrays (x, alpha: (4, n); q0, p0, finals: (2, E);
+// histories (rows, 2, E) or nullptr; d_set: map4_chunks(n) * 256 doubles of scratch)
+long map4_chunks(long n);
+int map4_run(Ctx& c, const double* d_x, const double* d_alpha, long n, double lq, double lP, double sig, double* d_set, long E,
+             long nsteps, const double* d_q0, const double* d_p0, double* d_qhist, double* d_phist, long out_every, double* d_qfinal,
+             double* d_pfinal, unsigned long long* d_stats);
 // StandardMapIterate (python/04_standard_map/main.py:32-39) on device arrays: X0 (2, N), f (2, N, nm)
 int standard_map_iterate(Ctx& c, double kk, long nm, long N, const double* d_X0, double* d_f);
 

@@ -686,3 +686,99 @@ def test_standard_map_iterate_matches_reference_loop(api, O):
     assert np.allclose(f[:, :, 1], fr[:, :, 1], rtol=1e-15, atol=1e-15)
     with pytest.raises(ValueError):
         api.StandardMapIterate(k, nm, N, X0.T)
+
+
+def test_learned_map_is_symplectic_at_full_ensemble_size(api, O):
+    """Size-independent property at BASELINE's map size (Nt = 4096 training pairs, 1e5 orbits): a map defined through a
+    mixed-variable generating function, P = p - F_q(q, P), Q = q + F_P(q, P), is symplectic whatever F is -- the
+    Jacobian of (q, p) -> (Q, P) has determinant 1 (the reason the reference solves the implicit equation at all).
+    Checked by central differences through the whole GPU path (guess GP, root solve, dQ sweep): any error in the
+    kernel sums, the analytic derivative or the root accuracy shows up as det != 1."""
+    Nt, E, eps = 4096, 100000, 1e-4
+    d = O.standard_map_training(Nt)
+    hyp = O.timing_hyp(Nt, d["sig"], 1e-8)
+    hypp = O.timing_hyp(Nt, d["sigp"], 1e-8)
+    hyp[:2] *= 2.0
+    hypp[:2] *= 2.0
+    f = api.fit(hyp, d["xtrain"], d["ztrain"], 2 * Nt)
+    fp = api.fit(hypp, d["xtrainp"], d["ztrainp"], Nt, reg=True)
+    q0 = 0.5 + 5.0 * O.halton(E, 5)
+    p0 = 1.0 + 4.0 * O.halton(E, 7)
+    Q, P = [], []
+    for dq, dp in ((eps, 0.0), (-eps, 0.0), (0.0, eps), (0.0, -eps)):
+        out = api.applymap_henon(2, E, hyp[:3], hypp[:3], q0 + dq, p0 + dp, d["xtrainp"], None, None, d["xtrain"], None, None,
+                                 family="product", solver="newton_delta", alphap=fp["alpha"], alpha=f["alpha"], out_every=0,
+                                 return_stats=True)
+        Q.append(out[0]); P.append(out[1])
+        assert out[-1]["unconverged"] <= 1e-4 * E
+    Qq, Qp = (Q[0] - Q[1]) / (2 * eps), (Q[2] - Q[3]) / (2 * eps)
+    Pq, Pp = (P[0] - P[1]) / (2 * eps), (P[2] - P[3]) / (2 * eps)
+    det = Qq * Pp - Qp * Pq
+    err = np.abs(det - 1.0)
+    # accuracy of the check: the residual of this model bottoms out near 4e-12 (rounding in the sums), so the difference
+    # quotients carry ~4e-12 / eps of noise (the CPU oracle gives 7e-9 median); a wrong term in any sweep shows up at
+    # the 1e-2 .. 1 level
+    assert np.isfinite(det).mean() > 0.999
+    assert np.nanmedian(err) < 1e-6, np.nanmedian(err)
+    assert np.nanquantile(err, 0.99) < 1e-4, np.nanquantile(err, 0.99)
+    # and the learned map is the standard map it was trained on (K = 0.9), to the accuracy of the regression
+    Pc = 0.5 * (P[2] + P[3])
+    assert np.nanmedian(np.abs(Pc - (p0 + 0.9 * np.sin(q0)))) < 1e-4
+
+
+# ------------------------------------------------------------------- 2-DOF map (BASELINE config 3, not in the reference)
+def _dof2_model(api, O, N):
+    x, z = O.henon_like_training(N)
+    hyp = np.array([0.35, 0.4, 2 * np.max(np.abs(z))**2, 1e-8])
+    f = api.fit(hyp, x, z, 4 * N, reg=4)
+    return x, z, hyp, f["alpha"]
+
+
+def test_dof2_map_matches_oracle(api, O):
+    """map4_kernel (2 x 2 Newton with the analytic Jacobian) against oracle.applymap4, whose grad F is the 4 x 4-block
+    matrix of build_k4 times alpha and whose Jacobian is taken by differences: same roots, same orbits."""
+    N = 150
+    x, z, hyp, alpha = _dof2_model(api, O, N)
+    import scipy.linalg
+    Ky = O.build_k4(x, x, hyp[:3]) + hyp[3] * np.eye(4 * N)
+    alpha_ref = scipy.linalg.cho_solve(scipy.linalg.cho_factor(Ky, lower=True), z)
+    assert np.allclose(alpha, alpha_ref, rtol=1e-6, atol=1e-6 * np.abs(alpha_ref).max())
+    E, nm = 45, 9
+    q0 = np.vstack((-0.25 + 0.5 * O.halton(E, 2, start=50), -0.25 + 0.5 * O.halton(E, 3, start=50)))
+    p0 = np.vstack((-0.25 + 0.5 * O.halton(E, 5, start=50), -0.25 + 0.5 * O.halton(E, 7, start=50)))
+    qr, pr = O.applymap4(nm, q0, p0, hyp[:3], x, alpha)
+    q, p, st = api.applymap4(nm, E, hyp[:3], q0, p0, x, alpha, return_stats=True)
+    assert q.shape == (nm, 2, E)
+    assert np.array_equal(q[0], q0) and np.array_equal(p[0], p0)
+    assert np.abs(q - qr).max() < 1e-9 and np.abs(p - pr).max() < 1e-9, (np.abs(q - qr).max(), np.abs(p - pr).max())
+    assert st["unconverged"] == 0 and st["evaluations"] >= 3 * E * (nm - 1)
+    assert np.array_equal(st["qfinal"], q[-1]) and np.array_equal(st["pfinal"], p[-1])
+    qs, ps = api.applymap4(nm, E, hyp[:3], q0, p0, x, alpha, out_every=4)
+    assert qs.shape == (3, 2, E) and np.array_equal(qs[2], q[8]) and np.array_equal(ps[1], p[4])
+    with pytest.raises(ValueError):
+        api.applymap4(nm, E, hyp[:3], q0.T, p0, x, alpha)
+
+
+def test_dof2_map_is_symplectic_and_follows_the_training_map(api, O):
+    """1e5 orbits (BASELINE config 3's ensemble size): M^T Omega M = Omega for the Jacobian M of one learned step, and the
+    step agrees with the kick-drift map the model was trained on."""
+    N, E, eps = 400, 100000, 1e-5
+    x, z, hyp, alpha = _dof2_model(api, O, N)
+    q0 = np.vstack((-0.3 + 0.6 * O.halton(E, 2, start=7), -0.3 + 0.6 * O.halton(E, 3, start=7)))
+    p0 = np.vstack((-0.3 + 0.6 * O.halton(E, 5, start=7), -0.3 + 0.6 * O.halton(E, 7, start=7)))
+    M = np.zeros((4, 4, E))
+    for c in range(4):
+        dq = np.zeros((2, 1)); dp = np.zeros((2, 1))
+        (dq if c < 2 else dp)[c % 2] = eps
+        qa, pa = api.applymap4(2, E, hyp[:3], q0 + dq, p0 + dp, x, alpha, out_every=0)
+        qb, pb = api.applymap4(2, E, hyp[:3], q0 - dq, p0 - dp, x, alpha, out_every=0)
+        M[:, c] = np.vstack((qa - qb, pa - pb)) / (2 * eps)
+    Om = np.block([[np.zeros((2, 2)), np.eye(2)], [-np.eye(2), np.zeros((2, 2))]])
+    R = np.einsum("ijk,il,lmk->jmk", M, Om, M) - Om[:, :, None]
+    err = np.abs(R).max(axis=(0, 1))
+    assert np.isfinite(err).all()
+    assert np.median(err) < 1e-6 and err.max() < 1e-4, (np.median(err), err.max())    # difference quotients: ~1e-12 / eps of noise
+    qf, pf = api.applymap4(2, E, hyp[:3], q0, p0, x, alpha, out_every=0)
+    dt = 0.3
+    P = np.vstack((p0[0] - dt * (q0[0] + 2 * q0[0] * q0[1]), p0[1] - dt * (q0[1] + q0[0]**2 - q0[1]**2)))
+    assert np.abs(pf - P).max() < 1e-3 and np.abs(qf - (q0 + dt * P)).max() < 1e-3

@@ -299,3 +299,35 @@ def test_quality_and_generator_restatements():
     Ht = O.energy_tok(np.array([[0.5]]), np.array([[2.0]]), 0.0, 2, 0.0)
     r = O.compute_r(np.array([2.0e-2, 0.5, 0.0]), 0.3)
     assert np.isclose(Ht[0, 0], r**2 / 2 - r**4)
+
+
+def test_dof2_map_oracle_learns_the_map_and_is_symplectic():
+    """oracle.applymap4 (twin of the 2-DOF map kernel, no reference code): the learned map reproduces the kick-drift
+    map it was trained on, and its Jacobian M satisfies M^T Omega M = Omega (generating-function maps are symplectic)."""
+    import scipy.linalg
+    from oracle import oracle as O
+    N = 150
+    x, z = O.henon_like_training(N)
+    hyp = np.array([0.35, 0.4, 2 * np.max(np.abs(z))**2, 1e-8])
+    K = O.build_k4(x, x, hyp[:3]) + hyp[3] * np.eye(4 * N)
+    alpha = scipy.linalg.cho_solve(scipy.linalg.cho_factor(K, lower=True), z)
+    E = 6
+    q0 = np.vstack((-0.25 + 0.5 * O.halton(E, 2, start=50), -0.25 + 0.5 * O.halton(E, 3, start=50)))
+    p0 = np.vstack((-0.25 + 0.5 * O.halton(E, 5, start=50), -0.25 + 0.5 * O.halton(E, 7, start=50)))
+    qm, pm = O.applymap4(2, q0, p0, hyp[:3], x, alpha)
+    dt = 0.3
+    P1 = p0[0] - dt * (q0[0] + 2 * q0[0] * q0[1]); P2 = p0[1] - dt * (q0[1] + q0[0]**2 - q0[1]**2)
+    assert np.abs(pm[1] - np.vstack((P1, P2))).max() < 2e-3
+    assert np.abs(qm[1] - (q0 + dt * np.vstack((P1, P2)))).max() < 2e-3
+    # symplecticity of the learned map by central differences, state order (q1, q2, p1, p2)
+    eps = 1e-5
+    M = np.zeros((4, 4, E))
+    for c in range(4):
+        dq = np.zeros((2, E)); dp = np.zeros((2, E))
+        (dq if c < 2 else dp)[c % 2] = eps
+        qa, pa = O.applymap4(2, q0 + dq, p0 + dp, hyp[:3], x, alpha)
+        qb, pb = O.applymap4(2, q0 - dq, p0 - dp, hyp[:3], x, alpha)
+        M[:, c] = np.vstack((qa[1] - qb[1], pa[1] - pb[1])) / (2 * eps)
+    Om = np.block([[np.zeros((2, 2)), np.eye(2)], [-np.eye(2), np.zeros((2, 2))]])
+    for k in range(E):
+        assert np.abs(M[:, :, k].T @ Om @ M[:, :, k] - Om).max() < 1e-6

@@ -10,8 +10,8 @@
 //     D_c = u_c(x_i) - u_c(x0_j)
 // with observations z = [p1 - P1; p2 - P2; Q1 - q1; Q2 - q2].  Parity is unpinned (no reference code): the oracle
 // twin (oracle/oracle.py build_k4 / nll_grad4) is validated by finite differences and by its 2 x 2 sub-blocks
-// reproducing the reference's SE x SE matrix.  Only the training side exists (fill, NLL, gradient); a 2-DOF map
-// kernel (2 x 2 Newton) is future work.
+// reproducing the reference's SE x SE matrix.  This file is the training side (fill, NLL, gradient); the prediction
+// side (2 x 2 Newton map kernel) is map4_kernel in map.cu.
 #include "dof2.cuh"
 
 namespace sgp {

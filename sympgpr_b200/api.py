@@ -11,8 +11,12 @@ tests read the same; everything numerical happens in libsympgpr_b200.so on the G
   applymap_standard                  python/04_standard_map/func.py:218-254
   applymap_tok                       python/05_tokamak/SympGPR/func.py:182-211
 
-Additive (not in the reference): fit(), Model / Model.applymap() for ensembles that stay on the
-device, and the `family` / `per` / `solver` keyword arguments.
+Additive (not in the reference): fit(); the `family` / `per` / `solver` keyword arguments ("newton_delta": Newton
+started at p + guess for guess GPs trained on P - p); applymap_quality() / quality() (the reference's `quality`
+metrics accumulated inside the map kernel, no histories); StandardMapIterate() on the device; the 2-DOF 4x4-block
+kernel (build_k4, nll_chol4, nll_grad4, fit(reg=4), applymap4); explicit and split maps (applymap_expl,
+applymap_tok_split).  Ensembles that stay on the device go through the C ABI's sgp_model_* entry points with device
+pointers (bench.py, ensemble.py hold them as torch tensors).
 """
 import ctypes
 

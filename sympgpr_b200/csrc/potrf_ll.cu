@@ -227,7 +227,7 @@ constexpr int DB = 32;
 //            d = row_j[0]; l = row[0] / sqrt(d); row[c-1] = row[c] - l * L(j+c, j)
 //   inverse: lane r accumulates row r of X = L^-1 in x[0..31] (x = e_r at the start);
 //            step k: lane k scales its finished row by 1/l_kk; lanes r > k: x[c] -= L(r,k) X(k,c)
-__device__ __noinline__ void warp_potrf32_reg(double* S, int k0, double* xd, int* info, int col0)
+__device__ __noinline__ void warp_factor32(double* S, int k0, double* xd, int* info, int col0)
 {
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
@@ -262,6 +262,17 @@ __device__ __noinline__ void warp_potrf32_reg(double* S, int k0, double* xd, int
     if (bad != 0 && lane == 0) atomicCAS(info, 0, col0 + k0 + bad);
     xd[k0 + lane] = myinv;
     __syncwarp();
+}
+
+// warp 0 only, after warp_factor32: inverse of the factored diagonal block (reads L and xd from shared memory, writes
+// X^T into the block's strict upper triangle).  Runs while the other consumer warps do the panel and the trailing update.
+__device__ __noinline__ void warp_invert32(double* S, int k0, const double* xd)
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned FULL = 0xffffffffu;
+    double* Sr = S + (k0 + lane) * LL_LD + k0;
+    const double myinv = xd[k0 + lane];
+    double row[DB];
 #pragma unroll
     for (int c = 0; c < DB; c++) row[c] = (c == lane) ? 1.0 : 0.0;
     double lk = Sr[0];
@@ -294,44 +305,43 @@ __device__ __noinline__ void warp_potrf32_reg(double* S, int k0, double* xd, int
 __device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, double* scratch, int tid, int* info, int col0, double* logout,
                                         unsigned long long* stamp)
 {
+    // per block column kb:  warp 0 factors the 32 x 32 diagonal block;  then, at the same time,
+    //   warp 0    : inverse of that block (needed only for the inverse of the whole tile, below)
+    //   warps 1-7 : panel L(i, kb) = A(i, kb) L_kk^-T by forward substitution (one thread per row, in place), then the
+    //               trailing update A(i, c) -= L(i, kb) L(c, kb)^T
+    // so the block inverse is off the critical path of the tile (it took as long as the block factorisation).
+    const int wtid = tid - 32;                               // index among the 224 threads of warps 1-7
+    constexpr int NW = LL_CONSUMERS - 32;
     for (int kb = 0; kb < TILE / DB; kb++) {
         const int k0 = kb * DB, R0 = k0 + DB, nrows = TILE - R0;
         unsigned long long tw0 = 0ull;
         if (stamp && tid == 0) tw0 = globaltimer();
         __syncwarp();                                        // (trace only diverges lane 0: re-converge, or the shuffles take their slow path)
-        if (tid < 32) warp_potrf32_reg(S, k0, xd, info, col0);
+        if (tid < 32) warp_factor32(S, k0, xd, info, col0);
         if (stamp && tid == 0) stamp[3] += globaltimer() - tw0;      // trace: time in the warp-level block factorisations
         consumer_bar();
-        if (nrows > 0) {
-            // panel: L(i, k0+c) = sum_{k<=c} A(i, k0+k) X_kk(c, k); results held back until every thread has read A
-            double out[12];
-#pragma unroll
-            for (int u = 0; u < 12; u++) {
-                const int idx = tid + u * LL_CONSUMERS;
-                out[u] = 0.0;
-                if (idx < nrows * DB) {
-                    const int i = R0 + idx % nrows, c = idx / nrows;
-                    const double* Ai = S + i * LL_LD + k0;
-                    double s0 = Ai[c] * xd[k0 + c], s1 = 0.0;
+        if (tid < 32) {
+            warp_invert32(S, k0, xd);
+        } else if (nrows > 0) {
+            if (wtid < nrows) {
+                // row i of the panel: l_c = (a_c - sum_{k<c} l_k L_kk(c,k)) / L_kk(c,c), in place (the row is this thread's own)
+                double* Ai = S + (R0 + wtid) * LL_LD + k0;
+                for (int c = 0; c < DB; c++) {
+                    const double* Lc = S + (k0 + c) * LL_LD + k0;
+                    double s0 = Ai[c], s1 = 0.0;
                     int k = 0;
                     for (; k + 1 < c; k += 2) {
-                        s0 = fma(Ai[k], S[(k0 + k) * LL_LD + k0 + c], s0);
-                        s1 = fma(Ai[k + 1], S[(k0 + k + 1) * LL_LD + k0 + c], s1);
+                        s0 = fma(-Ai[k], Lc[k], s0);
+                        s1 = fma(-Ai[k + 1], Lc[k + 1], s1);
                     }
-                    if (k < c) s0 = fma(Ai[k], S[(k0 + k) * LL_LD + k0 + c], s0);
-                    out[u] = s0 + s1;
+                    if (k < c) s0 = fma(-Ai[k], Lc[k], s0);
+                    Ai[c] = (s0 + s1) * xd[k0 + c];
                 }
             }
-            consumer_bar();
-#pragma unroll
-            for (int u = 0; u < 12; u++) {
-                const int idx = tid + u * LL_CONSUMERS;
-                if (idx < nrows * DB) S[(R0 + idx % nrows) * LL_LD + k0 + idx / nrows] = out[u];
-            }
-            consumer_bar();
+            asm volatile("bar.sync 2, %0;\n" ::"n"(NW) : "memory");        // warps 1-7: the panel is complete
             // trailing update: A(i, c) -= sum_k L(i, k0+k) L(c, k0+k) for R0 <= c <= i; 1 row x 4 columns per item
             const int ncg = nrows / 4;
-            for (int idx = tid; idx < nrows * ncg; idx += LL_CONSUMERS) {
+            for (int idx = wtid; idx < nrows * ncg; idx += NW) {
                 const int i = R0 + idx % nrows, c0 = R0 + 4 * (idx / nrows);
                 if (c0 > i) continue;
                 const double* Li = S + i * LL_LD + k0;
@@ -346,14 +356,14 @@ __device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, doub
                     s3 = fma(l, Lc[3 * LL_LD + k], s3);
                 }
                 double* Ai = S + i * LL_LD + c0;
-                // (entries above the diagonal belong to the X^T storage of finished blocks: only c <= i is written)
+                // (entries above the diagonal belong to the X^T storage of the diagonal blocks: only c <= i is written)
                 Ai[0] -= s0;
                 if (c0 + 1 <= i) Ai[1] -= s1;
                 if (c0 + 2 <= i) Ai[2] -= s2;
                 if (c0 + 3 <= i) Ai[3] -= s3;
             }
-            consumer_bar();
         }
+        consumer_bar();
     }
     // sum(log diag L) = -sum(log xd): one log per thread, fixed-order reduction
     if (tid < TILE) scratch[tid] = -log(xd[tid]);

@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--cpu-sample", type=int, default=2048, help="training pairs of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-map", action="store_true")
+    ap.add_argument("--big-orbits", type=int, default=10_000_000,
+                    help="TOTAL orbits of the 10^7-orbit prediction leg (BASELINE config 5), split over the GPUs; 0 skips it")
+    ap.add_argument("--big-steps", type=int, default=16, help="map steps of the 10^7-orbit leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the small-size NLL+gradient sweep (N = 2048..8192)")
     return ap.parse_args()
 
@@ -383,6 +386,19 @@ def main():
         t_mwall1 = time.time()
         t_map_local = m0.elapsed_time(m1) * 1e-3
         t_map = max_over_ranks(t_map_local)
+        # per-rank evidence for the scaling figure: time, lane-level evaluations, unconverged steps and the median SM clock
+        # of every rank's own GPU during its map run (a slow rank is either a slow GPU or a slow shard)
+        ck = sampler.summary(t_mwall0, t_mwall1)
+        mine_r = torch.tensor([t_map_local, float(stats[0].item()), float(stats[1].item()), ck["sm_mhz"] or 0.0,
+                               1.0 if ck["reasons"] else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            allr = [torch.zeros_like(mine_r) for _ in range(world)]
+            dist.all_gather(allr, mine_r)
+        else:
+            allr = [mine_r]
+        per_rank = {"seconds": [round(float(r[0]), 3) for r in allr], "evaluations": [int(r[1]) for r in allr],
+                    "unconverged": [int(r[2]) for r in allr], "sm_mhz": [float(r[3]) for r in allr],
+                    "throttle_reasons_seen": [bool(r[4] > 0) for r in allr]}
         st = stats.clone()
         npass = ctypes.c_ulonglong(0)
         _lib.check(L.sgp_map_last_passes(ctx.handle, ctypes.byref(npass)), "sgp_map_last_passes")
@@ -449,8 +465,48 @@ def main():
                     "newton_refstart_value": float(E) * world * hsteps / t_map_n,
                     "follows_exact_map_after_hsteps": {"within_1e-2": int(agree[0].item()), "finite": int(agree[1].item())},
                     "unconverged": int(st[1].item()),
-                    "clocks": sampler.summary(t_mwall0, t_mwall1), "rank0_s": t_map_local,
+                    "clocks": sampler.summary(t_mwall0, t_mwall1), "rank0_s": t_map_local, "per_rank": per_rank,
                     "checksum": [float(cks[0].item()), float(cks[1].item())]}
+        # ---- BASELINE config 5: ONE ensemble of 10^7 orbits split over the GPUs (strong scaling), a short step loop ----
+        if a.big_orbits > 0:
+            Eb_tot = int(a.big_orbits)
+            qb_all, pb_all = W.ensemble(Eb_tot)
+            qb = torch.from_numpy(qb_all[rank::world].copy()).to(dev)
+            pb = torch.from_numpy(pb_all[rank::world].copy()).to(dev)
+            del qb_all, pb_all
+            Eb = int(qb.numel())
+            qbf, pbf = torch.empty_like(qb), torch.empty_like(pb)
+
+            def big_run(steps):
+                _lib.check(L.sgp_model_applymap_dev(ctx.handle, model, 2, MAP_SOLVER, steps, Eb, qb.data_ptr(), pb.data_ptr(),
+                                                    qbf.data_ptr(), pbf.data_ptr(), None, None, 0, stats.data_ptr()),
+                           "sgp_model_applymap_dev")
+            big_run(1)
+            sync_all()
+            stats.zero_()
+            b0, b1 = ev(), ev()
+            b0.record(stream); big_run(a.big_steps); b1.record(stream)
+            sync_all()
+            t_big_local = b0.elapsed_time(b1) * 1e-3
+            t_big = max_over_ranks(t_big_local)
+            stb = stats.clone()
+            tl = torch.tensor([t_big_local], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(stb, op=dist.ReduceOp.SUM)
+                tls = [torch.zeros_like(tl) for _ in range(world)]
+                dist.all_gather(tls, tl)
+            else:
+                tls = [tl]
+            map_info["big"] = {"metric": "orbit_map_steps_per_s", "value": float(Eb_tot) * a.big_steps / t_big,
+                               "unit": "orbit-steps/s", "scaling": "strong", "orbits_total": Eb_tot, "steps": a.big_steps,
+                               "solver": MAP_SOLVER_NAME, "n_train": Nt,
+                               "sweeps_per_orbit_step": 1 + int(stb[0].item()) / (float(Eb_tot) * a.big_steps),
+                               "unconverged": int(stb[1].item()), "per_rank_s": [round(float(t[0]), 3) for t in tls],
+                               "note": "BASELINE config 5: one 10^7-orbit ensemble split over the GPUs (interleaved shards, model "
+                                       "replicated, no collective on the data path); the 1e5-orbit x 1000-step leg above is "
+                                       "config 4 replicated per GPU (weak scaling), whose time is set by the slowest 32-orbit "
+                                       "batch of a shard"}
+            del qb, pb, qbf, pbf
         L.sgp_model_destroy(model)
 
     sampler.stop()

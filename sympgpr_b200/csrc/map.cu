@@ -33,6 +33,8 @@
 // on scheduling.
 #include "map.cuh"
 
+#include <cstdlib>
+
 #include "hybrd.cuh"
 #include "mbar.cuh"
 
@@ -409,7 +411,7 @@ map_kernel(MapArgs a)
                 Newton1 sv;
                 // the reference starts at the guess GP's prediction as it is (sympgpr.f90:104-107) even where that GP was
                 // trained on P - p (scripts 03/04/05); start_delta adds p, which is the consistent start for such a model
-                sv.start(alive ? (a.start_delta ? p + pg : pg) : 0.0);
+                sv.start(alive ? (a.start_delta ? p + pg : pg) : 0.0, a.newton_max_nb, a.newton_max_b);
                 if (!alive) sv.phase = 3;
                 while (__any_sync(0xffffffffu, !sv.done())) {
                     const bool run = !sv.done();
@@ -836,6 +838,13 @@ int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched)
     if (a.nmodels > 1) ss = (ss + a.nmodels - 1) / a.nmodels * a.nmodels;      // work items start at a turn boundary of a split map
     a.slice_steps = ss;
     a.start_delta = (solver == 3) ? 1 : 0;
+    a.newton_max_nb = 30; a.newton_max_b = 60;
+    {   // measurement overrides
+        static const char* e_nb = getenv("SGP_NEWTON_MAX_NB");
+        static const char* e_b = getenv("SGP_NEWTON_MAX_B");
+        if (e_nb && atoi(e_nb) > 0) a.newton_max_nb = atoi(e_nb);
+        if (e_b && atoi(e_b) > 0) a.newton_max_b = atoi(e_b);
+    }
     const long warps_needed = nbatches;
     long blocks = (warps_needed + MAP_WARPS - 1) / MAP_WARPS;
     const long cap = (long)(c.sm_count > 0 ? c.sm_count : 148) * MAP_BLOCKS_PER_SM;

@@ -39,6 +39,7 @@ struct MapArgs {
     int nmodels;
     int kind;
     long E, nsteps;
+    int newton_max_nb, newton_max_b; // Newton give-up limits (evaluations) without / with a bracket
     int start_delta;                 // 1: the guess GP predicts P - p (SGP_SOLVER_NEWTON_DELTA): the solver starts at p + guess
     const double *q0, *p0;
     // history: row r (= step / out_every) of orbit k at [r*step_stride + k*orbit_stride]; out_every = 0: none

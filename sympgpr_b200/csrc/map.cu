@@ -42,6 +42,7 @@ namespace sgp {
 
 constexpr int MAP_THREADS = 128;
 constexpr int MAP_WARPS = MAP_THREADS / 32;
+constexpr int MAP_COOP_MAX = 8;                    // up to this many unconverged lanes are served by cooperative passes
 constexpr int MAP_BLOCKS_PER_SM = 4;               // 16 warps / SM, <= 128 registers per thread
 constexpr int MAP_BUF_DOUBLES = MAP_TF * MAP_CHUNK; // one buffer holds a chunk of either set
 constexpr double TWO_PI = 6.283185307179586;
@@ -183,7 +184,11 @@ __device__ __forceinline__ void point_eval(double au, double av, double ay, doub
 // One sweep of the warp over a whole training set (nch chunks of NF fields); the first two chunks are
 // already in flight.  While chunk c is evaluated, chunk c+2 is fetched -- for the last two chunks that
 // is chunk 0/1 of the set the NEXT sweep will read (nxt, nxf fields).
-template <int FAM, int MODE>
+// COOP = true: ONE query point (the caller broadcasts a straggler's b to all lanes) and the 32 lanes share the
+// training set -- lane l evaluates points 2l, 2l+1 of every 64-point chunk -- then the partial sums are added across
+// the warp in a fixed order.  1/32 of the arithmetic of a full pass: this is how the last few unconverged lanes of a
+// step are served, instead of a full pass in which 31 lanes idle (see the solver loops in map_kernel).
+template <int FAM, int MODE, bool COOP = false>
 __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set, int nch, const double* __restrict__ nxt, int nxf,
                                       int lane, const Pt& b, const HypC& h, const double* __restrict__ tab, bool active,
                                       double& o0, double& o1)
@@ -192,15 +197,15 @@ __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set
     Acc z;
     z.a0 = z.a1 = z.b0 = z.b1 = z.c0 = z.c1 = z.d0 = z.d1 = 0.0;
     const double nhx = -h.hx, nhy = -h.hy, lx2 = h.lx2, ly2 = h.ly2;
-    const bool any = __any_sync(0xffffffffu, active);
-    st.passes++;
+    const bool any = COOP ? true : __any_sync(0xffffffffu, active);
+    if (!COOP) st.passes++;
     for (int c = 0; c < nch; c++) {
         const uint32_t slot = st.seq & 1u, par = (st.seq >> 1) & 1u;
         mbar_wait(st.bar + slot, par);
         const double* sm = st.buf + slot * MAP_BUF_DOUBLES;
         if (any) {
 #pragma unroll 2
-            for (int j = 0; j < MAP_CHUNK; j += 2) {
+            for (int j = COOP ? 2 * lane : 0; j < MAP_CHUNK; j += COOP ? MAP_CHUNK : 2) {
                 const double2 u2 = *reinterpret_cast<const double2*>(sm + 0 * MAP_CHUNK + j);
                 const double2 v2 = *reinterpret_cast<const double2*>(sm + 1 * MAP_CHUNK + j);
                 const double2 y2 = *reinterpret_cast<const double2*>(sm + 2 * MAP_CHUNK + j);
@@ -241,7 +246,18 @@ __device__ __forceinline__ void sweep(Stream& st, const double* __restrict__ set
         st.seq++;
     }
     st.primed = nxt;
-    const double A = z.a0 + z.a1, B = z.b0 + z.b1, C = z.c0 + z.c1, D = z.d0 + z.d1;
+    double A = z.a0 + z.a1, B = z.b0 + z.b1, C = z.c0 + z.c1, D = z.d0 + z.d1;
+    if (COOP) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            A += __shfl_xor_sync(0xffffffffu, A, o);
+            if (MODE != SW_GUESS) B += __shfl_xor_sync(0xffffffffu, B, o);
+            if (MODE == SW_F_DF) {
+                C += __shfl_xor_sync(0xffffffffu, C, o);
+                D += __shfl_xor_sync(0xffffffffu, D, o);
+            }
+        }
+    }
     if (FAM == FAM_SUM) {
         o0 = h.sig * A;
         o1 = h.sig * C;
@@ -398,10 +414,27 @@ map_kernel(MapArgs a)
                 Hybrd1 sv;
                 sv.start(alive ? pg : 0.0);
                 if (!alive) sv.phase = 3;
-                while (__any_sync(0xffffffffu, !sv.done())) {
-                    const bool run = !sv.done();
-                    b.y = sv.query();
+                for (;;) {
+                    const unsigned pend = __ballot_sync(0xffffffffu, !sv.done());
+                    if (pend == 0u) break;
+                    const double yq = sv.query();
                     double F, dF;
+                    if (__popc(pend) <= MAP_COOP_MAX) {
+                        // the last few lanes: one cooperative pass each (1/32 of the arithmetic of a full pass)
+                        for (unsigned m = pend; m != 0u; m &= m - 1u) {
+                            const int src = __ffs(m) - 1;
+                            Pt bs;
+                            bs.u = __shfl_sync(0xffffffffu, b.u, src);
+                            bs.v = __shfl_sync(0xffffffffu, b.v, src);
+                            bs.y = __shfl_sync(0xffffffffu, yq, src);
+                            sweep<FAM, SW_F, true>(st, M.tch, M.ncht, M.tch, MAP_TF, lane, bs, M.h, s_tab, true, F, dF);
+                            if (lane == src) { sv.feed(F - p + yq); evals++; }
+                        }
+                        st.passes++;                         // (counted as one pass in the utilisation statistics)
+                        continue;
+                    }
+                    const bool run = !sv.done();
+                    b.y = yq;
                     sweep<FAM, SW_F>(st, M.tch, M.ncht, M.tch, MAP_TF, lane, b, M.h, s_tab, run, F, dF);
                     if (run) { sv.feed(F - p + b.y); evals++; }
                 }
@@ -413,10 +446,27 @@ map_kernel(MapArgs a)
                 // trained on P - p (scripts 03/04/05); start_delta adds p, which is the consistent start for such a model
                 sv.start(alive ? (a.start_delta ? p + pg : pg) : 0.0, a.newton_max_nb, a.newton_max_b);
                 if (!alive) sv.phase = 3;
-                while (__any_sync(0xffffffffu, !sv.done())) {
-                    const bool run = !sv.done();
-                    b.y = sv.query();
+                for (;;) {
+                    const unsigned pend = __ballot_sync(0xffffffffu, !sv.done());
+                    if (pend == 0u) break;
+                    const double yq = sv.query();
                     double F, dF;
+                    if (__popc(pend) <= MAP_COOP_MAX) {
+                        // the last few lanes: one cooperative pass each (1/32 of the arithmetic of a full pass)
+                        for (unsigned m = pend; m != 0u; m &= m - 1u) {
+                            const int src = __ffs(m) - 1;
+                            Pt bs;
+                            bs.u = __shfl_sync(0xffffffffu, b.u, src);
+                            bs.v = __shfl_sync(0xffffffffu, b.v, src);
+                            bs.y = __shfl_sync(0xffffffffu, yq, src);
+                            sweep<FAM, SW_F_DF, true>(st, M.tch, M.ncht, M.tch, MAP_TF, lane, bs, M.h, s_tab, true, F, dF);
+                            if (lane == src) { sv.feed(F - p + yq, 1.0 + dF); evals++; }
+                        }
+                        st.passes++;                         // (counted as one pass in the utilisation statistics)
+                        continue;
+                    }
+                    const bool run = !sv.done();
+                    b.y = yq;
                     sweep<FAM, SW_F_DF>(st, M.tch, M.ncht, M.tch, MAP_TF, lane, b, M.h, s_tab, run, F, dF);
                     if (run) { sv.feed(F - p + b.y, 1.0 + dF); evals++; }
                 }

@@ -24,13 +24,16 @@
 // (TMA engine, SASS UBLKCP) per 64-point chunk, completion is counted on a per-buffer mbarrier, and
 // the copy of chunk c+2 is in flight while the warp evaluates chunk c with broadcast LDS.128 reads
 // (two training points per load).  The 32 lanes advance their solvers in lock step only within the
-// warp (__any_sync), so a slow root solve delays 31 neighbours, not a thread block; slicing the step
+// warp, so a slow root solve delays 31 neighbours, not a thread block -- and not for long: once at most
+// MAP_COOP_MAX lanes are still iterating, each of them is served by a COOPERATIVE pass in which the 32 lanes
+// share the training set for that one orbit (1/32 of the arithmetic of a full pass).  Slicing the step
 // loop into work items keeps all SMs busy to the end whatever the ensemble size.  The kernel is bound
 // by the FP64 pipe (about 50 DP instructions per orbit-point pair incl. one exp), not by shared
 // memory, L2 or HBM: a chunk of 2.5 KB feeds 32 x 64 pair evaluations.
 //
-// Summation order is fixed (chunk by chunk, two interleaved partial sums), so results do not depend
-// on scheduling.
+// Summation order is fixed (full pass: chunk by chunk, two interleaved partial sums; cooperative pass:
+// per-lane partial sums, then a fixed xor-shuffle tree), so results do not depend on scheduling; which of
+// the two a given evaluation uses depends on how many lanes of the batch were still iterating.
 #include "map.cuh"
 
 #include <cstdlib>

@@ -454,9 +454,11 @@ def main():
         map_info = {"metric": "orbit_map_steps_per_s", "value": orbit_steps / t_map, "unit": "orbit-steps/s",
                     "solver": MAP_SOLVER_NAME, "n_train": Nt, "orbits_total": E * world, "steps": a.map_steps,
                     "sweeps_per_orbit_step": 1 + evals / orbit_steps,
-                    "lane_utilisation": (orbit_steps + evals) / (32.0 * max(1, int(passes.item()))),
+                    "passes_per_warp_step": int(passes.item()) / (orbit_steps / 32.0),
+                    "passes_note": "full passes over a training set per 32-orbit step (guess + lock-step residual passes + dQ); a "
+                                   "group of cooperative single-orbit passes for the last <= 8 lanes counts as one",
                     "pair_evals_per_s": orbit_steps * pair_evals / t_map,
-                    "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe", "note": "useful (per-orbit) pair evaluations x 34 DP instr; lanes of a warp that idle during a pass (waiting for the other training set, or for the end of a work item) are not counted: achieved / lane_utilisation is the issued rate",
+                    "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe", "note": "useful (per-orbit) pair evaluations x 34 DP instr (SASS of the F/dF sweep); lanes that idle during a full pass are not counted",
                                  "achieved": orbit_steps * pair_evals * dp_instr / t_map / world, "peak": fp64_peak,
                                  "unit": "DP instr/s per GPU", "frac": orbit_steps * pair_evals * dp_instr / t_map / world / fp64_peak},
                     "e2e": {"value": orbit_steps / t_map_e2e, "unit": "orbit-steps/s",

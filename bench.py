@@ -456,7 +456,7 @@ def main():
                     "sweeps_per_orbit_step": 1 + evals / orbit_steps,
                     "passes_per_warp_step": int(passes.item()) / (orbit_steps / 32.0),
                     "passes_note": "full passes over a training set per 32-orbit step (guess + lock-step residual passes + dQ); a "
-                                   "group of cooperative single-orbit passes for the last <= 8 lanes counts as one",
+                                   "group of cooperative single-orbit passes for the last <= 16 lanes counts as one",
                     "pair_evals_per_s": orbit_steps * pair_evals / t_map,
                     "roofline": {"kernel": "map_kernel<product,newton>", "bound": "fp64 pipe", "note": "useful (per-orbit) pair evaluations x 34 DP instr (SASS of the F/dF sweep); lanes that idle during a full pass are not counted",
                                  "achieved": orbit_steps * pair_evals * dp_instr / t_map / world, "peak": fp64_peak,

@@ -45,7 +45,7 @@ namespace sgp {
 
 constexpr int MAP_THREADS = 128;
 constexpr int MAP_WARPS = MAP_THREADS / 32;
-constexpr int MAP_COOP_MAX = 8;                    // up to this many unconverged lanes are served by cooperative passes
+constexpr int MAP_COOP_MAX = 16;                   // up to this many unconverged lanes are served by cooperative passes
 constexpr int MAP_BLOCKS_PER_SM = 4;               // 16 warps / SM, <= 128 registers per thread
 constexpr int MAP_BUF_DOUBLES = MAP_TF * MAP_CHUNK; // one buffer holds a chunk of either set
 constexpr double TWO_PI = 6.283185307179586;
@@ -422,7 +422,7 @@ map_kernel(MapArgs a)
                     if (pend == 0u) break;
                     const double yq = sv.query();
                     double F, dF;
-                    if (__popc(pend) <= MAP_COOP_MAX) {
+                    if (__popc(pend) <= a.coop_max) {
                         // the last few lanes: one cooperative pass each (1/32 of the arithmetic of a full pass)
                         for (unsigned m = pend; m != 0u; m &= m - 1u) {
                             const int src = __ffs(m) - 1;
@@ -454,7 +454,7 @@ map_kernel(MapArgs a)
                     if (pend == 0u) break;
                     const double yq = sv.query();
                     double F, dF;
-                    if (__popc(pend) <= MAP_COOP_MAX) {
+                    if (__popc(pend) <= a.coop_max) {
                         // the last few lanes: one cooperative pass each (1/32 of the arithmetic of a full pass)
                         for (unsigned m = pend; m != 0u; m &= m - 1u) {
                             const int src = __ffs(m) - 1;
@@ -892,9 +892,12 @@ int map_launch(Ctx& c, int fam, int solver, MapArgs a, void* sched)
     a.slice_steps = ss;
     a.start_delta = (solver == 3) ? 1 : 0;
     a.newton_max_nb = 30; a.newton_max_b = 60;
+    a.coop_max = MAP_COOP_MAX;
     {   // measurement overrides
         static const char* e_nb = getenv("SGP_NEWTON_MAX_NB");
         static const char* e_b = getenv("SGP_NEWTON_MAX_B");
+        static const char* e_cm = getenv("SGP_MAP_COOP_MAX");
+        if (e_cm) a.coop_max = atoi(e_cm);
         if (e_nb && atoi(e_nb) > 0) a.newton_max_nb = atoi(e_nb);
         if (e_b && atoi(e_b) > 0) a.newton_max_b = atoi(e_b);
     }

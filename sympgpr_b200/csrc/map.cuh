@@ -39,6 +39,7 @@ struct MapArgs {
     int nmodels;
     int kind;
     long E, nsteps;
+    int coop_max;                    // up to this many unconverged lanes of a step are served by cooperative passes (map.cu)
     int newton_max_nb, newton_max_b; // Newton give-up limits (evaluations) without / with a bracket
     int start_delta;                 // 1: the guess GP predicts P - p (SGP_SOLVER_NEWTON_DELTA): the solver starts at p + guess
     const double *q0, *p0;

@@ -99,23 +99,41 @@ class ClockSampler:
 
 # ------------------------------------------------------------------------------------------ reference arm
 def cpu_nll_grad_sample(N_s, N_full, steps, warmup):
-    """The reference maths on the host cores (oracle port; SciPy/OpenBLAS LAPACK with all threads):
-    one NLL+gradient evaluation at N_s pairs, scaled by (n_s/n)^3 to the full size (the evaluation
-    is n^3 LAPACK work: potrf + potri; the O(n^2) fill/contraction parts only make the scaled
-    figure flatter the CPU)."""
+    """The reference maths on the host cores (oracle port; SciPy/OpenBLAS LAPACK with all threads): NLL+gradient
+    evaluations at N_s and N_s/2 pairs, extrapolated to the full size with  t(n) = a n^3 + b n^2  fitted to the two
+    samples (potrf + potri are n^3, fill / dK / contraction n^2 with a large constant in NumPy).  Scaling one sample by
+    (n/n_s)^3 alone would overstate the CPU time threefold: here 7.0 s at N = 2048 -> 3580 s, the two-point fit from
+    N = 2048 / 4096 gives 640 s, and the blocked full-size evaluation behind tests/golden/fullsize_nll_N16384.json
+    (which does ~2x the LAPACK flops) took 1147 s on 8 cores.  Returns (evals/s at N_full, seconds at N_s, description)."""
     from oracle import oracle as O
-    d = O.standard_map_training(N_s)
-    hyp = O.timing_hyp(N_s, d["sig"], 1e-8)
-    for _ in range(warmup):
-        O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N_s)
-    ts = []
-    for _ in range(steps):
-        t = time.perf_counter()
-        O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N_s)
-        ts.append(time.perf_counter() - t)
-    t_s = float(np.mean(ts))
-    scale = (N_full / N_s) ** 3
-    return 1.0 / (t_s * scale), t_s
+
+    def timed(N, nrep, nwarm):
+        d = O.standard_map_training(N)
+        hyp = O.timing_hyp(N, d["sig"], 1e-8)
+        for _ in range(nwarm):
+            O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+        ts = []
+        for _ in range(nrep):
+            t = time.perf_counter()
+            O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+            ts.append(time.perf_counter() - t)
+        return float(np.mean(ts))
+
+    t1 = timed(N_s, steps, warmup)
+    N_h = max(64, N_s // 2)
+    t0 = timed(N_h, max(1, steps), 1)
+    n1, n0, nf = 2.0 * N_s, 2.0 * N_h, 2.0 * N_full
+    # a n1^3 + b n1^2 = t1,  a n0^3 + b n0^2 = t0
+    det = n1 ** 3 * n0 ** 2 - n0 ** 3 * n1 ** 2
+    a_c = (t1 * n0 ** 2 - t0 * n1 ** 2) / det
+    b_c = (n1 ** 3 * t0 - n0 ** 3 * t1) / det
+    if N_h < N_s and a_c > 0 and b_c >= 0:
+        t_full = a_c * nf ** 3 + b_c * nf ** 2
+        how = (f"t(n) = a n^3 + b n^2 fitted to N={N_h} ({t0:.3f} s) and N={N_s} ({t1:.3f} s): a={a_c:.3e}, b={b_c:.3e}")
+    else:
+        t_full = t1 * (nf / n1) ** 3
+        how = f"N={N_s} ({t1:.3f} s) scaled by (n/n_s)^3 (two-point fit degenerate)"
+    return 1.0 / t_full, t1, how
 
 
 def blas_threads():
@@ -135,13 +153,13 @@ def run_reference(a):
     try:                                    # torchrun exports OMP_NUM_THREADS=1: lift the BLAS/OpenMP limit again
         from threadpoolctl import threadpool_limits
         with threadpool_limits(limits=ncpu):
-            v, t_s = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
+            v, t_s, how = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
             cores = blas_threads()
     except ImportError:
-        v, t_s = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
+        v, t_s, how = cpu_nll_grad_sample(a.cpu_sample, a.n_train, steps, warm)
         cores = blas_threads()
-    sample = (f"oracle nll_grad (C/NumPy fill, SciPy potrf+potri, elementwise contraction) at N={a.cpu_sample} "
-              f"(n={2 * a.cpu_sample}): {t_s:.3f} s/eval, scaled by (n/n_s)^3 to N={a.n_train}")
+    sample = (f"oracle nll_grad (C/NumPy fill, SciPy potrf+potri, elementwise contraction) on the host cores, extrapolated to "
+              f"N={a.n_train}: {how}")
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": a.gpus, "steps": steps,
             "warmup": warm, "ms_per_step": 1e3 / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -517,10 +535,9 @@ def main():
     # ---- CPU baseline (rank 0, single GPU runs only) --------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:
-        v_cpu, t_s = cpu_nll_grad_sample(a.cpu_sample, N, 2, 1)
+        v_cpu, t_s, how = cpu_nll_grad_sample(a.cpu_sample, N, 2, 1)
         cpu = {"value": v_cpu, "unit": UNIT, "cores": blas_threads(), "kind": "port",
-               "sample": f"oracle nll_grad at N={a.cpu_sample} (n={2 * a.cpu_sample}): {t_s:.3f} s/eval on the host cores, "
-                         f"scaled by (n/n_s)^3 to N={N}"}
+               "sample": f"oracle nll_grad on the host cores, extrapolated to N={N}: {how}"}
 
     if rank == 0:
         # Dominant kernel: gemm_f64_kernel carries every flop of potrf/trtri/lauum (n^3/3 each).  Its

@@ -157,3 +157,23 @@ def test_device_solvers_on_host_match_oracle(harness, family, fid):
             if solver == 1:
                 assert n1.value <= (12 if family == "product" else 50)
     assert nconv >= (60 if family == "product" else 30)
+
+
+def test_quality_host_part_matches_reference_formula():
+    """api.quality: the host half of the reference's `quality` (python/functions/func.py:262-272): gd[k] =
+    mean_squared_error([q1, p1], ysint[Nm, :, k]) and stdgd = np.std(gd); the tokamak variant compares (p, q) with
+    the angle of the reference orbit wrapped (Split_SympGPR/func.py:221-232).  Pure NumPy: no device needed."""
+    from sympgpr_b200 import api
+    rng = np.random.default_rng(1)
+    E, Nm = 7, 3
+    q1, p1 = rng.uniform(0, 6, E), rng.uniform(-1, 1, E)
+    ys = rng.uniform(-3, 9, (Nm + 1, 2, E))
+    eo = rng.uniform(0, 1e-3, E)
+    Eosc, gd, stdgd = api.quality(q1, p1, eo, ys, Nm)
+    ref = np.array([np.mean((np.array([q1[k], p1[k]]) - ys[Nm, :, k])**2) for k in range(E)])      # sklearn's mean_squared_error
+    assert np.allclose(gd, ref, rtol=1e-15) and np.isclose(stdgd, np.std(ref)) and Eosc is not None and np.array_equal(Eosc, eo)
+    ys3 = rng.uniform(-3, 9, (Nm + 1, 3, E))
+    _, gd2, _ = api.quality(q1, p1, eo, ys3, Nm, order="pq")
+    ref2 = np.array([np.mean((np.array([p1[k], q1[k]]) - np.array([ys3[Nm, 0, k], np.mod(ys3[Nm, 1, k], 2 * np.pi)]))**2)
+                     for k in range(E)])
+    assert np.allclose(gd2, ref2, rtol=1e-15)

@@ -2,6 +2,8 @@
 
   * orbit ensembles       -- interleaved slices of (Q0map, P0map) per rank, model replicated
   * multi-start restarts  -- one hyper-parameter vector per rank at a time
+  * quality statistics    -- `quality` of the reference per shard, one all_gather of six numbers
+  * Sobol sample sets     -- Saltelli rows per rank, one all_reduce of the estimator sums
 One process per GPU (torch.distributed, NCCL on GPUs / gloo in the CPU tests); there is no
 collective on the data path, results are gathered once at the end.  The training Cholesky does
 not shard (replicas only).
@@ -100,6 +102,49 @@ def restarts_sharded(thetas, evaluate, group=None, device=None):
         for j, i in enumerate(range(r, T, world)):
             vals[i], grads[i] = a[j, 0], a[j, 1:]
     return vals, grads
+
+
+def quality_sharded(Q0map, P0map, ysint, Nm, quality_fn, order="qp", group=None, device=None):
+    """The reference's `quality` (python/functions/func.py:262-272; tokamak variant Split_SympGPR/func.py:221-232) for an
+    ensemble split over the ranks, with the statistics gathered by ONE all_reduce.
+
+    quality_fn(q0_local, p0_local) -> dict with q1, p1, Eosc of the local orbits (a closure over
+    sympgpr_b200.api.applymap_quality, whose map kernel accumulates Eosc without writing histories).  ysint (rows, >=2, E)
+    holds the reference orbits of ALL E initial conditions; gd[k] is the mean squared distance of the first mapped state
+    from ysint[Nm, :, k].  Returns dict(stdgd, gd_mean, Eosc_mean, Eosc_max, n) -- identical on every rank; orbits whose
+    Eosc or gd is NaN (lost orbits) are left out of the sums and counted in n_lost.  numpy.std semantics (population)."""
+    import torch
+    d = _dist()
+    rank, world = rank_world(group)
+    Q0map, P0map = np.asarray(Q0map, float), np.asarray(P0map, float)
+    ys = np.asarray(ysint, float)
+    E = Q0map.shape[0]
+    idx = shard_indices(E, rank, world)
+    out = quality_fn(Q0map[idx], P0map[idx])
+    q1, p1, eo = (np.asarray(out[k], float) for k in ("q1", "p1", "Eosc"))
+    if order == "pq":
+        ref = np.array([ys[Nm, 0, idx], np.mod(ys[Nm, 1, idx], 2 * np.pi)])
+        mine = np.array([p1, q1])
+    else:
+        ref = np.array([ys[Nm, 0, idx], ys[Nm, 1, idx]])
+        mine = np.array([q1, p1])
+    gd = np.mean((mine - ref)**2, axis=0)
+    ok = np.isfinite(gd) & np.isfinite(eo)
+    acc = np.array([ok.sum(), gd[ok].sum(), (gd[ok]**2).sum(), eo[ok].sum(), (~ok).sum()], float)
+    emax = eo[ok].max() if ok.any() else -np.inf
+    if d is not None and world > 1:
+        # the only collective: six numbers per rank (sums add, the maximum does not, hence a gather rather than a reduce)
+        t = torch.from_numpy(np.append(acc, emax))
+        if device is not None:
+            t = t.to(device)
+        parts = [torch.empty_like(t) for _ in range(world)]
+        d.all_gather(parts, t, group=group)
+        allv = np.stack([p_.cpu().numpy() for p_ in parts])
+        acc, emax = allv[:, :5].sum(axis=0), allv[:, 5].max()
+    n = max(acc[0], 1.0)
+    gmean = acc[1] / n
+    return dict(stdgd=float(np.sqrt(max(acc[2] / n - gmean**2, 0.0))), gd_mean=float(gmean), Eosc_mean=float(acc[3] / n),
+                Eosc_max=float(emax), n=int(acc[0]), n_lost=int(acc[4]))
 
 
 # --------------------------------------------------------------------------- Sobol sample sets (SURVEY 8a row X2)

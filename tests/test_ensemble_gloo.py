@@ -133,3 +133,56 @@ def test_single_process_paths():
     assert np.array_equal(q, qr) and np.array_equal(p, pr)
     v, g = ens.restarts_sharded([np.array([1.0, 2.0])], lambda t: (t.sum(), t))
     assert v.shape == (1,) and g.shape == (1, 2)
+
+
+def _fake_quality(q0, p0):
+    """stand-in for api.applymap_quality: first mapped state of the standard map and a made-up energy oscillation;
+    orbits with p0 < 0.3 are 'lost' (NaN)"""
+    P = p0 + 0.9 * np.sin(q0)
+    q1, p1 = np.mod(q0 + P, 2 * np.pi), P.copy()
+    eo = 1e-3 * (1 + np.cos(q0))
+    lost = p0 < 0.3
+    q1[lost] = np.nan; p1[lost] = np.nan; eo[lost] = np.nan
+    return dict(q1=q1, p1=p1, Eosc=eo)
+
+
+def _quality_reference(q0, p0, ys, Nm):
+    o = _fake_quality(q0, p0)
+    gd = np.mean((np.array([o["q1"], o["p1"]]) - ys[Nm, :2])**2, axis=0)
+    ok = np.isfinite(gd) & np.isfinite(o["Eosc"])
+    return dict(stdgd=np.std(gd[ok]), gd_mean=gd[ok].mean(), Eosc_mean=o["Eosc"][ok].mean(), Eosc_max=o["Eosc"][ok].max(),
+                n=int(ok.sum()), n_lost=int((~ok).sum()))
+
+
+def _quality_worker(rank, world, port, E, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sympgpr_b200 import ensemble as ens
+    rng = np.random.default_rng(5)
+    q0, p0 = rng.uniform(0, 6.28, E), rng.uniform(0, 6.28, E)
+    ys = rng.uniform(0, 6.28, (3, 2, E))
+    res = ens.quality_sharded(q0, p0, ys, 2, _fake_quality)
+    ref = _quality_reference(q0, p0, ys, 2)
+    ok = all(np.isclose(res[k], ref[k], rtol=1e-12, atol=0) for k in ("stdgd", "gd_mean", "Eosc_mean", "Eosc_max"))
+    ok = ok and res["n"] == ref["n"] and res["n_lost"] == ref["n_lost"] and res["n_lost"] > 0
+    out[rank] = 1 if ok else 0
+    dist.destroy_process_group()
+
+
+def test_quality_statistics_world2():
+    """`quality` of the reference (functions/func.py:262-272) over an ensemble split on 2 ranks: gd statistics and energy
+    oscillation agree with the single-process evaluation on every rank; lost (NaN) orbits are counted, not averaged."""
+    world, E = 2, 101
+    port = _free_port()
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_quality_worker, args=(world, port, E, out), nprocs=world, join=True)
+    assert all(out[r] == 1 for r in range(world))
+    # single-process path (no process group)
+    from sympgpr_b200 import ensemble as ens
+    rng = np.random.default_rng(5)
+    q0, p0 = rng.uniform(0, 6.28, E), rng.uniform(0, 6.28, E)
+    ys = rng.uniform(0, 6.28, (3, 2, E))
+    res = ens.quality_sharded(q0, p0, ys, 2, _fake_quality)
+    ref = _quality_reference(q0, p0, ys, 2)
+    assert np.isclose(res["stdgd"], ref["stdgd"], rtol=1e-12) and res["n"] == ref["n"]

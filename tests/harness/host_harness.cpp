@@ -51,7 +51,7 @@ static double calcp_t(int solver, double per, double q, double p, const double* 
         while (!sv.done()) { const double x = sv.query(); sums<FAM>(h, q, x, per, xt, yt, alpha, nt, &F, &dF, &dQ); sv.feed(F - p + x); n++; }
         P = sv.root(); *info = sv.info;
     } else {
-        Newton1 sv; sv.start(pg);
+        Newton1 sv; sv.start(solver == 3 ? p + pg : pg);        // 3 = SGP_SOLVER_NEWTON_DELTA: the guess GP predicts P - p
         while (!sv.done()) { const double x = sv.query(); sums<FAM>(h, q, x, per, xt, yt, alpha, nt, &F, &dF, &dQ); sv.feed(F - p + x, 1.0 + dF); n++; }
         P = sv.root(); *info = sv.info;
     }

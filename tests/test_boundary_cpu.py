@@ -177,3 +177,49 @@ def test_quality_host_part_matches_reference_formula():
     ref2 = np.array([np.mean((np.array([p1[k], q1[k]]) - np.array([ys3[Nm, 0, k], np.mod(ys3[Nm, 1, k], 2 * np.pi)]))**2)
                      for k in range(E)])
     assert np.allclose(gd2, ref2, rtol=1e-15)
+
+
+def test_newton_delta_start_on_host_finds_the_oracle_root_in_fewer_evaluations(harness):
+    """SGP_SOLVER_NEWTON_DELTA through the host build of the solver header: for a guess GP trained on P - p (scripts
+    03/04/05) Newton started at p + guess lands on the root next to the exact map -- the same one a bracketing solver
+    finds around p + K sin q for the reference residual -- and needs fewer residual evaluations than Newton from the
+    reference's start (the bare difference)."""
+    from oracle import c_oracle as C
+    from oracle import oracle as O
+    import scipy.optimize
+    N = 200
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8)
+    hyp[:2] *= 2
+    hypp[:2] *= 2
+    xt, zt, xtp, ztp = d["xtrain"], d["ztrain"], d["xtrainp"], d["ztrainp"]
+    alpha = O.fit_alpha(hyp, xt, zt, 2 * N)
+    alphap = O.fit_alpha(hypp, xtp, ztp, N, reg=True)
+    h3, hp3 = np.ascontiguousarray(hyp[:3]), np.ascontiguousarray(hypp[:3])
+    xq, yP = np.ascontiguousarray(xt[:N]), np.ascontiguousarray(xt[N:])
+    xpq, ypp = np.ascontiguousarray(xtp[:N]), np.ascontiguousarray(xtp[N:])
+    q0 = 0.5 + O.halton(30, 5) * 5.0
+    p0 = 1.5 + O.halton(30, 7) * 3.0
+    n_delta = n_ref = checked = 0
+    for q, p in zip(q0, p0):
+        res = {}
+        for solver in (1, 3):
+            i1, n1, dq = ctypes.c_int(), ctypes.c_int(), ctypes.c_double()
+            P = harness.harness_calcp(0, solver, ctypes.c_double(0.5), ctypes.c_double(q), ctypes.c_double(p), _dp(h3), _dp(hp3),
+                                      _dp(xpq), _dp(ypp), _dp(alphap), ctypes.c_long(N), _dp(xq), _dp(yP), _dp(alpha),
+                                      ctypes.c_long(N), ctypes.byref(i1), ctypes.byref(n1), ctypes.byref(dq))
+            res[solver] = (P, i1.value, n1.value)
+        Pd, info_d, nd = res[3]
+        assert info_d in (1, 3)
+        f = lambda P: C.target_alpha(q, p, P, h3, xq, yP, alpha)
+        assert abs(f(Pd)) < 1e-10                                    # a root of the reference residual
+        Pt = p + 0.9 * np.sin(q)                                     # the exact map; the model is accurate to ~1e-3 here
+        if f(Pt - 0.05) * f(Pt + 0.05) < 0:
+            Pb = scipy.optimize.brentq(f, Pt - 0.05, Pt + 0.05, xtol=1e-15, rtol=1e-15)
+            assert abs(Pd - Pb) <= 1e-10 * max(1.0, abs(Pb)), (q, p, Pd, Pb)
+            checked += 1
+        n_delta += nd
+        n_ref += res[1][2]
+    assert checked >= 25
+    assert n_delta < n_ref

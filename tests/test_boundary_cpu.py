@@ -223,3 +223,46 @@ def test_newton_delta_start_on_host_finds_the_oracle_root_in_fewer_evaluations(h
         n_ref += res[1][2]
     assert checked >= 25
     assert n_delta < n_ref
+
+
+def test_fieldlines_shim_generator_part():
+    """The out-of-scope generator half of the `fieldlines` module (fieldlines.f90:42-170), provided in Python so that
+    calc_fieldlines.py runs: closed forms against finite differences, the unperturbed field line (eps = 0) stays on its flux surface, and
+    the implicit-midpoint step is area preserving (det of its Jacobian = 1)."""
+    import importlib.util, os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "sympgpr_b200", "shims", "fieldlines.py")
+    spec = importlib.util.spec_from_file_location("fieldlines_shim_under_test", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    fl = mod.fieldlines
+    fl.init(32, -3, 2, 1e-3, 0.0, 0.3)
+    r, th, ph, h = 0.31, 1.1, 0.4, 1e-6
+    ath_host = lambda r_, th_: fl.B0 * (r_**2 / 2 - r_**3 / (3 * fl.R0) * np.cos(th_))        # fieldlines.f90:34-39
+    assert np.isclose(fl.dathdr(r, th, ph), (ath_host(r + h, th) - ath_host(r - h, th)) / (2 * h), rtol=1e-8)
+    assert np.isclose(fl.dathdth(r, th, ph), (ath_host(r, th + h) - ath_host(r, th - h)) / (2 * h), rtol=1e-7)
+    assert np.isclose(fl.daphdr(r, th, ph), (fl.aph(r + h, th, ph) - fl.aph(r - h, th, ph)) / (2 * h), rtol=1e-8)
+    assert np.isclose(fl.daphdth(r, th, ph), (fl.aph(r, th + h, ph) - fl.aph(r, th - h, ph)) / (2 * h), rtol=1e-6, atol=1e-12)
+    y, dy = fl.f_r(r, [ath_host(r, th), th, ph])
+    assert abs(y) < 1e-15 and np.isclose(dy, -fl.dathdr(r, th, ph))
+    assert np.isclose(fl._compute_r([ath_host(r, th), th, ph], 0.3), r, rtol=1e-13)
+
+    def step(z0, eps, nph=32):
+        fl.init(nph, -3, 2, eps, 0.0, 0.3)
+        z = np.array(z0, float)
+        fl.timestep(z)
+        return z
+    z0 = [ath_host(0.3, 0.7), 0.7, 0.0]
+    z1 = step(z0, 0.0, nph=256)
+    # unperturbed field: A_phi depends on r only, so the field line stays on its flux surface r = const (to the
+    # accuracy of one midpoint step) while theta advances
+    r1 = fl._compute_r([z1[0], z1[1], z1[2]], 0.3)
+    assert abs(r1 - 0.3) < 1e-6 and np.isclose(z1[2], 2 * np.pi / 256) and abs(z1[1] - z0[1]) > 1e-3
+    e = 1e-6
+    J = np.zeros((2, 2))
+    for c in range(2):
+        zp, zm = list(z0), list(z0)
+        zp[c] += e; zm[c] -= e
+        J[:, c] = (step(zp, 1e-2)[:2] - step(zm, 1e-2)[:2]) / (2 * e)
+    assert abs(np.linalg.det(J) - 1.0) < 1e-7                    # implicit midpoint rule: symplectic
+    with pytest.raises(ValueError):
+        fl.timestep([0.1, 0.2, 0.3])

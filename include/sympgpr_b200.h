@@ -227,6 +227,11 @@ int sgp_model_applymap_quality_dev(sgp_ctx* ctx, const sgp_model* m, int kind, i
  * well the independently advancing orbits of a warp share their passes. */
 int sgp_map_last_passes(sgp_ctx* ctx, unsigned long long* passes);
 
+/* sgp_guessp / sgp_calcq / sgp_calcp / sgp_applymap_tok keep alpha = Kyinv ztrain of the (Kyinv, ztrain) pairs they were
+ * last handed on the device (the reference recomputes that matvec in every call, sympgpr.f90:72,85,121; an unchanged
+ * Python map loop makes 2 E S calls with the same arrays).  Counters of that cache, for tests and profiling. */
+int sgp_alpha_cache_stats(sgp_ctx* ctx, unsigned long long* hits, unsigned long long* misses);
+
 /* ---- fieldlines module (tokamak loss test) ------------------------------------------------ */
 /* fieldlines.f90:94-107 compute_r(z(3), rstart): z = (pth, th, ph); host arithmetic. */
 double sgp_compute_r(double pth, double th, double ph, double rstart);
@@ -240,6 +245,10 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
 /* DMMA GEMM self test: random operands, compares against a plain FP64 kernel; see csrc/dmma_gemm.cuh
  * for al/bl/mode.  Returns the largest absolute difference in *max_err. */
 int sgp_selftest_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, double* max_err);
+/* The DMMA GEMM on HOST operands (tests compare it with NumPy): C = beta C + alpha A Bt over the tile set / k-ranges of
+ * `mode` (csrc/dmma_gemm.cuh); al / bl: 0 = element (m,k) at ptr[m + k ld], 1 = at ptr[k + m ld]; Mt, Nt in tiles of 128. */
+int sgp_gemm_host(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, double alpha, double beta, const double* A,
+                  long lda, const double* B, long ldb, double* C, long ldc);
 /* DMMA GEMM timing: `reps` launches on random operands (alpha = -1, beta = 1), average ms per launch */
 int sgp_bench_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, int reps, double* ms_avg);
 /* timing hooks for bench.py (device pointers, async): the individual stages of one evaluation */

@@ -37,6 +37,7 @@ def lib():
         L.oracle_target_alpha.restype = ctypes.c_double
         L.oracle_compute_r.restype = ctypes.c_double
         L.oracle_applymap_alpha.restype = ctypes.c_long
+        L.oracle_applymap_alpha_ex.restype = ctypes.c_long
         L.oracle_num_threads.restype = ctypes.c_int
         _lib = L
     return _lib
@@ -109,22 +110,33 @@ def compute_r(pth, th, rstart=0.3):
 
 
 def applymap_alpha(kind, nm, q0, p0, hyp, hypp, xtp, ytp, alphap, xt, yt, alpha, family="product", p=0.5,
-                   want_pdiff=False, want_notconv=False):
+                   want_pdiff=False, want_notconv=False, start_delta=False, reverse_sum=False, out_every=1):
     """Returns qmap, pmap (nm, E) [, pdiff], mean function evaluations per orbit-step
     [, per-orbit count of steps where hybrd1 returned info != 1, per-orbit largest
-    residual |f(P)| of an accepted root]."""
+    residual |f(P)| of an accepted root].
+
+    start_delta: hybrd1 is started at p + guess instead of the bare guess (sympgpr.f90:103-107 with a guess GP
+    trained on P - p, python/04_standard_map/main.py:89-90) -- the oracle twin of the library's "newton_delta" start.
+    reverse_sum: the training-set sums run backwards (rounding-sensitivity probe).  out_every = k > 1: only the
+    rows 0, k, 2k, ... of the history are returned ((nm - 1) // k + 1 rows)."""
     q0, p0, hyp, hypp, xtp, ytp, alphap, xt, yt, alpha = map(
         _d, (q0, p0, hyp, hypp, xtp, ytp, alphap, xt, yt, alpha))
     E = len(q0)
-    qmap = np.zeros((nm, E)); pmap = np.zeros((nm, E))
-    pdiff = np.zeros((nm, E)) if want_pdiff else None
+    ex = bool(start_delta or reverse_sum or out_every != 1)
+    rows = (nm - 1) // out_every + 1 if ex else nm
+    qmap = np.zeros((rows, E)); pmap = np.zeros((rows, E))
+    pdiff = np.zeros((rows, E)) if want_pdiff else None
     notconv = np.zeros(max(E, 1), dtype=np.int32)
     maxres = np.zeros(max(E, 1))
-    fev = lib().oracle_applymap_alpha(
-        kind, _fam(family), ctypes.c_double(p), ctypes.c_long(nm), ctypes.c_long(E), _p(q0), _p(p0),
-        _p(hyp), _p(hypp), _p(xtp), _p(ytp), _p(alphap), ctypes.c_long(len(xtp)),
-        _p(xt), _p(yt), _p(alpha), ctypes.c_long(len(xt)), _p(qmap), _p(pmap),
-        _p(pdiff) if want_pdiff else None, notconv.ctypes.data_as(c_ip), _p(maxres))
+    args = (kind, _fam(family), ctypes.c_double(p), ctypes.c_long(nm), ctypes.c_long(E), _p(q0), _p(p0),
+            _p(hyp), _p(hypp), _p(xtp), _p(ytp), _p(alphap), ctypes.c_long(len(xtp)),
+            _p(xt), _p(yt), _p(alpha), ctypes.c_long(len(xt)), _p(qmap), _p(pmap),
+            _p(pdiff) if want_pdiff else None, notconv.ctypes.data_as(c_ip), _p(maxres))
+    if ex:
+        fev = lib().oracle_applymap_alpha_ex(*args, ctypes.c_int((1 if start_delta else 0) | (2 if reverse_sum else 0)),
+                                             ctypes.c_long(out_every))
+    else:
+        fev = lib().oracle_applymap_alpha(*args)
     nev = fev / max(1, E * (nm - 1))
     out = [qmap, pmap]
     if want_pdiff:

@@ -147,14 +147,19 @@ typedef struct {
     long np, nt;
     const double *xtp, *ytp, *alphap;     /* ordinary GP: Np points, alphap(Np)   */
     const double *xt, *yt, *alpha;        /* symplectic GP: Nt points, alpha(2Nt) */
+    int start_delta;                      /* 1: hybrd1 starts at p + guess (guess GP trained on P - p) */
+    int reverse_sum;                      /* 1: training-set sums run from the last point to the first
+                                           * (rounding-sensitivity probe of the tests, not a reference mode) */
 } model_t;
 
 /* sympgpr.f90:62-73 with alphap = Kyinvp*ztrainp hoisted */
 static double guessp_m(const model_t *m, double q, double pp)
 {
     double acc = 0.0;
-    for (long j = 0; j < m->np; j++)
+    for (long jj = 0; jj < m->np; jj++) {
+        long j = m->reverse_sum ? m->np - 1 - jj : jj;
         acc += m->hypp[2] * kern_f(m->fam, m->xtp[j], m->ytp[j], q, pp, m->hypp[0], m->hypp[1], m->p) * m->alphap[j];
+    }
     return acc;
 }
 
@@ -163,7 +168,8 @@ static void kstar_dot(const model_t *m, double q, double P, double *row1, double
 {
     double r1a = 0.0, r1b = 0.0, r2a = 0.0, r2b = 0.0;
     long nt = m->nt;
-    for (long j = 0; j < nt; j++) {
+    for (long jj = 0; jj < nt; jj++) {
+        long j = m->reverse_sum ? nt - 1 - jj : jj;
         double o[3];
         hess_f(m->fam, m->xt[j], m->yt[j], q, P, m->hyp[0], m->hyp[1], m->p, o);
         r1a += m->hyp[2] * o[0] * m->alpha[j];
@@ -331,6 +337,10 @@ static double calcp_m(const model_t *m, double q, double p, int *info, int *nfev
 {
     target_ctx c = { m, q, p };
     double pg = guessp_m(m, q, p);
+    /* sympgpr.f90:103-107 hands the guess GP's prediction to hybrd1 as it is.  Scripts 03/04/05 train that GP on
+     * P - p (python/04_standard_map/main.py:89-90), so the prediction is the difference; start_delta adds p, the
+     * consistent start for such a model (same call sequence otherwise). */
+    if (m->start_delta) pg = p + pg;
     (void)target_f(&c, pg);
     return hybrd1_n1(&c, pg, 1e-13, info, nfev);
 }
@@ -355,7 +365,7 @@ double oracle_guessp(int fam, double pper, double x, double y, const double *hyp
                      const double *ytp, const double *ztp, const double *kyinvp, long np)
 {
     double *a = (double *)malloc(sizeof(double) * np), res;
-    model_t m = { fam, pper, NULL, hypp, np, 0, xtp, ytp, a, NULL, NULL, NULL };
+    model_t m = { fam, pper, NULL, hypp, np, 0, xtp, ytp, a, NULL, NULL, NULL, 0, 0 };
     matvec_cm(kyinvp, np, ztp, a);
     res = guessp_m(&m, x, y);
     free(a);
@@ -366,7 +376,7 @@ double oracle_calcq(int fam, double pper, double x, double y, const double *xt, 
                     const double *hyp, const double *kyinv, const double *zt, long nt)
 {
     double *a = (double *)malloc(sizeof(double) * 2 * nt), res;
-    model_t m = { fam, pper, hyp, NULL, 0, nt, NULL, NULL, NULL, xt, yt, a };
+    model_t m = { fam, pper, hyp, NULL, 0, nt, NULL, NULL, NULL, xt, yt, a, 0, 0 };
     matvec_cm(kyinv, 2 * nt, zt, a);
     res = calcq_m(&m, x, y);
     free(a);
@@ -378,14 +388,14 @@ double oracle_calcp_alpha(int fam, double pper, double x, double y, const double
                           const double *xt, const double *yt, const double *alpha, long nt,
                           int *info, int *nfev)
 {
-    model_t m = { fam, pper, hyp, hypp, np, nt, xtp, ytp, alphap, xt, yt, alpha };
+    model_t m = { fam, pper, hyp, hypp, np, nt, xtp, ytp, alphap, xt, yt, alpha, 0, 0 };
     return calcp_m(&m, x, y, info, nfev);
 }
 
 double oracle_target_alpha(int fam, double pper, double q, double p, double P, const double *hyp,
                            const double *xt, const double *yt, const double *alpha, long nt)
 {
-    model_t m = { fam, pper, hyp, NULL, 0, nt, NULL, NULL, NULL, xt, yt, alpha };
+    model_t m = { fam, pper, hyp, NULL, 0, nt, NULL, NULL, NULL, xt, yt, alpha, 0, 0 };
     target_ctx c = { &m, q, p };
     return target_f(&c, P);
 }
@@ -420,6 +430,72 @@ static double np_mod(double a, double b)
  * evaluations of the root solver (for the n_eval statistic).  notconv (optional, E ints) counts per
  * orbit the steps where hybrd1 returned info != 1 (the reference ignores info, sympgpr.f90:107);
  * maxres (optional, E doubles) the largest residual |f(P)| any accepted root of the orbit left. */
+/* flags: bit 0 = start hybrd1 at p + guess (see calcp_m), bit 1 = reversed summation order (sensitivity probe).
+ * out_every: 1 = full history (nm rows); k > 1 = rows 0, k, 2k, ... ((nm-1)/k + 1 rows); the loop is the same. */
+long oracle_applymap_alpha_ex(int kind, int fam, double pper, long nm, long E, const double *q0, const double *p0,
+                              const double *hyp, const double *hypp,
+                              const double *xtp, const double *ytp, const double *alphap, long np,
+                              const double *xt, const double *yt, const double *alpha, long nt,
+                              double *qmap, double *pmap, double *pdiff, int *notconv, double *maxres,
+                              int flags, long out_every)
+{
+    const double two_pi = 2.0 * M_PI;
+    model_t m = { fam, pper, hyp, hypp, np, nt, xtp, ytp, alphap, xt, yt, alpha, flags & 1, (flags >> 1) & 1 };
+    long total_fev = 0;
+    if (out_every < 1) out_every = 1;
+    for (long k = 0; k < E; k++) {
+        pmap[k] = p0[k];
+        qmap[k] = q0[k];
+        if (pdiff) pdiff[k] = p0[k];
+        if (notconv) notconv[k] = 0;
+        if (maxres) maxres[k] = 0.0;
+    }
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : total_fev)
+    for (long k = 0; k < E; k++) {
+        double qc = q0[k], pc = p0[k], pdc = p0[k];
+        for (long i = 0; i < nm - 1; i++) {
+            double q = qc, p = pc, P, Pst, qn;
+            const long row = ((i + 1) % out_every == 0) ? (i + 1) / out_every : -1;
+            int info, nfev;
+            if (kind == MAP_TOKAMAK && isnan(p)) {
+                pc = NAN; qc = NAN;
+                if (row >= 0) { pmap[row * E + k] = NAN; qmap[row * E + k] = NAN; }
+                continue;
+            }
+            P = calcp_m(&m, q, p, &info, &nfev);
+            total_fev += nfev + 1;
+            if (notconv && info != 1) notconv[k] += 1;
+            if (maxres) {
+                target_ctx tc = { &m, q, p };
+                double rr = fabs(target_f(&tc, P));
+                if (!(rr <= maxres[k])) maxres[k] = rr;
+            }
+            Pst = P;
+            if (kind == MAP_STANDARD) {
+                pdc = pdc + (P - p);
+                Pst = np_mod(P, two_pi);
+            }
+            if (kind == MAP_TOKAMAK) {
+                double r = oracle_compute_r(P * 1e-2, q, 0.3);
+                if (r > 0.5 || P < 0.0) Pst = NAN;
+            }
+            if (isnan(Pst)) {
+                qn = NAN;
+            } else {
+                double dq = calcq_m(&m, q, Pst);
+                qn = (kind == MAP_HENON) ? dq + q : np_mod(dq + q, two_pi);
+            }
+            qc = qn; pc = Pst;
+            if (row >= 0) {
+                pmap[row * E + k] = Pst;
+                qmap[row * E + k] = qn;
+                if (pdiff && kind == MAP_STANDARD) pdiff[row * E + k] = pdc;
+            }
+        }
+    }
+    return total_fev;
+}
+
 long oracle_applymap_alpha(int kind, int fam, double pper, long nm, long E, const double *q0, const double *p0,
                            const double *hyp, const double *hypp,
                            const double *xtp, const double *ytp, const double *alphap, long np,
@@ -427,7 +503,7 @@ long oracle_applymap_alpha(int kind, int fam, double pper, long nm, long E, cons
                            double *qmap, double *pmap, double *pdiff, int *notconv, double *maxres)
 {
     const double two_pi = 2.0 * M_PI;
-    model_t m = { fam, pper, hyp, hypp, np, nt, xtp, ytp, alphap, xt, yt, alpha };
+    model_t m = { fam, pper, hyp, hypp, np, nt, xtp, ytp, alphap, xt, yt, alpha, 0, 0 };
     long total_fev = 0;
     for (long k = 0; k < E; k++) {
         pmap[k] = p0[k];

@@ -73,10 +73,12 @@ _PROTOS = {
     "sgp_model_applymap_quality_dev": (c_i, [c_vp, c_vp, c_i, c_i, c_l, c_l, c_vp, c_vp, c_vp, c_vp, c_i, c_dp, c_l, c_vp,
                                              c_vp, c_vp, c_vp, c_vp, c_vp]),
     "sgp_map_last_passes": (c_i, [c_vp, c_ullp]),
+    "sgp_alpha_cache_stats": (c_i, [c_vp, c_ullp, c_ullp]),
     "sgp_compute_r": (c_d, [c_d, c_d, c_d, c_d]),
     "sgp_ath": (c_d, [c_d, c_d, c_d]),
     "sgp_spd_factor": (c_i, [c_vp, c_dp, c_l, c_dp, c_dp, c_dp]),
     "sgp_selftest_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
+    "sgp_gemm_host": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_d, c_dp, c_l, c_dp, c_l, c_dp, c_l]),
     "sgp_bench_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
     "sgp_fill_sym_dev": (c_i, [c_vp, c_i, c_d, c_i, c_dp, c_vp, c_l, c_vp, c_l]),
     "sgp_potrf_dev": (c_i, [c_vp, c_vp, c_l, c_l, c_vp]),

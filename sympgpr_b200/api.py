@@ -604,3 +604,17 @@ def selftest_gemm(al, bl, mode, Mt, Nt, K):
     err = ctypes.c_double(0.0)
     check(_lib.lib().sgp_selftest_gemm(_lib.context().handle, al, bl, mode, Mt, Nt, K, ctypes.byref(err)), "selftest_gemm")
     return err.value
+
+
+def gemm_host(al, bl, mode, A, B, C, alpha=1.0, beta=0.0):
+    """The library's DMMA GEMM on host operands, in place on the Fortran-ordered C (M x N, multiples of 128):
+    C = beta C + alpha A Bt restricted to the tile set / k-ranges of `mode` (csrc/dmma_gemm.cuh).  A is (M, K) Fortran
+    order for al = 0 and (K, M) Fortran order for al = 1 (i.e. element (m, k) at [k, m]); B likewise with N."""
+    A, B = as_f64_fortran(A), as_f64_fortran(B)
+    if not (isinstance(C, np.ndarray) and C.dtype == np.float64 and C.flags.f_contiguous):
+        raise ValueError("gemm_host: C must be a Fortran-ordered float64 array")
+    M, N = C.shape
+    K = A.shape[1] if al == 0 else A.shape[0]
+    check(_lib.lib().sgp_gemm_host(_lib.context().handle, int(al), int(bl), int(mode), M // 128, N // 128, K, float(alpha),
+                                   float(beta), dptr(A), A.shape[0], dptr(B), B.shape[0], dptr(C), C.shape[0]), "gemm_host")
+    return C

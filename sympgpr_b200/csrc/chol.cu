@@ -1,5 +1,5 @@
-// Blocked FP64 Cholesky (potrf), triangular solves (potrs), triangular inverse (trtri) and
-// X^T X (lauum) on one B200, built from the structured DMMA GEMM of dmma_gemm.cuh.
+// FP64 Cholesky driver (potrf -> potrf_ll.cu), backward substitution (potrs), triangular inverse (trtri) and
+// X^T X (lauum) on one B200, built from the structured DMMA GEMM of dmma_gemm_ws.cuh.
 //
 // Replaces the LAPACK calls the reference makes from Python:
 //   scipy.linalg.cholesky      python/05_tokamak/SympGPR/func.py:147       -> potrf
@@ -11,156 +11,27 @@
 // unchanged).  Only the lower triangle is referenced.
 #include "chol.cuh"
 
-#include <limits.h>
-#include <stdlib.h>
+#include <utility>
+#include <vector>
 
 namespace sgp {
 
-// ------------------------------------------------------------------------------------------
-// 128 x 128 diagonal tile: factor in place, zero the strict upper part, emit inv(L) and
-// sum(log(diag L)).  One CTA, tile resident in shared memory (row stride 129 doubles).
-// ------------------------------------------------------------------------------------------
-constexpr int PT_LD = TILE + 1;
-constexpr int PT_THREADS = 512;                      // 4 threads per row
-constexpr size_t PT_SMEM = (size_t)(TILE * PT_LD + 2 * PT_THREADS) * sizeof(double);
-
-__global__ void __launch_bounds__(PT_THREADS, 1)
-potrf_tile_kernel(double* __restrict__ A, long lda, double* __restrict__ Dinv, double* __restrict__ logpart,
-                  int* __restrict__ info, int col0)
+// diagonal tile j of the matrix <- Dinv_j (ld 128): the leaves of the recursive triangular inverse, one CTA per tile
+__global__ void copy_diag_tiles_kernel(double* __restrict__ A, long lda, const double* __restrict__ Dinv)
 {
-    extern __shared__ __align__(16) double sm[];
-    double* S = sm;                      // S[r*PT_LD + c]
-    double* tmp = sm + TILE * PT_LD;     // 2*PT_THREADS doubles scratch
-    const int tid = threadIdx.x;
-
-    for (int idx = tid; idx < TILE * TILE; idx += PT_THREADS) {
-        int r = idx & (TILE - 1), c = idx >> 7;
-        S[r * PT_LD + c] = (r >= c) ? A[r + (long)c * lda] : 0.0;
-    }
-    __syncthreads();
-
-    const int r = tid & (TILE - 1);      // row owned in the trailing update
-    const int part = tid >> 7;           // columns c with (c - j - 1) % 4 == part
-    double mylog = 0.0;
-    double* Sr = S + r * PT_LD;
-
-    for (int j = 0; j < TILE; j++) {
-        double d = S[j * PT_LD + j];
-        bool bad = !(d > 0.0);           // also true for NaN
-        if (bad) {
-            if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
-            d = 1.0;
-        }
-        const double dj = sqrt(d);
-        const double inv = 1.0 / dj;
-        __syncthreads();                 // everyone has read S[j][j]
-        if (part == 0) {
-            if (r > j) Sr[j] *= inv;
-            else if (r == j) { Sr[j] = dj; mylog = log(dj); }
-        }
-        __syncthreads();
-        if (r > j) {
-            const double lrj = Sr[j];
-            // columns c = j+1+part, j+5+part, ... <= r ; four independent updates per trip
-            int c = j + 1 + part;
-            for (; c + 12 <= r; c += 16) {
-                const double l0 = S[c * PT_LD + j], l1 = S[(c + 4) * PT_LD + j], l2 = S[(c + 8) * PT_LD + j],
-                             l3 = S[(c + 12) * PT_LD + j];
-                const double s0 = Sr[c], s1 = Sr[c + 4], s2 = Sr[c + 8], s3 = Sr[c + 12];
-                Sr[c] = s0 - lrj * l0; Sr[c + 4] = s1 - lrj * l1; Sr[c + 8] = s2 - lrj * l2; Sr[c + 12] = s3 - lrj * l3;
-            }
-            for (; c <= r; c += 4) Sr[c] -= lrj * S[c * PT_LD + j];
-        }
-        __syncthreads();                 // S[j+1][j+1] final before the next pivot is read
-    }
-
-    // L back to global (lower + explicit zeros above the diagonal)
-    for (int idx = tid; idx < TILE * TILE; idx += PT_THREADS) {
-        int rr = idx & (TILE - 1), c = idx >> 7;
-        A[rr + (long)c * lda] = S[rr * PT_LD + c];
-    }
-    // sum of log(diag): fixed order
-    if (part == 0) tmp[r] = mylog;
-    __syncthreads();
-    if (tid == 0) {
-        double s = 0.0;
-        for (int k = 0; k < TILE; k++) s += tmp[k];
-        *logpart = s;
-    }
-    __syncthreads();
-
-    // in-place inverse of the lower-triangular tile (unblocked, last column first):
-    //   X[j][j] = 1/L[j][j];  X[j+1:, j] = -X[j+1:, j+1:] * L[j+1:, j] * X[j][j]
-    for (int j = TILE - 1; j >= 0; j--) {
-        const double xjj = 1.0 / S[j * PT_LD + j];
-        double p0 = 0.0, p1 = 0.0;
-        if (r > j) {
-            int k = j + 1 + part;
-            for (; k + 4 <= r; k += 8) {
-                p0 += Sr[k] * S[k * PT_LD + j];
-                p1 += Sr[k + 4] * S[(k + 4) * PT_LD + j];
-            }
-            for (; k <= r; k += 4) p0 += Sr[k] * S[k * PT_LD + j];
-        }
-        tmp[tid] = p0 + p1;
-        __syncthreads();                 // all reads of column j (still L) done
-        if (part == 0) {
-            if (r > j) Sr[j] = -((tmp[r] + tmp[r + TILE]) + (tmp[r + 2 * TILE] + tmp[r + 3 * TILE])) * xjj;
-            else if (r == j) Sr[j] = xjj;
-        }
-        __syncthreads();
-    }
-    for (int idx = tid; idx < TILE * TILE; idx += PT_THREADS) {
-        int rr = idx & (TILE - 1), c = idx >> 7;
-        Dinv[rr + c * TILE] = S[rr * PT_LD + c];
-    }
-}
-
-// copy a 128x128 tile (src ld 128) into the matrix
-__global__ void copy_tile_kernel(double* __restrict__ dst, long ldd, const double* __restrict__ src)
-{
+    const long j = blockIdx.x;
+    double* dst = A + j * TILE + j * TILE * lda;
+    const double* src = Dinv + j * TILE * TILE;
     for (int idx = threadIdx.x; idx < TILE * TILE; idx += blockDim.x) {
         int r = idx & (TILE - 1), c = idx >> 7;
-        dst[r + (long)c * ldd] = src[idx];
+        dst[r + (long)c * lda] = src[idx];
     }
 }
 
 // ------------------------------------------------------------------------------------------
-// potrs by blocked substitution with the tile inverses.
-// forward step j:  w_j = Dinv_j * y_j ;  y[rows below] -= L[rows below, j] * w_j
+// potrs, second half, by blocked substitution with the tile inverses (the forward substitution
+// L w = y rides along in potrf_ll's diagonal tasks).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TILE)
-trsv_fwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Dinv, double* __restrict__ y,
-                     double* __restrict__ w, int j)
-{
-    __shared__ double yj[TILE];
-    __shared__ double wj[TILE];
-    const int tid = threadIdx.x;
-    const long base = (long)j * TILE;
-    yj[tid] = y[base + tid];
-    __syncthreads();
-    {
-        const double* D = Dinv + (long)j * TILE * TILE;
-        double s = 0.0;
-        for (int c = 0; c <= tid; c++) s += D[tid + c * TILE] * yj[c];
-        wj[tid] = s;
-    }
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        w[base + tid] = wj[tid];
-        return;
-    }
-    const long row = base + (long)blockIdx.x * TILE + tid;     // blockIdx.x >= 1: rows below the tile
-    const double* Lr = L + row + base * ld;
-    double s0 = 0.0, s1 = 0.0;
-#pragma unroll 4
-    for (int c = 0; c < TILE; c += 2) {
-        s0 += Lr[(long)c * ld] * wj[c];
-        s1 += Lr[(long)(c + 1) * ld] * wj[c + 1];
-    }
-    y[row] -= (s0 + s1);
-}
-
 // backward step j:  a_j = Dinv_j^T * w_j ;  w[cols left] -= L[tile rows j, cols left]^T * a_j
 __global__ void __launch_bounds__(256)
 trsv_bwd_step_kernel(const double* __restrict__ L, long ld, const double* __restrict__ Dinv, double* __restrict__ w,
@@ -200,22 +71,6 @@ trsv_bwd_step_kernel(const double* __restrict__ L, long ld, const double* __rest
 // ------------------------------------------------------------------------------------------
 // drivers
 // ------------------------------------------------------------------------------------------
-static int g_potrf_cfg = 0;
-
-static int launch_potrf_tile(Ctx& c, double* A, long lda, double* Dinv, double* logparts, int* info, int jt)
-{
-    if (!g_potrf_cfg) {
-        SGP_CUDA(cudaFuncSetAttribute(potrf_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PT_SMEM));
-        g_potrf_cfg = 1;
-    }
-    const long o = (long)jt * TILE;
-    potrf_tile_kernel<<<1, PT_THREADS, PT_SMEM, c.stream>>>(A + o + o * lda, lda, Dinv + (long)jt * TILE * TILE, logparts + jt,
-                                                      info, (int)o);
-    SGP_CUDA(cudaGetLastError());
-    count_launch();
-    return ST_OK;
-}
-
 static int gemm(Ctx& c, int al, int bl, const double* A, long lda, const double* B, long ldb, double* C, long ldc,
                 int Mt, int Nt, long K, double alpha, double beta, int mode)
 {
@@ -227,134 +82,12 @@ static int gemm(Ctx& c, int al, int bl, const double* A, long lda, const double*
 
 #define AT(A, lda, rt, ct) ((A) + (long)(rt) * TILE + (long)(ct) * TILE * (lda))
 
-// X * L[l0..l0+kt)^T = B,  B = A[r0..r0+rt) x [l0..l0+kt)  (tile indices), in place
-static int trsm_rec(Ctx& c, double* A, long lda, const double* Dinv, int l0, int kt, int r0, int rt)
-{
-    if (rt <= 0) return ST_OK;
-    if (kt == 1) {
-        double* B = AT(A, lda, r0, l0);
-        return gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, Dinv + (long)l0 * TILE * TILE, TILE, B, lda, rt, 1, TILE, 1.0, 0.0,
-                    TM_FULL);
-    }
-    const int k1 = kt / 2, k2 = kt - k1;
-    SGP_TRY(trsm_rec(c, A, lda, Dinv, l0, k1, r0, rt));
-    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, AT(A, lda, r0, l0), lda, AT(A, lda, l0 + k1, l0), lda, AT(A, lda, r0, l0 + k1),
-                 lda, rt, k2, (long)k1 * TILE, -1.0, 1.0, TM_FULL));
-    return trsm_rec(c, A, lda, Dinv, l0 + k1, k2, r0, rt);
-}
-
-static int potrf_rec(Ctx& c, double* A, long lda, double* Dinv, double* logparts, int* info, int j0, int mt)
-{
-    if (mt == 1) return launch_potrf_tile(c, A, lda, Dinv, logparts, info, j0);
-    const int m1 = mt / 2, m2 = mt - m1;
-    SGP_TRY(potrf_rec(c, A, lda, Dinv, logparts, info, j0, m1));
-    SGP_TRY(trsm_rec(c, A, lda, Dinv, j0, m1, j0 + m1, m2));
-    double* B = AT(A, lda, j0 + m1, j0);
-    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, B, lda, AT(A, lda, j0 + m1, j0 + m1), lda, m2, m2, (long)m1 * TILE,
-                 -1.0, 1.0, TM_LOWER));
-    return potrf_rec(c, A, lda, Dinv, logparts, info, j0 + m1, m2);
-}
-
-static int env_int(const char* name, int dflt, int lo, int hi)
-{
-    const char* v = getenv(name);
-    if (!v || !*v) return dflt;
-    int x = atoi(v);
-    if (x < lo) x = lo;
-    if (x > hi) x = hi;
-    return x;
-}
-
-// Right-looking blocked factorisation: panels of NB = nb_tiles*128 columns.  The diagonal block is
-// factored recursively (small, latency-bound launches), the panel below it is one recursive TRSM over
-// all remaining rows and the trailing update one lower-triangular SYRK launch with K = NB, so almost
-// all flops run in launches that fill the 148 SMs.
-static int potrf_multi(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info);
-
+// The whole factorisation is the left-looking persistent kernel of potrf_ll.cu, with the forward substitution fused in.
 int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* y, double* w)
 {
     if (n_pad % TILE || lda % 2) { set_error("potrf: n_pad %ld / lda %ld not tile aligned", n_pad, lda); return ST_BADARG; }
-    // default: the left-looking persistent kernel (potrf_ll.cu) with the forward substitution fused in.
-    // SGP_POTRF=rec selects the recursive / blocked multi-launch drivers below (kept for comparison).
-    static const int use_rec = [] { const char* v = getenv("SGP_POTRF"); return (v && v[0] == 'r') ? 1 : 0; }();
-    if (!use_rec) {
-        SGP_TRY(c.flags.reserve(potrf_ll_flag_bytes(n_pad)));
-        return potrf_ll(c, A, n_pad, lda, Dinv, logparts, info, c.flags.as<int>(), y, w);
-    }
-    SGP_TRY(potrf_multi(c, A, n_pad, lda, Dinv, logparts, info));
-    if (y && w) SGP_TRY(trsv_fwd(c, A, n_pad, lda, Dinv, y, w));
-    return ST_OK;
-}
-
-static int potrf_multi(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info)
-{
-    const int nt = (int)(n_pad / TILE);
-    const int nb = env_int("SGP_POTRF_NB", 0, 0, 64);
-    if (nb == 0) return potrf_rec(c, A, lda, Dinv, logparts, info, 0, nt);      // fully recursive
-    const int lookahead = env_int("SGP_LOOKAHEAD", 1, 0, 1) && c.side != nullptr && nt > 2 * nb;
-    cudaStream_t s0 = c.stream, s1 = c.side;
-
-    auto panel = [&](int k0, int kb) -> int {            // diagonal block + everything below it
-        SGP_TRY(potrf_rec(c, A, lda, Dinv, logparts, info, k0, kb));
-        return trsm_rec(c, A, lda, Dinv, k0, kb, k0 + kb, nt - (k0 + kb));
-    };
-
-    if (!lookahead) {
-        for (int k0 = 0; k0 < nt; k0 += nb) {
-            const int kb = (nt - k0 < nb) ? (nt - k0) : nb;
-            SGP_TRY(panel(k0, kb));
-            const int rt = nt - (k0 + kb);
-            if (rt > 0) {
-                double* B = AT(A, lda, k0 + kb, k0);
-                SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, B, lda, AT(A, lda, k0 + kb, k0 + kb), lda, rt, rt,
-                             (long)kb * TILE, -1.0, 1.0, TM_LOWER));
-            }
-        }
-        return ST_OK;
-    }
-
-    // Look-ahead of depth one: after panel k, first update only the next block column, then factor
-    // panel k+1 on the high-priority side stream while the main stream applies panel k to the rest
-    // of the trailing matrix.  The two touch disjoint block columns.
-    SGP_TRY(panel(0, nb < nt ? nb : nt));
-    for (int k0 = 0; k0 < nt; k0 += nb) {
-        const int kb = (nt - k0 < nb) ? (nt - k0) : nb;
-        const int n0 = k0 + kb;                          // first tile of the next panel
-        const int rt = nt - n0;
-        if (rt <= 0) break;
-        const int kn = (rt < nb) ? rt : nb;              // width of the next panel
-        double* B = AT(A, lda, n0, k0);
-        // (a) next block column: rows n0.., cols n0..n0+kn
-        SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B, lda, B, lda, AT(A, lda, n0, n0), lda, rt, kn, (long)kb * TILE, -1.0, 1.0,
-                     TM_FULL));
-        SGP_CUDA(cudaEventRecord(c.ev[0], s0));
-        SGP_CUDA(cudaStreamWaitEvent(s1, c.ev[0], 0));
-        c.stream = s1;
-        int st = panel(n0, kn);
-        c.stream = s0;
-        SGP_TRY(st);
-        SGP_CUDA(cudaEventRecord(c.ev[1], s1));
-        // (b) rest of the trailing matrix: rows/cols from n0+kn
-        const int r2 = rt - kn;
-        if (r2 > 0) {
-            double* B2 = AT(A, lda, n0 + kn, k0);
-            SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_MN, B2, lda, B2, lda, AT(A, lda, n0 + kn, n0 + kn), lda, r2, r2, (long)kb * TILE,
-                         -1.0, 1.0, TM_LOWER));
-        }
-        SGP_CUDA(cudaStreamWaitEvent(s0, c.ev[1], 0));
-    }
-    return ST_OK;
-}
-
-int trsv_fwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w)
-{
-    const int nt = (int)(n_pad / TILE);
-    for (int j = 0; j < nt; j++) {
-        trsv_fwd_step_kernel<<<nt - j, TILE, 0, c.stream>>>(L, lda, Dinv, y, w, j);
-    }
-    SGP_CUDA(cudaGetLastError());
-    count_launch((unsigned long long)nt);
-    return ST_OK;
+    SGP_TRY(c.flags.reserve(potrf_ll_flag_bytes(n_pad)));
+    return potrf_ll(c, A, n_pad, lda, Dinv, logparts, info, c.flags.as<int>(), y, w);
 }
 
 int trsv_bwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* w, double* alpha)
@@ -458,107 +191,107 @@ int symv_lower(Ctx& c, const double* W, long n_pad, long ldw, const double* y, d
     return ST_OK;
 }
 
-// scratch (in 128x128 tiles) of trtri_rec on mt tiles: the m2 x m1 product T of this level, after the two
-// halves, which may run concurrently and therefore get disjoint regions
-static size_t trtri_tiles(int mt)
+// ------------------------------------------------------------------------------------------
+// Triangular inverse X = L^-1, in place, by the recursion
+//     X = [X11 0; X21 X22],   X11 = inv(L11), X22 = inv(L22) (independent),   X21 = -X22 (L21 X11)
+// down to single tiles, whose inverses potrf_ll left in Dinv.  All nodes of one recursion depth are independent,
+// so a depth is TWO grouped launches of the persistent DMMA GEMM (T = L21 X11 for every node, then L21 = -X22 T
+// for every node) however many nodes it has: 2 ceil(log2 nt) + 1 launches for the whole inverse (17 at
+// n = 32768, 13 at n = 8192; the node-by-node recursion took 510 launches and left the GPU mostly idle at the
+// bottom of the tree, where a node is a handful of tiles of depth 128).
+// ------------------------------------------------------------------------------------------
+struct TrtriPlan {
+    // key
+    const double* A = nullptr; long lda = 0; int nt = 0; const double* T = nullptr;
+    // per depth: [first, last) into the entry arrays, tile counts
+    std::vector<int> first;          // size depths + 1
+    std::vector<long> tiles1, tiles2;
+    DBuf d_e1, d_e2;                 // GemmGroupEntry arrays in device memory (step 1 / step 2 of every depth)
+};
+
+static void trtri_collect(double* A, long lda, double* T, int j0, int mt, int depth, std::vector<std::vector<std::pair<int, int>>>& lv)
 {
-    if (mt <= 1) return 0;
-    const int m1 = mt / 2, m2 = mt - m1;
-    const size_t own = (size_t)m1 * m2, kids = trtri_tiles(m1) + trtri_tiles(m2);
-    return own > kids ? own : kids;
+    if (mt <= 1) return;
+    if ((int)lv.size() <= depth) lv.resize((size_t)depth + 1);
+    lv[(size_t)depth].push_back({j0, mt});
+    const int m1 = mt / 2;
+    trtri_collect(A, lda, T, j0, m1, depth + 1, lv);
+    trtri_collect(A, lda, T, j0 + m1, mt - m1, depth + 1, lv);
 }
 
-constexpr int TRTRI_FORK_MAX = 32;     // blocks of up to 32 tiles run their two halves on different streams
-
-// side streams / events for the forked sub-trees (created on first use, live as long as the process)
-static cudaStream_t g_fork_streams[8];
-static cudaEvent_t g_fork_events[64];
-static int g_fork_ready = 0, g_fork_next_stream = 0, g_fork_next_event = 0;
-
-static int fork_init()
+static int trtri_build_plan(Ctx& c, TrtriPlan& pl, double* A, long lda, int nt, double* T)
 {
-    if (g_fork_ready) return ST_OK;
-    for (auto& s : g_fork_streams) SGP_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    for (auto& e : g_fork_events) SGP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    g_fork_ready = 1;
+    pl.A = nullptr;
+    std::vector<std::vector<std::pair<int, int>>> lv;
+    trtri_collect(A, lda, T, 0, nt, 0, lv);
+    std::vector<GemmGroupEntry> e1, e2;
+    pl.first.assign(1, 0);
+    pl.tiles1.clear(); pl.tiles2.clear();
+    for (size_t d = 0; d < lv.size(); d++) {
+        long t1 = 0, t2 = 0;
+        size_t toff = 0;                                         // nodes of one depth get disjoint scratch regions
+        for (auto& nd : lv[d]) {
+            const int j0 = nd.first, mt = nd.second, m1 = mt / 2, m2 = mt - m1;
+            double* Tn = T + toff * TILE * TILE;
+            toff += (size_t)m1 * m2;
+            const long ldt = (long)m2 * TILE;
+            GemmGroupEntry a{}, b{};
+            // T = L21 * X11        (X11 lower: k >= tn*128)
+            a.a.A = AT(A, lda, j0 + m1, j0); a.a.lda = lda; a.a.B = AT(A, lda, j0, j0); a.a.ldb = lda; a.a.C = Tn; a.a.ldc = ldt;
+            a.a.Mt = m2; a.a.Nt = m1; a.a.K = m1 * TILE; a.a.alpha = 1.0; a.a.beta = 0.0; a.a.mode = TM_B_LOWER; a.tile0 = t1;
+            // L21 = -X22 * T       (X22 lower: k < (tm+1)*128)
+            b.a.A = AT(A, lda, j0 + m1, j0 + m1); b.a.lda = lda; b.a.B = Tn; b.a.ldb = ldt; b.a.C = AT(A, lda, j0 + m1, j0); b.a.ldc = lda;
+            b.a.Mt = m2; b.a.Nt = m1; b.a.K = m2 * TILE; b.a.alpha = -1.0; b.a.beta = 0.0; b.a.mode = TM_A_LOWER; b.tile0 = t2;
+            t1 += (long)m2 * m1; t2 += (long)m2 * m1;
+            e1.push_back(a); e2.push_back(b);
+        }
+        pl.first.push_back((int)e1.size());
+        pl.tiles1.push_back(t1); pl.tiles2.push_back(t2);
+    }
+    if (!e1.empty()) {
+        SGP_TRY(pl.d_e1.reserve(e1.size() * sizeof(GemmGroupEntry)));
+        SGP_TRY(pl.d_e2.reserve(e2.size() * sizeof(GemmGroupEntry)));
+        // pageable source: the copy is staged before the call returns, the vectors may go out of scope
+        SGP_CUDA(cudaMemcpyAsync(pl.d_e1.p, e1.data(), e1.size() * sizeof(GemmGroupEntry), cudaMemcpyHostToDevice, c.stream));
+        SGP_CUDA(cudaMemcpyAsync(pl.d_e2.p, e2.data(), e2.size() * sizeof(GemmGroupEntry), cudaMemcpyHostToDevice, c.stream));
+    }
+    pl.A = A; pl.lda = lda; pl.nt = nt; pl.T = T;
     return ST_OK;
 }
 
-// X = L^-1 for the diagonal block of mt tiles starting at tile j0, in place, on c.stream.
-// X11 and X22 are independent; X21 = -X22 L21 X11.  The small blocks at the bottom of the recursion are
-// launches of a few CTAs each: their two halves are forked onto side streams so that they fill the GPU together.
-static int trtri_rec(Ctx& c, double* A, long lda, const double* Dinv, double* T, int j0, int mt)
+// scratch (in 128x128 tiles): the products T of all nodes of one depth at the same time; the root alone needs
+// floor(nt/2) ceil(nt/2) tiles and no deeper level needs more
+static size_t trtri_tiles(int nt)
 {
-    if (mt == 1) {
-        copy_tile_kernel<<<1, 256, 0, c.stream>>>(AT(A, lda, j0, j0), lda, Dinv + (long)j0 * TILE * TILE);
-        count_launch();
-        SGP_CUDA(cudaGetLastError());
-        return ST_OK;
-    }
-    const int m1 = mt / 2, m2 = mt - m1;
-    double* T2 = T + trtri_tiles(m1) * TILE * TILE;          // scratch of the second half
-    if (mt <= TRTRI_FORK_MAX && mt >= 2) {
-        SGP_TRY(fork_init());
-        cudaStream_t s0 = c.stream;
-        cudaStream_t s1 = g_fork_streams[g_fork_next_stream++ % 8];
-        cudaEvent_t ef = g_fork_events[g_fork_next_event++ % 64];
-        cudaEvent_t ej = g_fork_events[g_fork_next_event++ % 64];
-        SGP_CUDA(cudaEventRecord(ef, s0));
-        SGP_CUDA(cudaStreamWaitEvent(s1, ef, 0));
-        SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, m1));
-        c.stream = s1;
-        const int st = trtri_rec(c, A, lda, Dinv, T2, j0 + m1, m2);
-        c.stream = s0;
-        SGP_TRY(st);
-        SGP_CUDA(cudaEventRecord(ej, s1));
-        SGP_CUDA(cudaStreamWaitEvent(s0, ej, 0));
-    } else {
-        SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, m1));
-        SGP_TRY(trtri_rec(c, A, lda, Dinv, T2, j0 + m1, m2));
-    }
-    const long ldt = (long)m2 * TILE;
-    // T = L21 * X11        (X11 lower: k >= tn*128)
-    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + m1, j0), lda, AT(A, lda, j0, j0), lda, T, ldt, m2, m1,
-                 (long)m1 * TILE, 1.0, 0.0, TM_B_LOWER));
-    // L21 = -X22 * T       (X22 lower: k < (tm+1)*128)
-    SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + m1, j0 + m1), lda, T, ldt, AT(A, lda, j0 + m1, j0), lda, m2, m1,
-                 (long)m2 * TILE, -1.0, 0.0, TM_A_LOWER));
-    return ST_OK;
+    return (size_t)(nt / 2) * (size_t)(nt - nt / 2);
 }
 
-// Blocked lower-triangular inverse, last block column first (LAPACK dtrtri order):
-//   X_jj = inv(L_jj) (recursive);  T = X[j+1:, j+1:] * L[j+1:, j];  X[j+1:, j] = -T * X_jj
 int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T)
 {
     const int nt = (int)(n_pad / TILE);
-    const int nb = env_int("SGP_TRTRI_NB", 0, 0, 64);
-    if (nb == 0) return trtri_rec(c, A, lda, Dinv, T, 0, nt);                    // fully recursive
-    int j0 = ((nt - 1) / nb) * nb;
-    for (; j0 >= 0; j0 -= nb) {
-        const int jb = (nt - j0 < nb) ? (nt - j0) : nb;
-        SGP_TRY(trtri_rec(c, A, lda, Dinv, T, j0, jb));          // needs jb/2 x jb/2 tiles of T
-        const int rt = nt - (j0 + jb);
-        if (rt > 0) {
-            double* T2 = T + (trtri_tiles(nb) + 1) * TILE * TILE;   // past trtri_rec's scratch
-            const long ldt = (long)rt * TILE;
-            // T2 = X22 * L21          (X22 lower: k < (tm+1)*128)
-            SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, AT(A, lda, j0 + jb, j0 + jb), lda, AT(A, lda, j0 + jb, j0), lda, T2, ldt, rt, jb,
-                         (long)rt * TILE, 1.0, 0.0, TM_A_LOWER));
-            // L21 = -T2 * X_jj        (X_jj lower: k >= tn*128)
-            SGP_TRY(gemm(c, LAYOUT_MN, LAYOUT_K, T2, ldt, AT(A, lda, j0, j0), lda, AT(A, lda, j0 + jb, j0), lda, rt, jb,
-                         (long)jb * TILE, -1.0, 0.0, TM_B_LOWER));
-        }
+    copy_diag_tiles_kernel<<<nt, 256, 0, c.stream>>>(A, lda, Dinv);
+    SGP_CUDA(cudaGetLastError());
+    count_launch();
+    if (nt == 1) return ST_OK;
+    // the plan (per-depth problem lists in device memory) depends only on the pointers and the order: one per device
+    static TrtriPlan plans[64];
+    if (c.device < 0 || c.device >= 64) { set_error("trtri: device index %d out of range", c.device); return ST_BADARG; }
+    TrtriPlan& pl = plans[c.device];
+    if (pl.A != A || pl.lda != lda || pl.nt != nt || pl.T != T) SGP_TRY(trtri_build_plan(c, pl, A, lda, nt, T));
+    const GemmGroupEntry* e1 = pl.d_e1.as<GemmGroupEntry>();
+    const GemmGroupEntry* e2 = pl.d_e2.as<GemmGroupEntry>();
+    for (int d = (int)pl.tiles1.size() - 1; d >= 0; d--) {          // deepest nodes first
+        const int f = pl.first[(size_t)d], np = pl.first[(size_t)d + 1] - f;
+        SGP_CUDA((gemm_ws_launch_grouped_t<LAYOUT_MN, LAYOUT_K>(e1 + f, np, pl.tiles1[(size_t)d], c.stream)));
+        SGP_CUDA((gemm_ws_launch_grouped_t<LAYOUT_MN, LAYOUT_K>(e2 + f, np, pl.tiles2[(size_t)d], c.stream)));
+        count_launch(2);
     }
     return ST_OK;
 }
 
 size_t trtri_workspace_doubles(long n_pad)
 {
-    const size_t nb = 64;                                        // upper bound of SGP_TRTRI_NB
-    const size_t rec = (trtri_tiles((int)nb) + 1) * TILE * TILE;
-    const size_t blocked = rec + (size_t)n_pad * (nb * TILE);
-    const size_t recursive = (trtri_tiles((int)(n_pad / TILE)) + 1) * TILE * TILE;
-    return blocked > recursive ? blocked : recursive;
+    return (trtri_tiles((int)(n_pad / TILE)) + 1) * TILE * TILE;
 }
 
 int lauum(Ctx& c, const double* X, long n_pad, long lda, double* W, long ldw)
@@ -602,13 +335,9 @@ int ref_gemm(Ctx& c, int al, int bl, const GemmArgs& g, double* out)
     return ST_OK;
 }
 
-// SGP_GEMM=v1 selects the cp.async ring kernel (dmma_gemm.cuh); default is the warp-specialised
-// persistent kernel (dmma_gemm_ws.cuh).  Same arguments, same results up to summation order (identical).
 int dmma_gemm(Ctx& c, int al, int bl, const GemmArgs& g)
 {
-    static const int use_v1 = [] { const char* v = getenv("SGP_GEMM"); return (v && v[0] == 'v' && v[1] == '1') ? 1 : 0; }();
-    if (use_v1) SGP_CUDA(gemm_launch(al, bl, g, c.stream));
-    else SGP_CUDA(gemm_ws_launch(al, bl, g, c.stream));
+    SGP_CUDA(gemm_ws_launch(al, bl, g, c.stream));
     count_launch();
     return ST_OK;
 }

@@ -6,15 +6,13 @@
 
 namespace sgp {
 
-// Cholesky factor in place; with y and w given also the forward substitution L w = y (y is overwritten
-// on the multi-launch path, left alone on the fused one)
+// Cholesky factor in place; with y and w given also the forward substitution L w = y (y is left alone)
 int potrf(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* y = nullptr, double* w = nullptr);
 // one persistent cooperative kernel (potrf_ll.cu); flags: potrf_ll_flag_bytes(n_pad) bytes of device scratch
 int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags, const double* y,
              double* w);
 size_t potrf_ll_flag_bytes(long n_pad);
-// blocked substitutions with the tile inverses: forward L w = y (y destroyed), backward L^T alpha = w (w destroyed)
-int trsv_fwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* y, double* w);
+// blocked backward substitution with the tile inverses: L^T alpha = w (w destroyed); the forward half is fused into potrf_ll
 int trsv_bwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* w, double* alpha);
 // alpha = X^T w for the explicit lower-triangular inverse factor X (entries above the diagonal are not read)
 int gemv_t_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* w, double* alpha);

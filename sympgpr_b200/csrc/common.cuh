@@ -70,13 +70,25 @@ constexpr int RES_DOUBLES = 16;
 // stage boundaries of one NLL(+gradient) evaluation: start | fill | potrf | potrs | trtri | lauum | grad | finalize
 constexpr int NSTAGE_EV = 8;
 
+// alpha = Kyinv z of one (Kyinv, z) pair the f2py-signature entry points were handed, kept on the device: the
+// reference recomputes this matvec inside every guessP / calcq / target call (sympgpr.f90:72,85,121); an unchanged
+// Python loop makes 2 E S such calls with the same arrays, so re-uploading n^2 doubles per call would dominate.
+struct AlphaEntry {
+    const double* kyinv = nullptr;    // host addresses + order + sampled checksum identify the pair
+    const double* z = nullptr;
+    long n = 0;
+    unsigned long long sum = 0ull, stamp = 0ull;
+    DBuf buf;                         // [alpha (n) | z staging (n)]
+};
+constexpr int ALPHA_CACHE = 8;
+
 struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;    // main stream (borrowed or owned)
     bool own_stream = false;
-    cudaStream_t side = nullptr;      // panel / look-ahead stream (owned)
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io, flags;
+    AlphaEntry acache[ALPHA_CACHE];
+    unsigned long long aclock = 0ull, ahits = 0ull, amisses = 0ull;
     double* h_res = nullptr;          // pinned host staging (RES_DOUBLES + spare)
     int sm_count = 148;
     // optional stage timers of one NLL evaluation (sgp_set_profiling / sgp_stage_times)

@@ -43,6 +43,26 @@ struct TileInfo {
     int nk;       // k-slabs of GK
 };
 
+// One problem of a GROUPED launch: independent GEMMs (the nodes of one level of the recursive triangular
+// inverse, chol.cu) share one persistent launch; global tile index t belongs to the entry with
+// tile0 <= t < tile0 + gemm_num_tiles(a).
+struct GemmGroupEntry {
+    GemmArgs a;
+    long tile0;
+};
+
+// global tile index -> (problem, tile index inside the problem); entries are sorted by tile0
+__device__ __forceinline__ void group_lookup(const GemmGroupEntry* __restrict__ grp, int nprob, long tile, GemmArgs& p, long& b)
+{
+    int lo = 0, hi = nprob - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (grp[mid].tile0 <= tile) lo = mid; else hi = mid - 1;
+    }
+    p = grp[lo].a;
+    b = tile - grp[lo].tile0;
+}
+
 // tile index -> position and k-range (same enumeration as gemm_f64_kernel: long k-ranges first)
 __device__ __forceinline__ TileInfo tile_info(const GemmArgs& p, long b)
 {
@@ -106,8 +126,9 @@ __device__ __forceinline__ void load_frags_b(const double* sb, int wn, int g, in
     for (int j = 0; j < 4; j++) bf[j] = frag<LAY>(sb, wn + j * 8 + g, kk + t);
 }
 
-template <int AL, int BL>
-__global__ void __launch_bounds__(WS_GEMM_THREADS, 1) gemm_f64_ws_kernel(GemmArgs p, long ntiles)
+// GROUPED = false: one problem `p0`.  GROUPED = true: `nprob` problems `grp` (device memory), `ntiles` tiles in all.
+template <int AL, int BL, bool GROUPED>
+__global__ void __launch_bounds__(WS_GEMM_THREADS, 1) gemm_f64_ws_kernel(GemmArgs p0, long ntiles, const GemmGroupEntry* __restrict__ grp, int nprob)
 {
     extern __shared__ __align__(16) double smem[];
     unsigned long long* full = reinterpret_cast<unsigned long long*>(smem + (size_t)WS_STAGES * 2 * STAGE_DOUBLES);
@@ -133,7 +154,10 @@ __global__ void __launch_bounds__(WS_GEMM_THREADS, 1) gemm_f64_ws_kernel(GemmArg
         if (part > 0 && AL == LAYOUT_MN && BL == LAYOUT_MN) return;      // nothing to do for bulk-only operands
         uint32_t it = 0;
         for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-            const TileInfo ti = tile_info(p, tile);
+            GemmArgs p = p0;
+            long tb = tile;
+            if (GROUPED) group_lookup(grp, nprob, tile, p, tb);
+            const TileInfo ti = tile_info(p, tb);
             const long m0 = (long)ti.tm * GT, n0 = (long)ti.tn * GT;
             for (int kb = 0; kb < ti.nk; kb++, it++) {
                 const int s = (int)(it % WS_STAGES);
@@ -158,10 +182,13 @@ __global__ void __launch_bounds__(WS_GEMM_THREADS, 1) gemm_f64_ws_kernel(GemmArg
     const int g = lane >> 2, t = lane & 3;
     const int wm = (warp & 1) * 64;
     const int wn = (warp >> 1) * 32;
-    const double alpha = p.alpha, beta = p.beta;
     uint32_t it = 0;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const TileInfo ti = tile_info(p, tile);
+        GemmArgs p = p0;
+        long tb = tile;
+        if (GROUPED) group_lookup(grp, nprob, tile, p, tb);
+        const double alpha = p.alpha, beta = p.beta;
+        const TileInfo ti = tile_info(p, tb);
         const long m0 = (long)ti.tm * GT, n0 = (long)ti.tn * GT;
         double acc[8][4][2];
 #pragma unroll
@@ -230,7 +257,7 @@ inline cudaError_t gemm_ws_launch_t(const GemmArgs& a, cudaStream_t st)
 {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_f64_ws_kernel<AL, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_f64_ws_kernel<AL, BL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
         if (e != cudaSuccess) return e;
         configured = true;
     }
@@ -238,7 +265,25 @@ inline cudaError_t gemm_ws_launch_t(const GemmArgs& a, cudaStream_t st)
     if (nt <= 0 || a.K <= 0) return cudaSuccess;
     const int sms = ws_sm_count();
     const unsigned grid = (unsigned)(nt < sms ? nt : sms);
-    gemm_f64_ws_kernel<AL, BL><<<grid, WS_GEMM_THREADS, WS_SMEM, st>>>(a, nt);
+    gemm_f64_ws_kernel<AL, BL, false><<<grid, WS_GEMM_THREADS, WS_SMEM, st>>>(a, nt, nullptr, 0);
+    return cudaGetLastError();
+}
+
+// grouped launch: `d_grp` = nprob entries in device memory, `ntiles` = sum of their tile counts
+template <int AL, int BL>
+inline cudaError_t gemm_ws_launch_grouped_t(const GemmGroupEntry* d_grp, int nprob, long ntiles, cudaStream_t st)
+{
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_f64_ws_kernel<AL, BL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (nprob <= 0 || ntiles <= 0) return cudaSuccess;
+    const int sms = ws_sm_count();
+    const unsigned grid = (unsigned)(ntiles < sms ? ntiles : sms);
+    GemmArgs none{};
+    gemm_f64_ws_kernel<AL, BL, true><<<grid, WS_GEMM_THREADS, WS_SMEM, st>>>(none, ntiles, d_grp, nprob);
     return cudaGetLastError();
 }
 

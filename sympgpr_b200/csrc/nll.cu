@@ -8,6 +8,8 @@
 //   Kyinv = scipy.linalg.inv(K + sig2_n I)  python/01_pendulum/implicit/main.py:138-140,159-161
 #include "nll.cuh"
 
+#include <float.h>
+
 #include "chol.cuh"
 #include "fill.cuh"
 #include "dof2.cuh"
@@ -101,7 +103,11 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     const int fam = job.fam;
     if (fam < 0 || fam > 2) { set_error("unknown kernel family %d", fam); return ST_BADARG; }
     if (job.reg < 0 || job.reg > 4 || ((job.reg == 2 || job.reg == 3) && job.ngrad > 0)) { set_error("nll: reg must be 0..4 (no gradient for 2 and 3)"); return ST_BADARG; }
-    if (!(job.hyp[0] > 0.0) || !(job.hyp[1] > 0.0)) { set_error("nll: length scales must be positive"); return ST_BADARG; }
+    // the kernels depend on l^2 only (kernels.f90:9-10) and their l-derivatives are odd in l, so a negative length scale
+    // is a valid argument exactly as in the reference (an optimiser working on raw hyper-parameters may pass one)
+    if (job.hyp[0] == 0.0 || job.hyp[1] == 0.0 || !(fabs(job.hyp[0]) <= DBL_MAX) || !(fabs(job.hyp[1]) <= DBL_MAX)) {
+        set_error("nll: length scales must be finite and non-zero"); return ST_BADARG;
+    }
     const bool need_inv = job.ngrad > 0 || job.d_kinv != nullptr;
 
     SGP_TRY(c.Kmat.reserve((size_t)n_pad * n_pad * sizeof(double)));

@@ -77,3 +77,71 @@ extern "C" void harness_f_df(int fam, double per, double q, double P, const doub
     if (fam == FAM_SQ) { const HypC h = make_hypc(FAM_SQ, hyp[0], hyp[1], hyp[2], per); sums<FAM_SQ>(h, q, P, per, xt, yt, alpha, nt, F, dF, dQ); }
     else { const HypC h = make_hypc(FAM_PRODUCT, hyp[0], hyp[1], hyp[2], per); sums<FAM_PRODUCT>(h, q, P, per, xt, yt, alpha, nt, F, dF, dQ); }
 }
+
+// Ensemble loops (python/functions/func.py:216-260, 04_standard_map/func.py:218-254, 05_tokamak/SympGPR/func.py:182-211)
+// on the host with the product's own arithmetic (forms.cuh closed forms, Newton1 / Hybrd1 state machines of hybrd.cuh,
+// sequential sums): a CPU stand-in for map_kernel that lets the parity fixtures be checked against the device code's
+// logic without a GPU.  kind: 0 pendulum, 1 henon, 2 standard, 3 tokamak.  Rows 0, every, 2 every, ... are returned.
+static double np_mod_h(double a, double b)
+{
+    double r = fmod(a, b);
+    if (r != 0.0 && r < 0.0) r += b;
+    return r;
+}
+
+static double compute_r_h(double pth, double th, double rstart)
+{
+    double r = rstart;
+    const double ct = cos(th);
+    for (int k = 0; k < 20; k++) {
+        const double yv = pth - (r * r / 2.0 - r * r * r / 3.0 * ct);
+        const double dy = -(r - r * r * ct);
+        r = r - yv / dy;
+    }
+    return r;
+}
+
+template <int FAM>
+static long applymap_t(int kind, int solver, double per, long nsteps, long E, const double* q0, const double* p0,
+                       const double* hyp, const double* hypp, const double* xtp, const double* ytp, const double* alphap, long np,
+                       const double* xt, const double* yt, const double* alpha, long nt, long every, double* qout, double* pout)
+{
+    const double two_pi = 6.283185307179586;
+    long evals = 0;
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : evals)
+    for (long k = 0; k < E; k++) {
+        double q = q0[k], p = p0[k];
+        qout[k] = q; pout[k] = p;
+        for (long s = 1; s <= nsteps; s++) {
+            double qn = NAN, Pst = NAN;
+            if (q == q && p == p) {
+                int info, nfev;
+                double dq;
+                const double P = calcp_t<FAM>(solver, per, q, p, hyp, hypp, xtp, ytp, alphap, np, xt, yt, alpha, nt, &info, &nfev, &dq);
+                evals += nfev + 1;
+                Pst = P;
+                if (kind == 2) Pst = np_mod_h(P, two_pi);
+                if (kind == 3) { const double r = compute_r_h(P * 1e-2, q, 0.3); if (r > 0.5 || P < 0.0) Pst = NAN; }
+                if (Pst == Pst) {
+                    // the reference evaluates dq at the stored (possibly wrapped) momentum
+                    const HypC h = make_hypc(FAM, hyp[0], hyp[1], hyp[2], per);
+                    double F, dF, dQ;
+                    sums<FAM>(h, q, Pst, per, xt, yt, alpha, nt, &F, &dF, &dQ);
+                    qn = (kind == 1) ? dQ + q : np_mod_h(dQ + q, two_pi);
+                }
+            }
+            q = qn; p = Pst;
+            if (s % every == 0) { qout[(s / every) * E + k] = q; pout[(s / every) * E + k] = p; }
+        }
+    }
+    return evals;
+}
+
+extern "C" long harness_applymap(int fam, int kind, int solver, double per, long nsteps, long E, const double* q0, const double* p0,
+                                 const double* hyp, const double* hypp, const double* xtp, const double* ytp,
+                                 const double* alphap, long np, const double* xt, const double* yt, const double* alpha,
+                                 long nt, long every, double* qout, double* pout)
+{
+    if (fam == FAM_SQ) return applymap_t<FAM_SQ>(kind, solver, per, nsteps, E, q0, p0, hyp, hypp, xtp, ytp, alphap, np, xt, yt, alpha, nt, every, qout, pout);
+    return applymap_t<FAM_PRODUCT>(kind, solver, per, nsteps, E, q0, p0, hyp, hypp, xtp, ytp, alphap, np, xt, yt, alpha, nt, every, qout, pout);
+}

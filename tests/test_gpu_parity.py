@@ -50,6 +50,37 @@ def test_dmma_gemm_matches_plain_fp64(api, al, bl, mode, Mt, Nt, K):
     assert err < 1e-11 * max(1, K / 64), err
 
 
+@pytest.mark.parametrize("al,bl,mode,Mt,Nt,K", [
+    (0, 0, 0, 2, 3, 128), (0, 0, 1, 3, 3, 256), (0, 1, 3, 3, 2, 256), (0, 1, 4, 3, 2, 384), (1, 1, 2, 3, 3, 384),
+    (1, 0, 0, 2, 1, 48), (0, 0, 0, 5, 4, 1024),
+])
+def test_dmma_gemm_matches_numpy(api, al, bl, mode, Mt, Nt, K):
+    """The DMMA kernel on host operands against NumPy (not against a sibling kernel of the library): every operand
+    layout and tile mode (full / lower / the three triangular k-ranges) the Cholesky drivers use."""
+    rng = np.random.default_rng(1000 * al + 100 * bl + 10 * mode + Mt)
+    M, N = 128 * Mt, 128 * Nt
+    A = rng.standard_normal((M, K)); B = rng.standard_normal((N, K))
+    C0 = np.asfortranarray(rng.standard_normal((M, N)))
+    alpha, beta = -1.25, 0.75
+    C = C0.copy(order="F")
+    api.gemm_host(al, bl, mode, A if al == 0 else A.T, B if bl == 0 else B.T, C, alpha, beta)
+    ref = C0.copy()
+    for tm in range(Mt):
+        for tn in range(Nt):
+            if mode in (1, 2) and tn > tm:
+                continue                                          # lower modes leave the upper tiles alone
+            k0, k1 = 0, K
+            if mode == 2:
+                k0 = tm * 128
+            if mode == 3:
+                k0 = tn * 128
+            if mode == 4:
+                k1 = min((tm + 1) * 128, K)
+            r, c = slice(tm * 128, (tm + 1) * 128), slice(tn * 128, (tn + 1) * 128)
+            ref[r, c] = beta * C0[r, c] + alpha * A[r, k0:k1] @ B[c, k0:k1].T
+    assert np.allclose(C, ref, rtol=0, atol=1e-12 * max(1, K / 16)), np.abs(C - ref).max()
+
+
 @pytest.mark.parametrize("n", [1, 5, 127, 128, 129, 300, 640, 1500])
 def test_spd_factor_and_inverse(api, n):
     rng = np.random.default_rng(n)
@@ -304,21 +335,30 @@ def _check_orbits(C, m, q, p, qr, pr, good, wrapq, wrapp, max_other_root=0.0, fa
     return len(bad)
 
 
-def _oracle_map(C, kind, nm, q0, p0, m, want_pdiff=False):
+def _oracle_map(C, kind, nm, q0, p0, m, want_pdiff=False, start_delta=False):
     """Oracle trajectories + mask of orbits whose every accepted root is a real root (|f| < 1e-10).
     Where the learned map has no root the reference's hybrd1 stops on a non-root (info is ignored,
-    sympgpr.f90:107); such orbits are garbage in any implementation and are not compared."""
+    sympgpr.f90:107); such orbits are garbage in any implementation and are not compared.
+    start_delta: hybrd1 started at p + guess (the oracle twin of the "newton_delta" start)."""
     N = m["N"]
     out = C.applymap_alpha(kind, nm, q0, p0, m["hyp"], m["hypp"], m["xtp"][:N], m["xtp"][N:], m["alphap"], m["xt"][:N],
-                           m["xt"][N:], m["alpha"], want_pdiff=want_pdiff, want_notconv=True)
+                           m["xt"][N:], m["alpha"], want_pdiff=want_pdiff, want_notconv=True, start_delta=start_delta)
     good = out[-1] < 1e-10
     return out, good
 
 
 @pytest.mark.parametrize("kind,kname", [(0, "pendulum"), (1, "henon"), (2, "standard"), (3, "tokamak")])
-@pytest.mark.parametrize("solver", ["hybrd", "newton"])
+@pytest.mark.parametrize("solver", ["hybrd", "newton", "newton_delta"])
 def test_applymap_matches_oracle(api, O, C, kind, kname, solver):
+    """Every map-loop variant x every solver against the oracle started at the SAME point:
+       hybrd         = the reference's solver and start (guess as it is)            -> oracle as the reference runs it
+       newton        = analytic Newton from the reference's start                   -> same oracle
+       newton_delta  = analytic Newton from p + guess (guess GP trained on P - p)   -> oracle with hybrd1 started at p + guess
+    1e-8 on every comparable orbit.  Only Newton from the FAR start of the P - p models (kinds 2, 3; neither a default nor
+    benchmarked) may settle on another genuine root of a multi-root residual for a few orbits."""
     guess = "P" if kind in (0, 1) else "dP"          # what the respective reference scripts do
+    if solver == "newton_delta" and guess == "P":
+        pytest.skip("newton_delta is the start for guess GPs trained on P - p (scripts 03/04/05)")
     m = _model(O, 100, guess=guess)
     N = m["N"]
     E, nm = 37, 12
@@ -327,7 +367,7 @@ def test_applymap_matches_oracle(api, O, C, kind, kname, solver):
     if kind == 3:
         p0 = p0 * 0.6          # some orbits fall below 0 / outside r < 0.5 and are lost
     want_pd = kind == 2
-    ref, good = _oracle_map(C, kind, nm, q0, p0, m, want_pd)
+    ref, good = _oracle_map(C, kind, nm, q0, p0, m, want_pd, start_delta=(solver == "newton_delta"))
     assert good.sum() >= 0.7 * E
     fn = {0: api.applymap, 1: api.applymap_henon, 2: api.applymap_standard, 3: api.applymap_tok}[kind]
     out = fn(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"], m["Kyinv"],
@@ -335,23 +375,10 @@ def test_applymap_matches_oracle(api, O, C, kind, kname, solver):
     q, p = out[0], out[1]
     qr, pr = ref[0], ref[1]
     assert q.shape == (nm, E) and p.shape == (nm, E)
-    if solver == "hybrd":
-        # same algorithm as the reference: trajectories agree to 1e-8 on every comparable orbit
-        _check_orbits(C, m, q, p, qr, pr, good, kind != 1, kind == 2)
-        if want_pd:
-            assert np.allclose(out[2][:, good], ref[2][:, good], rtol=1e-8, atol=1e-8)
-    elif kind != 2:
-        # safeguarded Newton: same root as MINPACK wherever the residual has one root in reach; from the
-        # far start Delta P (scripts 03/04/05) it may settle on another genuine root
-        _check_orbits(C, m, q, p, qr, pr, good, kind != 1, False, max_other_root=0.05 if guess == "P" else 0.5)
-    else:
-        # standard-map variant stores p mod 2pi; compare the first step only (root property per orbit)
-        Praw = out[2][1] - out[2][0] + p0
-        for k in np.nonzero(good)[0]:
-            r = C.target_alpha(q0[k], p0[k], Praw[k], m["hyp"], m["xt"][:N], m["xt"][N:], m["alpha"])
-            assert abs(r) < 1e-9, (k, r)
-        same = (_wrapdiff(q[1], qr[1], True) < 1e-8) & (_wrapdiff(p[1], pr[1], True) < 1e-8)
-        assert same[good].mean() > 0.5
+    far_newton = solver == "newton" and guess == "dP"
+    _check_orbits(C, m, q, p, qr, pr, good, kind != 1, kind == 2, max_other_root=0.1 if far_newton else 0.0)
+    if want_pd and not far_newton:
+        assert np.allclose(out[2][:, good], ref[2][:, good], rtol=1e-8, atol=1e-8)
     st = out[-1]
     assert st["evaluations"] > 0
     if kind == 3:
@@ -359,23 +386,22 @@ def test_applymap_matches_oracle(api, O, C, kind, kname, solver):
 
 
 def test_newton_delta_start(api, O, C):
-    """SGP_SOLVER_NEWTON_DELTA: Newton started at p + guess for a guess GP trained on P - p (scripts 03/04/05).  Same
-    trajectories as the oracle's hybrd1 from the reference's far start wherever both land on the root next to p
-    (the far start may pick another genuine root), in fewer residual evaluations than Newton from the far start."""
+    """SGP_SOLVER_NEWTON_DELTA: Newton started at p + guess for a guess GP trained on P - p (scripts 03/04/05), against the
+    oracle's hybrd1 started at the same point: the same trajectories (1e-8) on EVERY orbit whose roots are roots, no
+    unconverged step, and fewer residual evaluations than Newton from the reference's far start."""
     m = _model(O, 150, guess="dP")
     E, nm = 64, 12
     q0 = O.halton(E, 5) * 2 * np.pi
     p0 = 1.0 + O.halton(E, 7) * 4.0
-    ref, good = _oracle_map(C, 2, nm, q0, p0, m, True)
-    assert good.sum() >= 0.7 * E
+    ref, good = _oracle_map(C, 2, nm, q0, p0, m, True, start_delta=True)
+    assert good.sum() >= 0.8 * E
     outs = {}
     for solver in ("newton", "newton_delta"):
         outs[solver] = api.applymap_standard(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"],
                                              m["Kyinv"], solver=solver, alphap=m["alphap"], alpha=m["alpha"], return_stats=True)
     q, p, pd, st = outs["newton_delta"]
-    _check_orbits(C, m, q, p, ref[0], ref[1], good, True, True, max_other_root=0.3)
-    agree = (_wrapdiff(q[-1], ref[0][-1], True) < 1e-8) & (_wrapdiff(p[-1], ref[1][-1], True) < 1e-8)
-    assert agree[good].mean() > 0.7
+    _check_orbits(C, m, q, p, ref[0], ref[1], good, True, True, max_other_root=0.0)
+    assert np.allclose(pd[:, good], ref[2][:, good], rtol=1e-8, atol=1e-8)
     assert st["unconverged"] == 0
     assert st["evaluations"] < outs["newton"][-1]["evaluations"]
 
@@ -428,7 +454,7 @@ def test_applymap_multi_chunk_training_set(api, O, C):
     for solver in ("hybrd", "newton"):
         q, p = api.applymap(nm, E, m["hyp"], m["hypp"], q0, p0, m["xtp"], m["ztp"], m["Kyinvp"], m["xt"], m["zt"],
                             m["Kyinv"], solver=solver, alphap=m["alphap"], alpha=m["alpha"])
-        _check_orbits(C, m, q, p, qr, pr, good, True, False, max_other_root=0.0 if solver == "hybrd" else 0.03)
+        _check_orbits(C, m, q, p, qr, pr, good, True, False, max_other_root=0.0)
 
 
 def _rotation_model(O, N=100, a=0.5, l=1.0, noise=1e-8):

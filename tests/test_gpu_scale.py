@@ -1,0 +1,308 @@
+"""GPU parity tests at BASELINE config sizes (pytest -m gpu): the map path pinned at config scale, the tokamak kind with lost
+orbits on a large ensemble, the device-resident ensemble helpers (Sobol sample sets, DeviceMapModel) and the
+entry-point details added in round 2 (alpha cache, negative length scales, lost-orbit semantics of applymap_tok).
+
+Everything goes through the C ABI (sympgpr_b200.api / _lib); the oracle is the checker."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = os.path.join(HERE, "golden")
+
+
+@pytest.fixture(scope="module")
+def api():
+    from sympgpr_b200 import _lib, api as a
+    if _lib.device_count() < 1:
+        pytest.fail("no CUDA device: the GPU tests need a B200 (the product has no CPU fallback)")
+    return a
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def C():
+    from oracle import c_oracle
+    return c_oracle
+
+
+def _wrapdist(a, b):
+    d = np.abs(a - b)
+    return np.minimum(d, np.abs(d - 2 * np.pi))
+
+
+# ------------------------------------------------------------------------------- config 4: Nt = 4096, 1000 steps
+def test_newton_delta_config4_golden(api):
+    """The benchmarked map solver ("newton_delta": Newton with the analytic derivative, started at p + guess) at BASELINE
+    config 4 scale -- 4096 training pairs, 1000 map steps, orbits taken from bench.py's own ensemble -- against the CPU
+    oracle's hybrd1 (sympgpr.f90:88-125 restated, tol 1e-13) started at the SAME point, on the same model bit for bit
+    (tests/golden/map_config4_newton_delta.npz, generator make_golden_map_config4.py).
+
+    Which orbits can be compared at 1e-8 after 1000 steps is decided by the oracle alone: the regular-orbit
+    subset = orbits whose oracle trajectories from p0 and p0 + 1e-12 differ by < 1e-9 after 1000 steps and whose every
+    accepted root is a root (|f| < 1e-10).  The GPU must stay within 1e-8 of the oracle on ALL of them, at every
+    recorded row (every 100 steps).  The whole candidate set is mapped in one launch, so regular and irregular orbits
+    share warps and the cooperative passes (summation order depends on the batch composition) are exercised."""
+    from sympgpr_b200 import workloads as W
+    g = np.load(os.path.join(G, "map_config4_newton_delta.npz"))
+    Nt, nm, every = int(g["nt"]), int(g["nm"]), int(g["every"])
+    assert Nt == 4096 and nm == 1001
+    d = W.standard_map_training(Nt)
+    q0a, p0a = W.ensemble(int(g["e_bench"]))
+    idx = g["idx"]
+    assert np.array_equal(q0a[idx], g["q0"]) and np.array_equal(p0a[idx], g["p0"])          # orbits of the bench ensemble
+    E = len(idx)
+    regular = (g["sens_pert"][-1] < 1e-9) & (g["maxres"] < 1e-10)
+    assert regular.sum() >= 256, regular.sum()
+    q, p, st = api.applymap_standard(nm, E, g["hyp"][:3], g["hypp"][:3], g["q0"], g["p0"], d["xtrainp"], None, None, d["xtrain"],
+                                     None, None, solver="newton_delta", alphap=g["alphap"], alpha=g["alpha"], out_every=every,
+                                     want_pdiff=False, return_stats=True)
+    assert q.shape == g["q"].shape
+    dist = np.maximum(_wrapdist(q, g["q"]), _wrapdist(p, g["p"]))
+    worst = dist[:, regular].max(axis=1)
+    print(f"\nconfig-4 parity: {int(regular.sum())} regular orbits of {E} candidates; max distance per 100 steps:",
+          " ".join(f"{w:.1e}" for w in worst))
+    assert worst.max() < 1e-8, worst
+    # the first 100 steps are comparable for every orbit whose roots are roots and whose 100-step sensitivity is small
+    early = (g["sens_pert"][1] < 1e-10) & (g["maxres"] < 1e-10)
+    assert early.sum() >= 0.5 * E
+    assert dist[1, early].max() < 1e-8, dist[1, early].max()
+    assert st["unconverged"] <= 0.002 * E * (nm - 1)          # orbits trapped at the edge of the training domain (no root there)
+    assert 2.0 < st["evaluations"] / (E * (nm - 1.0)) < 3.6        # Newton + dQ sweeps per orbit-step (hybrd1 needs ~14)
+
+
+def test_hybrd_config4_first_steps(api, C):
+    """The reference's own solver and start (hybrd1 at the bare guess, sympgpr.f90:103-107) at Nt = 4096 on orbits of the
+    bench ensemble: 3 steps against the oracle, 1e-8 on every orbit whose accepted roots are roots."""
+    from sympgpr_b200 import workloads as W
+    g = np.load(os.path.join(G, "map_config4_newton_delta.npz"))
+    Nt = int(g["nt"])
+    d = W.standard_map_training(Nt)
+    sel = np.arange(0, len(g["idx"]), 8)[:192]
+    q0, p0 = g["q0"][sel], g["p0"][sel]
+    xt, xtp = d["xtrain"], d["xtrainp"]
+    qr, pr, _, notconv, maxres = C.applymap_alpha(2, 4, q0, p0, g["hyp"][:3], g["hypp"][:3], xtp[:Nt], xtp[Nt:], g["alphap"], xt[:Nt],
+                                                  xt[Nt:], g["alpha"], want_notconv=True)
+    good = maxres < 1e-10
+    q, p, _ = api.applymap_standard(4, len(sel), g["hyp"][:3], g["hypp"][:3], q0, p0, xtp, None, None, xt, None, None,
+                                    solver="hybrd", alphap=g["alphap"], alpha=g["alpha"])
+    dist = np.maximum(_wrapdist(q, qr), _wrapdist(p, pr))
+    assert good.sum() >= 20                                    # the far start leaves few orbits with genuine roots
+    assert dist[:, good].max() < 1e-8, dist[:, good].max()
+
+
+# ------------------------------------------------------------------------------- tokamak kind, E >= 1e4
+@pytest.mark.parametrize("solver,delta", [("hybrd", False), ("newton_delta", True)])
+def test_tokamak_kind_with_lost_orbits_large_ensemble(api, O, C, solver, delta):
+    """python/05_tokamak/SympGPR/func.py:182-211 on 12 000 orbits: q wrapped, orbit lost (NaN from then on) where
+    compute_r([1e-2 P, q, 0], 0.3) > 0.5 or P < 0.  Same NaN pattern as the oracle and 1e-8 on every orbit whose roots are
+    roots; the oracle runs the same solver start (hybrd1 at the guess / at p + guess)."""
+    from sympgpr_b200 import workloads as W
+    N = 256
+    d = W.tokamak_training(N)
+    hyp = W.aniso_hyp(N, d["sig"], 2 * np.pi, 9.4, 1.5, 1e-8)
+    hypp = W.aniso_hyp(N, d["sigp"], 2 * np.pi, 9.4, 1.5, 1e-8)
+    xt, zt, xtp, ztp = d["xtrain"], d["ztrain"], d["xtrainp"], d["ztrainp"]
+    alpha = O.fit_alpha(hyp, xt, zt, 2 * N)
+    alphap = O.fit_alpha(hypp, xtp, ztp, N, reg=True)
+    E, nm = 12000, 7
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = -0.3 + 11.0 * O.halton(E, 7)                      # some start below 0 (lost at once), some beyond r = 0.5
+    out = C.applymap_alpha(3, nm, q0, p0, hyp[:3], hypp[:3], xtp[:N], xtp[N:], alphap, xt[:N], xt[N:], alpha,
+                           want_notconv=True, start_delta=delta)
+    qr, pr, maxres = out[0], out[1], out[-1]
+    good = maxres < 1e-10
+    q, p, st = api.applymap_tok(nm, E, hyp[:3], hypp[:3], q0, p0, xtp, None, None, xt, None, None, solver=solver, alphap=alphap,
+                                alpha=alpha, return_stats=True)
+    lost_ref = np.isnan(pr[-1])
+    assert 0.05 * E < lost_ref.sum() < 0.8 * E, lost_ref.sum()          # the ensemble does lose orbits, and not all of them
+    assert good.sum() > 0.6 * E, good.sum()
+    assert np.array_equal(np.isnan(p[:, good]), np.isnan(pr[:, good]))
+    assert np.array_equal(np.isnan(q[:, good]), np.isnan(qr[:, good]))
+    fin = ~np.isnan(pr)
+    dist = np.where(fin, np.maximum(_wrapdist(np.nan_to_num(q), np.nan_to_num(qr)), np.abs(np.nan_to_num(p) - np.nan_to_num(pr))), 0.0)
+    assert dist[:, good].max() < 1e-8, dist[:, good].max()
+
+
+def test_applymap_tok_f2py_follows_the_python_loss_semantics(api, O, C):
+    """sympgpr.applymap_tok through the f2py-signature entry point follows the AUTHORITATIVE Python loop
+    (05_tokamak/SympGPR/func.py:182-211): a lost orbit is NaN in q and p from the step it is lost; the Fortran
+    twin's loss test is a no-op `continue` (sympgpr.f90:161-163) -- a deliberate choice, DESIGN.md 1 / INTEGRATION.md."""
+    from sympgpr_b200 import workloads as W
+    N = 64
+    d = W.tokamak_training(N)
+    hyp = W.aniso_hyp(N, d["sig"], 2 * np.pi, 9.4, 1.5, 1e-8)
+    hypp = W.aniso_hyp(N, d["sigp"], 2 * np.pi, 9.4, 1.5, 1e-8)
+    xt, zt, xtp, ztp = d["xtrain"], d["ztrain"], d["xtrainp"], d["ztrainp"]
+    Kyinv = np.linalg.inv(O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp[:3]) + hyp[3] * np.eye(2 * N))
+    Kyinvp = np.linalg.inv(O.buildkreg_vec(xtp[:N], xtp[N:], xtp[:N], xtp[N:], hypp[:3]) + hypp[3] * np.eye(N))
+    q0 = np.array([0.3, 1.0, 2.0, 0.1])
+    p0 = np.array([3.0, -0.2, 5.0, 17.5])          # orbit 1 starts at P < 0, orbit 3 beyond r = 0.5
+    nm, E = 4, 4
+    qmap = np.zeros((nm, E, 1), order="F")
+    pmap = np.zeros((nm, E, 1), order="F")
+    api.applymap_tok_f2py(hyp[:3], hypp[:3], q0, p0, xtp[:N], xtp[N:], ztp, Kyinvp, xt[:N], xt[N:], zt, Kyinv, qmap, pmap)
+    assert np.isfinite(qmap[:, 0, 0]).all() and np.isfinite(pmap[:, 2, 0]).all()
+    assert qmap[0, 1, 0] == q0[1] and pmap[0, 3, 0] == p0[3]             # row 0 = initial conditions
+    assert np.isnan(qmap[1:, 1, 0]).all() and np.isnan(pmap[1:, 1, 0]).all()
+    assert np.isnan(qmap[1:, 3, 0]).all() and np.isnan(pmap[1:, 3, 0]).all()
+
+
+# ------------------------------------------------------------------------------- alpha cache of the scalar entry points
+def test_scalar_entry_points_cache_alpha(api, O, C):
+    """calcp / calcq / guessp called in a loop with the same (Kyinv, ztrain) arrays upload the inverse once
+    (sgp_alpha_cache_stats); a changed matrix is noticed (sampled checksum) and gives the new result."""
+    from sympgpr_b200 import _lib
+    N = 40
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8); hyp[:2] *= 2
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8); hypp[:2] *= 2
+    xt, zt, xtp, ztp = d["xtrain"], d["ztrain"], d["xtrainp"], d["P"].copy()
+    hypp[2] = 2 * np.amax(np.abs(ztp))**2
+    Kyinv = np.linalg.inv(O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp[:3]) + hyp[3] * np.eye(2 * N))
+    Kyinvp = np.linalg.inv(O.buildkreg_vec(xtp[:N], xtp[N:], xtp[:N], xtp[N:], hypp[:3]) + hypp[3] * np.eye(N))
+
+    def stats():
+        h, m = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+        _lib.check(_lib.lib().sgp_alpha_cache_stats(_lib.context().handle, ctypes.byref(h), ctypes.byref(m)), "stats")
+        return h.value, m.value
+    h0, m0 = stats()
+    qs, ps = 0.5 + O.halton(6, 5) * 5.0, 1.5 + O.halton(6, 7) * 3.0
+    vals = []
+    for q, p in zip(qs, ps):
+        P = api.calcP(q, p, hyp[:3], hypp[:3], xtp, ztp, Kyinvp, xt, zt, Kyinv)          # C-ordered Kyinv: a fresh copy per call
+        dq = api.calcQ(q, P, xt, hyp[:3], Kyinv, zt)
+        pg = api.guessP(q, p, hypp[:3], xtp, ztp, Kyinvp)
+        Pr, info, _ = C.calcp_alpha(q, p, hyp[:3], hypp[:3], xtp[:N], xtp[N:], Kyinvp @ ztp, xt[:N], xt[N:], Kyinv @ zt)
+        assert abs(P - Pr) < 1e-9 and abs(pg - O.guessp(q, p, hypp[:3], xtp[:N], xtp[N:], ztp, Kyinvp)) < 1e-10
+        vals.append((P, dq, pg))
+    h1, m1 = stats()
+    assert m1 - m0 == 2, (m0, m1)                  # one upload per matrix, not per call
+    assert h1 - h0 == 4 * len(qs) - 2
+    K2 = Kyinv.copy()
+    K2[3, 3] *= 1.5
+    dq2 = api.calcQ(qs[0], vals[0][0], xt, hyp[:3], K2, zt)
+    assert stats()[1] == m1 + 1
+    assert abs(dq2 - O.calcq(qs[0], vals[0][0], xt[:N], xt[N:], hyp[:3], K2, zt)) < 1e-10
+    assert abs(dq2 - vals[0][1]) > 1e-12
+
+
+def test_negative_length_scales_are_accepted(api, O):
+    """The kernels depend on l^2 only (kernels.f90:9-10), so the reference accepts negative length scales; value as for
+    |l|, gradient odd in the negated scale (an optimiser on raw hyper-parameters, python/02_pert_pendulum/main.py:53-58)."""
+    N = 60
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    hn = hyp.copy(); hn[0] = -hn[0]
+    v, g = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    vn, gn = api.nll_grad(hn, d["xtrain"], d["ztrain"], 2 * N)
+    vr, gr = O.nll_grad(hn, d["xtrain"], d["ztrain"], 2 * N)
+    assert np.isclose(vn, v, rtol=1e-12) and np.isclose(vn, vr, rtol=1e-9)
+    assert np.allclose(gn, gr, rtol=1e-9, atol=1e-9 * np.abs(gr).max())
+    assert np.isclose(gn[0], -g[0], rtol=1e-10) and np.isclose(gn[1], g[1], rtol=1e-10)
+    with pytest.raises(ValueError):
+        api.nll_chol([0.0, 1.0, 1.0, 1e-8], d["xtrain"], d["ztrain"], 2 * N)
+
+
+# ------------------------------------------------------------------------------- device-resident ensembles
+def test_device_map_model_equals_host_buffer_path(api, O):
+    """ensemble.DeviceMapModel (torch tensors in, torch tensors out, nothing leaves the GPU) launches the same kernel on the
+    same data as api.applymap with host buffers: bit-identical final states."""
+    import torch
+    from sympgpr_b200 import ensemble as En
+    N = 150
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8); hyp[:2] *= 2
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8); hypp[:2] *= 2
+    alpha = O.fit_alpha(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    alphap = O.fit_alpha(hypp, d["xtrainp"], d["ztrainp"], N, reg=True)
+    E, S = 1000, 9
+    q0 = O.halton(E, 5) * 2 * np.pi
+    p0 = 1.0 + O.halton(E, 7) * 4.0
+    qh, ph = api.applymap_standard(S + 1, E, hyp[:3], hypp[:3], q0, p0, d["xtrainp"], None, None, d["xtrain"], None, None,
+                                   solver="newton_delta", alphap=alphap, alpha=alpha, out_every=0, want_pdiff=False)
+    dev = torch.device("cuda", 0)
+    m = En.DeviceMapModel(hyp[:3], hypp[:3], d["xtrainp"], alphap, d["xtrain"], alpha, device=dev)
+    from sympgpr_b200 import _lib
+    side = torch.cuda.Stream(device=dev)                      # (kept alive until the context has let go of it)
+    with torch.cuda.stream(side):
+        qd, pd = m.applymap(torch.from_numpy(q0).to(dev), torch.from_numpy(p0).to(dev), S, kind="standard", solver="newton_delta")
+        side.synchronize()
+    _lib.context(0).set_stream(None)
+    qd2, pd2 = m.applymap(torch.from_numpy(q0).to(dev), torch.from_numpy(p0).to(dev), S, kind="standard", solver="newton_delta")
+    torch.cuda.synchronize()
+    m.close()
+    assert np.array_equal(qd.cpu().numpy(), qh) and np.array_equal(pd.cpu().numpy(), ph)
+    assert np.array_equal(qd2.cpu().numpy(), qh) and np.array_equal(pd2.cpu().numpy(), ph)
+
+
+def test_sobol_on_device_ishigami(api):
+    """ensemble.sobol_indices_sharded(on_device=True): sample rows generated on the GPU, model evaluated there, estimator
+    sums accumulated there -- against the analytic Sobol indices of the Ishigami function (a = 7, b = 0.1) and against the
+    host (NumPy) path of the same function on the same rows."""
+    import torch
+    from sympgpr_b200 import ensemble as En
+    dev = torch.device("cuda", 0)
+    a, b = 7.0, 0.1
+
+    def ish_t(X):
+        return torch.sin(X[:, 0]) + a * torch.sin(X[:, 1])**2 + b * X[:, 2]**4 * torch.sin(X[:, 0])
+
+    def ish_n(X):
+        return np.sin(X[:, 0]) + a * np.sin(X[:, 1])**2 + b * X[:, 2]**4 * np.sin(X[:, 0])
+    bounds = [(-np.pi, np.pi)] * 3
+    n = 1 << 18
+    r = En.sobol_indices_sharded(ish_t, bounds, n, device=dev, on_device=True, block=1 << 16)
+    V = a**2 / 8 + b * np.pi**4 / 5 + b**2 * np.pi**8 / 18 + 0.5
+    S1 = np.array([0.5 * (1 + b * np.pi**4 / 5)**2, a**2 / 8, 0.0]) / V
+    ST = np.array([0.5 * (1 + b * np.pi**4 / 5)**2 + 8 * b**2 * np.pi**8 / 225, a**2 / 8, 8 * b**2 * np.pi**8 / 225]) / V
+    assert np.allclose(r["S1"], S1, atol=5e-3), (r["S1"], S1)
+    assert np.allclose(r["ST"], ST, atol=5e-3), (r["ST"], ST)
+    assert abs(r["var"] - V) < 2e-2 * V and r["n_used"] == n
+    rh = En.sobol_indices_sharded(ish_n, bounds, n, block=1 << 16)
+    assert np.allclose(r["S1"], rh["S1"], atol=1e-9) and np.allclose(r["ST"], rh["ST"], atol=1e-9)
+
+
+def test_sobol_of_the_learned_map_on_device(api, O):
+    """The bench's Sobol leg in small: indices of the action after S steps of a learned tokamak-kind map w.r.t. the initial
+    conditions, device path against the host path (api.applymap_tok with host buffers) on the same rows; lost orbits are
+    dropped from every estimator in both."""
+    import torch
+    from sympgpr_b200 import ensemble as En, workloads as W
+    N = 200
+    d = W.tokamak_training(N)
+    hyp = W.aniso_hyp(N, d["sig"], 2 * np.pi, 9.4, 1.5, 1e-8)
+    hypp = W.aniso_hyp(N, d["sigp"], 2 * np.pi, 9.4, 1.5, 1e-8)
+    f = api.fit(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    fp = api.fit(hypp, d["xtrainp"], d["ztrainp"], N, reg=True)
+    dev = torch.device("cuda", 0)
+    m = En.DeviceMapModel(hyp[:3], hypp[:3], d["xtrainp"], fp["alpha"], d["xtrain"], f["alpha"], device=dev)
+    S = 5
+
+    def model_t(X):
+        return m.applymap(X[:, 0].contiguous(), X[:, 1].contiguous(), S, kind="tokamak", solver="newton_delta")[1]
+
+    def model_n(X):
+        out = api.applymap_tok(S + 1, X.shape[0], hyp[:3], hypp[:3], X[:, 0], X[:, 1], d["xtrainp"], None, None, d["xtrain"], None, None,
+                               solver="newton_delta", alphap=fp["alpha"], alpha=f["alpha"], out_every=0)
+        return out[1]
+    bounds = [(0.0, 2 * np.pi), (0.2, 10.5)]
+    n = 20000
+    r = En.sobol_indices_sharded(model_t, bounds, n, device=dev, on_device=True, block=8192)
+    rh = En.sobol_indices_sharded(model_n, bounds, n, block=8192)
+    m.close()
+    from sympgpr_b200 import _lib
+    _lib.context(0).set_stream(None)
+    assert 0 < r["n_used"] < n                                           # some rows lose their orbit
+    assert r["n_used"] == rh["n_used"]
+    assert np.allclose(r["S1"], rh["S1"], atol=1e-10) and np.allclose(r["ST"], rh["ST"], atol=1e-10)
+    assert r["ST"][1] > 0.5                                              # the final action is mostly the initial action

@@ -11,7 +11,8 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsympgpr_b200.so")
+# SYMPGPR_B200_LIB: load another build of the same library (kernel experiments, tools/build_variant.py)
+LIB_PATH = os.environ.get("SYMPGPR_B200_LIB") or os.path.join(_HERE, "libsympgpr_b200.so")
 
 c_dp = ctypes.POINTER(ctypes.c_double)
 c_ullp = ctypes.POINTER(ctypes.c_ulonglong)

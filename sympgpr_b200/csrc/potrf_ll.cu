@@ -140,71 +140,6 @@ __device__ __forceinline__ void ll_consume(double (&acc)[8][4][2], int nk, uint3
     if (MATVEC) *vout = v;
 }
 
-// (unblocked variant, used by the kernel instantiation for large matrices)
-// Cholesky factor and inverse of the 128 x 128 tile held in shared memory S[r*LL_LD + c] (lower part),
-// by the 256 consumer threads.  Unblocked right-looking factorisation, then the unblocked inverse of
-// the triangular factor (last column first).  Returns this thread's share of sum(log diag L).
-__device__ void diag_tile_factor(double* S, double* tmp, int tid, int* info, int col0, double& mylog)
-{
-    const int r = tid & (TILE - 1);
-    const int part = tid >> 7;                   // 0/1: columns c with (c - j - 1) % 2 == part
-    double* Sr = S + r * LL_LD;
-    mylog = 0.0;
-    for (int j = 0; j < TILE; j++) {
-        double d = S[j * LL_LD + j];
-        if (!(d > 0.0)) {                        // also NaN
-            if (tid == 0) atomicCAS(info, 0, col0 + j + 1);
-            d = 1.0;
-        }
-        const double dj = sqrt(d);
-        const double inv = 1.0 / dj;
-        consumer_bar();                          // everyone has read S[j][j]
-        if (part == 0) {
-            if (r > j) Sr[j] *= inv;
-            else if (r == j) { Sr[j] = dj; mylog = log(dj); }
-        }
-        consumer_bar();
-        if (r > j) {
-            const double lrj = Sr[j];
-            int c = j + 1 + part;
-            for (; c + 6 <= r; c += 8) {
-                const double l0 = S[c * LL_LD + j], l1 = S[(c + 2) * LL_LD + j], l2 = S[(c + 4) * LL_LD + j], l3 = S[(c + 6) * LL_LD + j];
-                const double s0 = Sr[c], s1 = Sr[c + 2], s2 = Sr[c + 4], s3 = Sr[c + 6];
-                Sr[c] = s0 - lrj * l0; Sr[c + 2] = s1 - lrj * l1; Sr[c + 4] = s2 - lrj * l2; Sr[c + 6] = s3 - lrj * l3;
-            }
-            for (; c <= r; c += 2) Sr[c] -= lrj * S[c * LL_LD + j];
-        }
-        consumer_bar();                          // S[j+1][j+1] final before the next pivot is read
-    }
-}
-
-__device__ void diag_tile_invert(double* S, double* tmp, int tid)
-{
-    const int r = tid & (TILE - 1);
-    const int part = tid >> 7;
-    double* Sr = S + r * LL_LD;
-    // X[j][j] = 1/L[j][j];  X[j+1:, j] = -X[j+1:, j+1:] * L[j+1:, j] * X[j][j]
-    for (int j = TILE - 1; j >= 0; j--) {
-        const double xjj = 1.0 / S[j * LL_LD + j];
-        double p0 = 0.0, p1 = 0.0;
-        if (r > j) {
-            int k = j + 1 + part;
-            for (; k + 2 <= r; k += 4) {
-                p0 += Sr[k] * S[k * LL_LD + j];
-                p1 += Sr[k + 2] * S[(k + 2) * LL_LD + j];
-            }
-            for (; k <= r; k += 2) p0 += Sr[k] * S[k * LL_LD + j];
-        }
-        tmp[tid] = p0 + p1;
-        consumer_bar();                          // all reads of column j (still L) done
-        if (part == 0) {
-            if (r > j) Sr[j] = -(tmp[r] + tmp[r + TILE]) * xjj;
-            else if (r == j) Sr[j] = xjj;
-        }
-        consumer_bar();
-    }
-}
-
 // ---------------------------------------------------------------------------------------------------------
 // Diagonal tile: Cholesky factor L and inverse X = L^-1 of a 128 x 128 block in shared memory, blocked 4 x 4
 // with 32 x 32 blocks so that block-wide barriers are per PHASE (about 30), not per column (the unblocked
@@ -216,6 +151,14 @@ __device__ void diag_tile_invert(double* S, double* tmp, int tid)
 //   then per block row bi = 1..3:  T = sum_k L(bi,k) X(k, 0..bi-1),  X(bi, 0..bi-1) = -X_bibi T.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int DB = 32;
+
+// unroll factor of the 16-step column loops of the two warp-level 32 x 32 routines below (measured: see DESIGN.md 4)
+#ifndef LL_UNR
+#define LL_UNR 1
+#endif
+#define LL_STR2(x) #x
+#define LL_STR(x) LL_STR2(x)
+#define LL_UNROLL _Pragma(LL_STR(unroll LL_UNR))
 
 
 // warp 0 only.  Factor the diagonal block at k0 in place (lower), write its inverse transposed into the block's strict
@@ -241,7 +184,7 @@ __device__ __noinline__ void warp_factor32(double* S, int k0, double* xd, int* i
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const int NC = half == 0 ? DB : DB / 2;              // live register slots in this half
-#pragma unroll 1
+        LL_UNROLL
         for (int j = half * (DB / 2); j < (half + 1) * (DB / 2); j++) {
             double d = __shfl_sync(FULL, row[0], j);
             const bool neg = !(d > 0.0);                     // also NaN
@@ -280,7 +223,7 @@ __device__ __noinline__ void warp_invert32(double* S, int k0, const double* xd)
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const int NC = half == 0 ? DB / 2 : DB;
-#pragma unroll 1
+        LL_UNROLL
         for (int k = half * (DB / 2); k < (half + 1) * (DB / 2); k++) {
             const double lnext = Sr[(k + 1) & 31];           // L(r, k+1): off the dependent chain
             const double sc = (lane == k) ? myinv : 1.0;
@@ -301,31 +244,87 @@ __device__ __noinline__ void warp_invert32(double* S, int k0, const double* xd)
     __syncwarp();
 }
 
-// all 256 consumer threads; S lower = matrix on entry, L on exit; upper/xd = X^T; scratch: >= 32*96 doubles
-__device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, double* scratch, int tid, int* info, int col0, double* logout,
-                                        unsigned long long* stamp)
+// named barrier over the first NWARPS... a group of GROUP threads (all of them must call it): id 1 = the 8 consumer warps
+template <int BARID, int GROUP>
+__device__ __forceinline__ void group_bar() { asm volatile("bar.sync %0, %1;\n" ::"n"(BARID), "n"(GROUP) : "memory"); }
+
+// Off-diagonal blocks of the tile inverse by DMMA, block rows bi0 .. bi1, by a group of NWARPS warps (wid = index of the
+// calling warp inside the group, BARID = the group's named barrier; 8 x 8 output tiles handed out round-robin).  For block
+// row bi (rows r0 = 32 bi ...), with X known for the rows above and for the diagonal block bi:
+//     T(rr, c)      =  sum_{k = c .. r0-1} L(r0+rr, k) X(k, c)           (32 x r0, into scratch[c*32 + rr])
+//     X(r0+rr, c)   = -sum_{q <= rr} X_bibi(rr, q) T(q, c)               (stored transposed: S[c*LL_LD + r0+rr])
+// Fragments come straight from the tile's storage (X transposed in the strict upper triangle, diagonal in xd), so the
+// triangular structure is a select per operand.  The scalar version of this phase took 31 us per tile and sat on the
+// critical path of the whole factorisation (every tile (i,j) waits for Dinv_j); as 8 x 8 x 4 DMMAs it is a few us.
+template <int NWARPS, int BARID>
+__device__ __forceinline__ void tile_inverse_offdiag(double* S, const double* xd, double* scratch, int wid, int lane, int bi0, int bi1)
 {
-    // per block column kb:  warp 0 factors the 32 x 32 diagonal block;  then, at the same time,
-    //   warp 0    : inverse of that block (needed only for the inverse of the whole tile, below)
-    //   warps 1-7 : panel L(i, kb) = A(i, kb) L_kk^-T by forward substitution (one thread per row, in place), then the
-    //               trailing update A(i, c) -= L(i, kb) L(c, kb)^T
-    // so the block inverse is off the critical path of the tile (it took as long as the block factorisation).
-    const int wtid = tid - 32;                               // index among the 224 threads of warps 1-7
-    constexpr int NW = LL_CONSUMERS - 32;
+    const int g = lane >> 2, t = lane & 3;
+    for (int bi = bi0; bi <= bi1; bi++) {
+        const int r0 = bi * DB;
+        const int ntile = (DB / 8) * (r0 / 8);                   // 4 x (4 bi) output tiles of 8 x 8
+        for (int tl = wid; tl < ntile; tl += NWARPS) {
+            const int mi = tl & 3, ni = tl >> 2;
+            const int c = ni * 8 + g;                            // this lane's B column
+            const double* La = S + (r0 + mi * 8 + g) * LL_LD;    // this lane's A row: L(r0 + rr, .)
+            const double* Xc = S + c * LL_LD;                    // Xc[k] = X(k, c) for k > c
+            const double xcc = xd[c];
+            double c0 = 0.0, c1 = 0.0;
+            for (int kk = ni * 8; kk < r0; kk += 4) {
+                const int k = kk + t;
+                double b = (k > c) ? Xc[k] : 0.0;
+                b = (k == c) ? xcc : b;
+                dmma884(c0, c1, La[k], b);
+            }
+            scratch[(ni * 8 + 2 * t) * DB + mi * 8 + g] = c0;
+            scratch[(ni * 8 + 2 * t + 1) * DB + mi * 8 + g] = c1;
+        }
+        group_bar<BARID, NWARPS * 32>();
+        for (int tl = wid; tl < ntile; tl += NWARPS) {
+            const int mi = tl & 3, ni = tl >> 2;
+            const int rr = mi * 8 + g;                           // this lane's A row: X_bibi(rr, .)
+            const double* Tc = scratch + (ni * 8 + g) * DB;      // this lane's B column: T(., c)
+            const double xrr = xd[r0 + rr];
+            double c0 = 0.0, c1 = 0.0;
+            for (int kk = 0; kk < mi * 8 + 8; kk += 4) {
+                const int q = kk + t;
+                double a = (q < rr) ? S[(r0 + q) * LL_LD + r0 + rr] : 0.0;
+                a = (q == rr) ? xrr : a;
+                dmma884(c0, c1, a, Tc[q]);
+            }
+            S[(ni * 8 + 2 * t) * LL_LD + r0 + rr] = -c0;
+            S[(ni * 8 + 2 * t + 1) * LL_LD + r0 + rr] = -c1;
+        }
+        group_bar<BARID, NWARPS * 32>();
+    }
+}
+
+// all 256 consumer threads; S lower = matrix on entry, L on exit; upper/xd = X^T; scratch: >= 32*96 doubles; logs: 128 doubles
+//   per block column kb (two phases, one block-wide barrier each):
+//     phase 1   warp 0: Cholesky of the 32 x 32 diagonal block kb (register-resident, shuffles)
+//               warp 1: inverse of diagonal block kb-1 -- one step behind: the block inverses are needed only by the tile
+//                       inverse at the end, so they never sit on the chain of block factorisations
+//     phase 2   all:    panel L(i, kb) = A(i, kb) L_kk^-T by forward substitution (one thread per row, in place), barrier,
+//                       trailing update A(i, c) -= L(i, kb) L(c, kb)^T as 8 x 8 x 4 DMMAs on the lower 8 x 8 tiles
+//   then the inverse of the tile: warp 0 inverts the last diagonal block while warps 1-7 form block rows 1 and 2 of the
+//   off-diagonal part; block row 3 by all eight warps.
+__device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, double* scratch, double* logs, int tid, int* info, int col0,
+                                                     double* logout, unsigned long long* stamp)
+{
+    const int warp = tid >> 5, lane = tid & 31, g = lane >> 2, t = lane & 3;
     for (int kb = 0; kb < TILE / DB; kb++) {
         const int k0 = kb * DB, R0 = k0 + DB, nrows = TILE - R0;
         unsigned long long tw0 = 0ull;
         if (stamp && tid == 0) tw0 = globaltimer();
         __syncwarp();                                        // (trace only diverges lane 0: re-converge, or the shuffles take their slow path)
-        if (tid < 32) warp_factor32(S, k0, xd, info, col0);
+        if (warp == 0) warp_factor32(S, k0, xd, info, col0);
+        else if (warp == 1 && kb > 0) warp_invert32(S, k0 - DB, xd);
         if (stamp && tid == 0) stamp[3] += globaltimer() - tw0;      // trace: time in the warp-level block factorisations
         consumer_bar();
-        if (tid < 32) {
-            warp_invert32(S, k0, xd);
-        } else if (nrows > 0) {
-            if (wtid < nrows) {
+        if (nrows > 0) {
+            if (tid < nrows) {
                 // row i of the panel: l_c = (a_c - sum_{k<c} l_k L_kk(c,k)) / L_kk(c,c), in place (the row is this thread's own)
-                double* Ai = S + (R0 + wtid) * LL_LD + k0;
+                double* Ai = S + (R0 + tid) * LL_LD + k0;
                 for (int c = 0; c < DB; c++) {
                     const double* Lc = S + (k0 + c) * LL_LD + k0;
                     double s0 = Ai[c], s1 = 0.0;
@@ -338,85 +337,50 @@ __device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, doub
                     Ai[c] = (s0 + s1) * xd[k0 + c];
                 }
             }
-            asm volatile("bar.sync 2, %0;\n" ::"n"(NW) : "memory");        // warps 1-7: the panel is complete
-            // trailing update: A(i, c) -= sum_k L(i, k0+k) L(c, k0+k) for R0 <= c <= i; 1 row x 4 columns per item
-            const int ncg = nrows / 4;
-            for (int idx = wtid; idx < nrows * ncg; idx += NW) {
-                const int i = R0 + idx % nrows, c0 = R0 + 4 * (idx / nrows);
-                if (c0 > i) continue;
-                const double* Li = S + i * LL_LD + k0;
-                const double* Lc = S + c0 * LL_LD + k0;
-                double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-#pragma unroll 8
-                for (int k = 0; k < DB; k++) {
-                    const double l = Li[k];
-                    s0 = fma(l, Lc[k], s0);
-                    s1 = fma(l, Lc[LL_LD + k], s1);
-                    s2 = fma(l, Lc[2 * LL_LD + k], s2);
-                    s3 = fma(l, Lc[3 * LL_LD + k], s3);
-                }
-                double* Ai = S + i * LL_LD + c0;
+            consumer_bar();                                  // the panel is complete
+            // trailing update A(i, c) -= sum_k L(i, k0+k) L(c, k0+k), R0 <= c <= i: lower 8 x 8 tiles, 8 DMMAs each
+            const int nb = nrows / 8, ntl = nb * (nb + 1) / 2;
+            for (int tl = warp; tl < ntl; tl += WS_CONSUMER_WARPS) {
+                int mi = (int)((sqrtf(8.0f * (float)tl + 1.0f) - 1.0f) * 0.5f);
+                while ((mi + 1) * (mi + 2) / 2 <= tl) mi++;
+                while (mi * (mi + 1) / 2 > tl) mi--;
+                const int ni = tl - mi * (mi + 1) / 2;
+                const double* La = S + (R0 + mi * 8 + g) * LL_LD + k0 + t;     // A(row g, k t)
+                const double* Lb = S + (R0 + ni * 8 + g) * LL_LD + k0 + t;     // B(k t, col g) = L(R0 + 8 ni + g, k)
+                double c0 = 0.0, c1 = 0.0;
+#pragma unroll
+                for (int kk = 0; kk < DB; kk += 4) dmma884(c0, c1, La[kk], Lb[kk]);
+                const int i = R0 + mi * 8 + g, c = R0 + ni * 8 + 2 * t;
                 // (entries above the diagonal belong to the X^T storage of the diagonal blocks: only c <= i is written)
-                Ai[0] -= s0;
-                if (c0 + 1 <= i) Ai[1] -= s1;
-                if (c0 + 2 <= i) Ai[2] -= s2;
-                if (c0 + 3 <= i) Ai[3] -= s3;
+                if (c <= i) S[i * LL_LD + c] -= c0;
+                if (c + 1 <= i) S[i * LL_LD + c + 1] -= c1;
             }
+            consumer_bar();
         }
-        consumer_bar();
     }
-    // sum(log diag L) = -sum(log xd): one log per thread, fixed-order reduction
-    if (tid < TILE) scratch[tid] = -log(xd[tid]);
-    consumer_bar();
-    if (tid == 0) {
-        double sl = 0.0;
-        for (int k = 0; k < TILE; k++) sl += scratch[k];
-        *logout = sl;
-    }
+    // sum(log diag L) = -sum(log xd): one log per thread, fixed-order reduction by warp 0
+    if (tid < TILE) logs[tid] = -log(xd[tid]);
     consumer_bar();
     if (stamp && tid == 0) *stamp = globaltimer();           // factor done (trace only)
-    // off-diagonal blocks of the inverse, block row by block row
-    for (int bi = 1; bi < TILE / DB; bi++) {
-        const int r0 = bi * DB, ncols = r0;                  // X(bi, 0..bi-1): 32 x ncols
-        // T(rr, c) = sum_{k = c .. r0-1} L(r0+rr, k) X(k, c)
-        for (int idx = tid; idx < DB * ncols; idx += LL_CONSUMERS) {
-            const int rr = idx % DB, c = idx / DB;
-            const double* Lr = S + (r0 + rr) * LL_LD;
-            double s0 = Lr[c] * xd[c], s1 = 0.0, s2 = 0.0, s3 = 0.0;
-            const double* Xc = S + c * LL_LD;                // Xc[k] = X(k, c), k > c
-            int k = c + 1;
-            for (; k + 3 < r0; k += 4) {
-                s0 = fma(Lr[k], Xc[k], s0);
-                s1 = fma(Lr[k + 1], Xc[k + 1], s1);
-                s2 = fma(Lr[k + 2], Xc[k + 2], s2);
-                s3 = fma(Lr[k + 3], Xc[k + 3], s3);
-            }
-            for (; k < r0; k++) s0 = fma(Lr[k], Xc[k], s0);
-            scratch[c * DB + rr] = (s0 + s1) + (s2 + s3);
-        }
-        consumer_bar();
-        // X(r0+rr, c) = - sum_{q <= rr} X_bibi(rr, q) T(q, c)
-        for (int idx = tid; idx < DB * ncols; idx += LL_CONSUMERS) {
-            const int rr = idx % DB, c = idx / DB;
-            const double* Tc = scratch + c * DB;
-            double s0 = xd[r0 + rr] * Tc[rr], s1 = 0.0;
-            int q = 0;
-            for (; q + 1 < rr; q += 2) {
-                s0 = fma(S[(r0 + q) * LL_LD + r0 + rr], Tc[q], s0);
-                s1 = fma(S[(r0 + q + 1) * LL_LD + r0 + rr], Tc[q + 1], s1);
-            }
-            if (q < rr) s0 = fma(S[(r0 + q) * LL_LD + r0 + rr], Tc[q], s0);
-            S[c * LL_LD + r0 + rr] = -(s0 + s1);
-        }
-        consumer_bar();
+    __syncwarp();
+    if (warp == 0) {
+        double sl = (logs[lane] + logs[lane + 32]) + (logs[lane + 64] + logs[lane + 96]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sl += __shfl_xor_sync(0xffffffffu, sl, o);
+        if (lane == 0) *logout = sl;
+        warp_invert32(S, TILE - DB, xd);
+    } else {
+        tile_inverse_offdiag<WS_CONSUMER_WARPS - 1, 2>(S, xd, scratch, warp - 1, lane, 1, 2);
     }
+    consumer_bar();
+    tile_inverse_offdiag<WS_CONSUMER_WARPS, 1>(S, xd, scratch, warp, lane, 3, 3);
 }
 
 // TRACE: record per-task time stamps (tools/ll_trace.py); a separate instantiation so that the production
 // kernel carries no trace state through the register-tight main loop
-// BLOCKED: diagonal tiles by the blocked routine (default; its two helpers are __noinline__ so that their register
-// allocation stays out of the DMMA main loop: 0 bytes spilled) or by the unblocked one (kept for comparison).
-template <bool TRACE, bool BLOCKED>
+// (the helpers of the diagonal tile are __noinline__ so that their register allocation stays out of the DMMA main loop:
+// 0 bytes spilled)
+template <bool TRACE>
 __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
 {
     extern __shared__ __align__(16) double smem[];
@@ -514,16 +478,11 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
                 }
             }
             consumer_bar();
-            if (BLOCKED) {
             double* xd = tmp + 3 * TILE;                     // diagonal of the inverse
             double* scratch = tmp + 4 * TILE;                // 32 x 96 doubles
             if (TRACE && dbg && tid == 0) dbg[2] = globaltimer();       // S built
-            diag_tile_factor_invert(S, xd, scratch, tid, a.info, j * TILE, a.logparts + j, (TRACE && dbg) ? dbg + 3 : nullptr);
+            diag_tile_factor_invert(S, xd, scratch, tmp, tid, a.info, j * TILE, a.logparts + j, (TRACE && dbg) ? dbg + 3 : nullptr);
             if (TRACE && dbg && tid == 0) dbg[4] = globaltimer();       // factored and inverted
-            for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
-                const int rr = idx & (TILE - 1), c = idx >> 7;
-                tile[rr + (long)c * a.lda] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
-            }
             if (solve) {
                 // w_j = X (y_j - v_j); the two k-halves of v_j are in vpart
                 tmp[tid] = vpart;
@@ -536,55 +495,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
                     a.w[(long)j * TILE + tid] = sacc;
                 }
             }
+            // Dinv_j (and w_j) first: they are all that the tiles below and the later diagonal tasks wait for.  L(j,j) itself
+            // is read by no task of this kernel (only off-diagonal tiles are operands), so its store comes after the flag.
             double* Dj = a.Dinv + (long)j * TILE * TILE;
             for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
                 const int rr = idx & (TILE - 1), c = idx >> 7;
                 Dj[rr + c * TILE] = (rr > c) ? S[c * LL_LD + rr] : (rr == c ? xd[c] : 0.0);
             }
-            } else {
-            double mylog;
-            if (TRACE && dbg && tid == 0) dbg[2] = globaltimer();       // S built
-            diag_tile_factor(S, tmp, tid, a.info, j * TILE, mylog);
-            if (TRACE && dbg && tid == 0) dbg[3] = globaltimer();       // factored
+            __threadfence();
+            consumer_bar();                                  // Dinv_j and w_j stored and fenced
+            if (tid == 0) {
+                st_release(a.ready + j + (long)j * nt, 1);
+                if (TRACE && dbg) dbg[5] = globaltimer();
+            }
             for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
                 const int rr = idx & (TILE - 1), c = idx >> 7;
                 tile[rr + (long)c * a.lda] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
             }
-            if (tid < TILE) tmp[tid] = mylog;
-            consumer_bar();
-            if (tid == 0) {
-                double s = 0.0;
-                for (int k = 0; k < TILE; k++) s += tmp[k];
-                a.logparts[j] = s;
-            }
-            consumer_bar();
-            diag_tile_invert(S, tmp, tid);
-            if (TRACE && dbg && tid == 0) dbg[4] = globaltimer();       // inverted
-            if (solve) {
-                // w_j = L(j,j)^-1 (y_j - v_j); S holds L(j,j)^-1, the two k-halves of v_j are in vpart
-                tmp[tid] = vpart;
-                consumer_bar();
-                if (tid < TILE) tmp[2 * TILE + tid] = a.y[(long)j * TILE + tid] - (tmp[tid] + tmp[tid + TILE]);
-                consumer_bar();
-                if (tid < TILE) {
-                    double sacc = 0.0;
-                    for (int c = 0; c <= tid; c++) sacc = fma(S[tid * LL_LD + c], tmp[2 * TILE + c], sacc);
-                    a.w[(long)j * TILE + tid] = sacc;
-                }
-            }
-            double* Dj = a.Dinv + (long)j * TILE * TILE;
-            for (int idx = tid; idx < TILE * TILE; idx += LL_CONSUMERS) {
-                const int rr = idx & (TILE - 1), c = idx >> 7;
-                Dj[rr + c * TILE] = (rr >= c) ? S[rr * LL_LD + c] : 0.0;
-            }
-            }
-            __threadfence();
-            consumer_bar();                                  // all stores issued and fenced; S no longer used
-            if (tid == 0) {
-                st_release(a.ready + j + (long)j * nt, 1);
-                mbar_arrive(c2p);                            // the producer may refill the ring
-                if (TRACE && dbg) dbg[5] = globaltimer();
-            }
+            consumer_bar();                                  // S no longer used
+            if (tid == 0) mbar_arrive(c2p);                  // the producer may refill the ring
         } else {
             // ---- off-diagonal tile: C' = A(i,j) - acc, in place; then L(i,j) = C' Dinv_j^T through the ring
 #pragma unroll
@@ -641,10 +570,8 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
 {
     static bool configured = false;
     if (!configured) {
-        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
-        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
-        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
-        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
+        SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
         configured = true;
     }
     static_assert((size_t)TILE * LL_LD * sizeof(double) + (4 * TILE + 32 * 96) * sizeof(double) <= (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double),
@@ -670,13 +597,7 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     const unsigned grid = (unsigned)(ntasks < sms ? ntasks : sms);
     void* args[] = {&a};
-    // diagonal tiles by the blocked routine: the chain of diagonal tiles paces the factorisation up to n ~ 16k
-    // (n = 8192: 12.0 ms against 18.7 ms unblocked; n = 32 768: 344 against 348 ms).  SGP_LL_BLOCKED=0 selects the
-    // unblocked routine (measurements only).
-    static const char* force_blocked = getenv("SGP_LL_BLOCKED");
-    const bool blocked = force_blocked ? force_blocked[0] != '0' : true;
-    const void* kern = trace ? (blocked ? (const void*)potrf_ll_kernel<true, true> : (const void*)potrf_ll_kernel<true, false>)
-                             : (blocked ? (const void*)potrf_ll_kernel<false, true> : (const void*)potrf_ll_kernel<false, false>);
+    const void* kern = trace ? (const void*)potrf_ll_kernel<true> : (const void*)potrf_ll_kernel<false>;
     SGP_CUDA(cudaLaunchCooperativeKernel(kern, dim3(grid), dim3(WS_THREADS), args, LL_SMEM, c.stream));
     count_launch();
     if (trace) {

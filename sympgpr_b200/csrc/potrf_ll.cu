@@ -39,6 +39,8 @@ struct LLArgs {
     double* logparts;      // nt
     int* info;
     int* ready;            // nt*nt, ready[i + j*nt] = 1 once L(i,j) (and Dinv_j for i == j) is final
+    int* slab;             // nt*8: slab[j*8 + s] counts the warps (2) that have stored columns [16 s, 16 s + 16) of the
+                           // SUB-DIAGONAL tile L(j+1, j): the next diagonal task streams that tile slab by slab
     int* abort;
     // optional fused forward substitution  L w = y  (potrs, first half): the diagonal task of column j also
     // accumulates v_j = sum_{k<j} L(j,k) w_k from the slabs it streams anyway, then w_j = Dinv_j (y_j - v_j)
@@ -57,6 +59,21 @@ __device__ __forceinline__ void wait_ready(const int* flag, int* abort, int* inf
     unsigned n = 0;
     while (ld_acquire(flag) == 0) {
         __nanosleep(100);
+        if ((++n & 255u) == 0u) {
+            if (*(volatile int*)abort) return;
+            if (globaltimer() - t0 > 10000000000ull) { atomicExch(abort, 1); atomicExch(info, -1); return; }
+        }
+    }
+}
+
+// one lane spins until a counter has reached `need` (or abort)
+__device__ __forceinline__ void wait_count(const int* cnt, int need, int* abort, int* info)
+{
+    if (ld_acquire(cnt) >= need) return;
+    const unsigned long long t0 = globaltimer();
+    unsigned n = 0;
+    while (ld_acquire(cnt) < need) {
+        __nanosleep(40);
         if ((++n & 255u) == 0u) {
             if (*(volatile int*)abort) return;
             if (globaltimer() - t0 > 10000000000ull) { atomicExch(abort, 1); atomicExch(info, -1); return; }
@@ -154,7 +171,7 @@ constexpr int DB = 32;
 
 // unroll factor of the 16-step column loops of the two warp-level 32 x 32 routines below (measured: see DESIGN.md 4)
 #ifndef LL_UNR
-#define LL_UNR 1
+#define LL_UNR 2
 #endif
 #define LL_STR2(x) #x
 #define LL_STR(x) LL_STR2(x)
@@ -256,47 +273,85 @@ __device__ __forceinline__ void group_bar() { asm volatile("bar.sync %0, %1;\n" 
 // Fragments come straight from the tile's storage (X transposed in the strict upper triangle, diagonal in xd), so the
 // triangular structure is a select per operand.  The scalar version of this phase took 31 us per tile and sat on the
 // critical path of the whole factorisation (every tile (i,j) waits for Dinv_j); as 8 x 8 x 4 DMMAs it is a few us.
-template <int NWARPS, int BARID>
-__device__ __forceinline__ void tile_inverse_offdiag(double* S, const double* xd, double* scratch, int wid, int lane, int bi0, int bi1)
+// phase 1 of block row bi: T = L(bi, 0..bi-1) X(0..bi-1, 0..bi-1) into scratch (needs X of the rows above only)
+template <int NWARPS>
+__device__ __forceinline__ void tile_inverse_T(const double* S, const double* xd, double* scratch, int wid, int lane, int bi)
 {
     const int g = lane >> 2, t = lane & 3;
-    for (int bi = bi0; bi <= bi1; bi++) {
-        const int r0 = bi * DB;
-        const int ntile = (DB / 8) * (r0 / 8);                   // 4 x (4 bi) output tiles of 8 x 8
-        for (int tl = wid; tl < ntile; tl += NWARPS) {
-            const int mi = tl & 3, ni = tl >> 2;
-            const int c = ni * 8 + g;                            // this lane's B column
-            const double* La = S + (r0 + mi * 8 + g) * LL_LD;    // this lane's A row: L(r0 + rr, .)
-            const double* Xc = S + c * LL_LD;                    // Xc[k] = X(k, c) for k > c
-            const double xcc = xd[c];
-            double c0 = 0.0, c1 = 0.0;
-            for (int kk = ni * 8; kk < r0; kk += 4) {
-                const int k = kk + t;
-                double b = (k > c) ? Xc[k] : 0.0;
-                b = (k == c) ? xcc : b;
-                dmma884(c0, c1, La[k], b);
-            }
-            scratch[(ni * 8 + 2 * t) * DB + mi * 8 + g] = c0;
-            scratch[(ni * 8 + 2 * t + 1) * DB + mi * 8 + g] = c1;
+    const int r0 = bi * DB;
+    const int ntile = (DB / 8) * (r0 / 8);                       // 4 x (4 bi) output tiles of 8 x 8
+    for (int tl = wid; tl < ntile; tl += NWARPS) {
+        const int mi = tl & 3, ni = tl >> 2;
+        const int c = ni * 8 + g;                                // this lane's B column
+        const double* La = S + (r0 + mi * 8 + g) * LL_LD;        // this lane's A row: L(r0 + rr, .)
+        const double* Xc = S + c * LL_LD;                        // Xc[k] = X(k, c) for k > c
+        const double xcc = xd[c];
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;           // two chains: the k-range is a multiple of 8
+        for (int kk = ni * 8; kk < r0; kk += 8) {
+            const int k = kk + t, k2 = k + 4;
+            double b = (k > c) ? Xc[k] : 0.0;
+            b = (k == c) ? xcc : b;
+            double b2 = (k2 > c) ? Xc[k2] : 0.0;
+            b2 = (k2 == c) ? xcc : b2;
+            dmma884(c0, c1, La[k], b);
+            dmma884(d0, d1, La[k2], b2);
         }
-        group_bar<BARID, NWARPS * 32>();
-        for (int tl = wid; tl < ntile; tl += NWARPS) {
-            const int mi = tl & 3, ni = tl >> 2;
-            const int rr = mi * 8 + g;                           // this lane's A row: X_bibi(rr, .)
-            const double* Tc = scratch + (ni * 8 + g) * DB;      // this lane's B column: T(., c)
-            const double xrr = xd[r0 + rr];
-            double c0 = 0.0, c1 = 0.0;
-            for (int kk = 0; kk < mi * 8 + 8; kk += 4) {
-                const int q = kk + t;
-                double a = (q < rr) ? S[(r0 + q) * LL_LD + r0 + rr] : 0.0;
-                a = (q == rr) ? xrr : a;
-                dmma884(c0, c1, a, Tc[q]);
-            }
-            S[(ni * 8 + 2 * t) * LL_LD + r0 + rr] = -c0;
-            S[(ni * 8 + 2 * t + 1) * LL_LD + r0 + rr] = -c1;
-        }
-        group_bar<BARID, NWARPS * 32>();
+        scratch[(ni * 8 + 2 * t) * DB + mi * 8 + g] = c0 + d0;
+        scratch[(ni * 8 + 2 * t + 1) * DB + mi * 8 + g] = c1 + d1;
     }
+}
+
+// phase 2 of block row bi: X(bi, 0..bi-1) = -X_bibi T (needs the inverse of diagonal block bi)
+template <int NWARPS>
+__device__ __forceinline__ void tile_inverse_X(double* S, const double* xd, const double* scratch, int wid, int lane, int bi)
+{
+    const int g = lane >> 2, t = lane & 3;
+    const int r0 = bi * DB;
+    const int ntile = (DB / 8) * (r0 / 8);
+    for (int tl = wid; tl < ntile; tl += NWARPS) {
+        const int mi = tl & 3, ni = tl >> 2;
+        const int rr = mi * 8 + g;                               // this lane's A row: X_bibi(rr, .)
+        const double* Tc = scratch + (ni * 8 + g) * DB;          // this lane's B column: T(., c)
+        const double xrr = xd[r0 + rr];
+        double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
+        for (int kk = 0; kk < mi * 8 + 8; kk += 8) {
+            const int q = kk + t, q2 = q + 4;
+            double a = (q < rr) ? S[(r0 + q) * LL_LD + r0 + rr] : 0.0;
+            a = (q == rr) ? xrr : a;
+            double a2 = (q2 < rr) ? S[(r0 + q2) * LL_LD + r0 + rr] : 0.0;
+            a2 = (q2 == rr) ? xrr : a2;
+            dmma884(c0, c1, a, Tc[q]);
+            dmma884(d0, d1, a2, Tc[q2]);
+        }
+        S[(ni * 8 + 2 * t) * LL_LD + r0 + rr] = -(c0 + d0);
+        S[(ni * 8 + 2 * t + 1) * LL_LD + r0 + rr] = -(c1 + d1);
+    }
+}
+
+// Panel of block column kb for one row of the tile (one thread per row, nrows a multiple of 32, so whole warps take part):
+// l_c = (a_c - sum_{k<c} l_k L_kk(c,k)) / L_kk(c,c), c = 0..31.  The row lives in 32 registers and both loops are fully
+// unrolled (496 FMAs on four partial sums per column, the term with the newest l_{c-1} added last so that the dependent
+// chain per column is one FMA + the combine): the rolled shared-memory version spent ~5 us per call waiting on its own
+// stores.  __noinline__: own register allocation.
+__device__ __noinline__ void panel_row32(double* S, int k0, int R0, const double* xd, int tid)
+{
+    double* Ai = S + (R0 + tid) * LL_LD + k0;
+    double row[DB];
+#pragma unroll
+    for (int c = 0; c < DB; c++) row[c] = Ai[c];
+#pragma unroll
+    for (int c = 0; c < DB; c++) {
+        const double* Lc = S + (k0 + c) * LL_LD + k0;
+        double s[4] = {row[c], 0.0, 0.0, 0.0};
+#pragma unroll
+        for (int k = 0; k < c; k++) {
+            const int slot = (k == c - 1) ? 0 : 1 + (k % 3);     // the last term joins the chain that ends the column
+            s[slot] = fma(-row[k], Lc[k], s[slot]);
+        }
+        row[c] = ((s[1] + s[2]) + s[3] + s[0]) * xd[k0 + c];
+    }
+#pragma unroll
+    for (int c = 0; c < DB; c++) Ai[c] = row[c];
 }
 
 // all 256 consumer threads; S lower = matrix on entry, L on exit; upper/xd = X^T; scratch: >= 32*96 doubles; logs: 128 doubles
@@ -322,21 +377,7 @@ __device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, doub
         if (stamp && tid == 0) stamp[3] += globaltimer() - tw0;      // trace: time in the warp-level block factorisations
         consumer_bar();
         if (nrows > 0) {
-            if (tid < nrows) {
-                // row i of the panel: l_c = (a_c - sum_{k<c} l_k L_kk(c,k)) / L_kk(c,c), in place (the row is this thread's own)
-                double* Ai = S + (R0 + tid) * LL_LD + k0;
-                for (int c = 0; c < DB; c++) {
-                    const double* Lc = S + (k0 + c) * LL_LD + k0;
-                    double s0 = Ai[c], s1 = 0.0;
-                    int k = 0;
-                    for (; k + 1 < c; k += 2) {
-                        s0 = fma(-Ai[k], Lc[k], s0);
-                        s1 = fma(-Ai[k + 1], Lc[k + 1], s1);
-                    }
-                    if (k < c) s0 = fma(-Ai[k], Lc[k], s0);
-                    Ai[c] = (s0 + s1) * xd[k0 + c];
-                }
-            }
+            if (tid < nrows) panel_row32(S, k0, R0, xd, tid);
             consumer_bar();                                  // the panel is complete
             // trailing update A(i, c) -= sum_k L(i, k0+k) L(c, k0+k), R0 <= c <= i: lower 8 x 8 tiles, 8 DMMAs each
             const int nb = nrows / 8, ntl = nb * (nb + 1) / 2;
@@ -347,13 +388,16 @@ __device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, doub
                 const int ni = tl - mi * (mi + 1) / 2;
                 const double* La = S + (R0 + mi * 8 + g) * LL_LD + k0 + t;     // A(row g, k t)
                 const double* Lb = S + (R0 + ni * 8 + g) * LL_LD + k0 + t;     // B(k t, col g) = L(R0 + 8 ni + g, k)
-                double c0 = 0.0, c1 = 0.0;
+                double c0 = 0.0, c1 = 0.0, d0 = 0.0, d1 = 0.0;
 #pragma unroll
-                for (int kk = 0; kk < DB; kk += 4) dmma884(c0, c1, La[kk], Lb[kk]);
+                for (int kk = 0; kk < DB; kk += 8) {
+                    dmma884(c0, c1, La[kk], Lb[kk]);
+                    dmma884(d0, d1, La[kk + 4], Lb[kk + 4]);
+                }
                 const int i = R0 + mi * 8 + g, c = R0 + ni * 8 + 2 * t;
                 // (entries above the diagonal belong to the X^T storage of the diagonal blocks: only c <= i is written)
-                if (c <= i) S[i * LL_LD + c] -= c0;
-                if (c + 1 <= i) S[i * LL_LD + c + 1] -= c1;
+                if (c <= i) S[i * LL_LD + c] -= c0 + d0;
+                if (c + 1 <= i) S[i * LL_LD + c + 1] -= c1 + d1;
             }
             consumer_bar();
         }
@@ -370,10 +414,37 @@ __device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, doub
         if (lane == 0) *logout = sl;
         warp_invert32(S, TILE - DB, xd);
     } else {
-        tile_inverse_offdiag<WS_CONSUMER_WARPS - 1, 2>(S, xd, scratch, warp - 1, lane, 1, 2);
+        // warps 1-7, meanwhile: block rows 1 and 2 of the off-diagonal inverse and the first phase of block row 3
+        // (everything that does not need the inverse of the last diagonal block)
+        constexpr int NG = WS_CONSUMER_WARPS - 1;
+        tile_inverse_T<NG>(S, xd, scratch, warp - 1, lane, 1);
+        group_bar<2, NG * 32>();
+        tile_inverse_X<NG>(S, xd, scratch, warp - 1, lane, 1);
+        group_bar<2, NG * 32>();
+        tile_inverse_T<NG>(S, xd, scratch, warp - 1, lane, 2);
+        group_bar<2, NG * 32>();
+        tile_inverse_X<NG>(S, xd, scratch, warp - 1, lane, 2);
+        group_bar<2, NG * 32>();
+        tile_inverse_T<NG>(S, xd, scratch, warp - 1, lane, 3);
     }
     consumer_bar();
-    tile_inverse_offdiag<WS_CONSUMER_WARPS, 1>(S, xd, scratch, warp, lane, 3, 3);
+    tile_inverse_X<WS_CONSUMER_WARPS>(S, xd, scratch, warp, lane, 3);
+    consumer_bar();
+}
+
+// columns [wn + 16 HALF, wn + 16 HALF + 16) of a warp's 64 x 32 accumulator block to the tile in global memory
+template <int HALF>
+__device__ __forceinline__ void store_cols16(const double (&acc)[8][4][2], double* tile, long lda, int wm, int wn, int g, int t)
+{
+#pragma unroll
+    for (int ii = 0; ii < 8; ii++) {
+#pragma unroll
+        for (int jj = 2 * HALF; jj < 2 * HALF + 2; jj++) {
+            double* c0 = tile + (wm + ii * 8 + g) + (long)(wn + jj * 8 + 2 * t) * lda;
+            c0[0] = acc[ii][jj][0];
+            c0[lda] = acc[ii][jj][1];
+        }
+    }
 }
 
 // TRACE: record per-task time stamps (tools/ll_trace.py); a separate instantiation so that the production
@@ -414,6 +485,18 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             const double* rowi = a.A + (long)i * TILE;
             const double* rowj = a.A + (long)j * TILE;
             for (int kb = 0; kb < j; kb++) {
+                if (i == j && kb == j - 1) {
+                    // the tile L(j, j-1) comes off the critical path of the whole factorisation (its task had to wait for
+                    // Dinv_{j-1}): take it slab by slab as that task stores its column slabs, instead of waiting for the tile
+                    for (int sl = 0; sl < TILE / GK; sl++) {
+                        if (lane == 0) wait_count(a.slab + (long)kb * (TILE / GK) + sl, 2, a.abort, a.info);
+                        __syncwarp();
+                        fence_proxy_async();
+                        const double* src = rowi + ((long)kb * TILE + (long)sl * GK) * a.lda;
+                        ll_produce(src, a.lda, src, a.lda, 1, it, smem, full, empty, lane, vabort);
+                    }
+                    continue;
+                }
                 if (lane == 0) {
                     wait_ready(a.ready + i + (long)kb * nt, a.abort, a.info);
                     if (i != j) wait_ready(a.ready + j + (long)kb * nt, a.abort, a.info);
@@ -449,6 +532,13 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
 
         int i, j;
         ll_ticket(task, nt, i, j);
+        if (i == j) {
+            // the diagonal tile A(j,j) is read once, after the main loop, on the critical path of the whole factorisation:
+            // pull it into L2 now (128 columns x 1 KB = 1024 lines, 4 per thread)
+            const char* tp = reinterpret_cast<const char*>(a.A + (long)j * TILE + (long)j * TILE * a.lda);
+            for (int ln = tid; ln < TILE * 8; ln += LL_CONSUMERS)
+                asm volatile("prefetch.global.L2 [%0];\n" ::"l"(tp + (long)(ln >> 3) * a.lda * 8 + (ln & 7) * 128));
+        }
         unsigned long long* dbg = (TRACE && a.dbg) ? a.dbg + task * 8 : nullptr;
         if (TRACE && dbg && tid == 0) { dbg[0] = globaltimer(); dbg[7] = ((unsigned long long)i << 32) | (unsigned)j; }
         double acc[8][4][2];
@@ -535,15 +625,39 @@ __global__ void __launch_bounds__(WS_THREADS, 1) potrf_ll_kernel(LLArgs a)
             for (int ii = 0; ii < 8; ii++)
 #pragma unroll
                 for (int jj = 0; jj < 4; jj++) acc[ii][jj][0] = acc[ii][jj][1] = 0.0;
-            ll_consume<false>(acc, TILE / GK, it, smem, full, empty, wm, wn, g, t, lane, vabort);
+            if (i == j + 1) {
+                // sub-diagonal tile: Dinv_j is lower triangular, so columns [16 s, 16 s + 16) of L(i,j) are final after k-slab s.
+                // The two warps that own them store them at once and bump the slab counter: the diagonal task of the next
+                // column streams the tile slab by slab behind this pass instead of starting after it.
+                int* cnt = a.slab + (long)j * (TILE / GK);
 #pragma unroll
-            for (int ii = 0; ii < 8; ii++) {
+                for (int sp = 0; sp < TILE / GK / 2; sp++) {
+                    ll_consume<false>(acc, 1, it, smem, full, empty, wm, wn, g, t, lane, vabort);
+                    if (wn == 32 * sp) {
+                        store_cols16<0>(acc, tile, a.lda, wm, wn, g, t);
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) atomicAdd(cnt + 2 * sp, 1);
+                    }
+                    ll_consume<false>(acc, 1, it, smem, full, empty, wm, wn, g, t, lane, vabort);
+                    if (wn == 32 * sp) {
+                        store_cols16<1>(acc, tile, a.lda, wm, wn, g, t);
+                        __threadfence();
+                        __syncwarp();
+                        if (lane == 0) atomicAdd(cnt + 2 * sp + 1, 1);
+                    }
+                }
+            } else {
+                ll_consume<false>(acc, TILE / GK, it, smem, full, empty, wm, wn, g, t, lane, vabort);
 #pragma unroll
-                for (int jj = 0; jj < 4; jj++) {
-                    double* c0 = tile + (wm + ii * 8 + g) + (long)(wn + jj * 8 + 2 * t) * a.lda;
-                    double* c1 = c0 + a.lda;
-                    *c0 = acc[ii][jj][0];
-                    *c1 = acc[ii][jj][1];
+                for (int ii = 0; ii < 8; ii++) {
+#pragma unroll
+                    for (int jj = 0; jj < 4; jj++) {
+                        double* c0 = tile + (wm + ii * 8 + g) + (long)(wn + jj * 8 + 2 * t) * a.lda;
+                        double* c1 = c0 + a.lda;
+                        *c0 = acc[ii][jj][0];
+                        *c1 = acc[ii][jj][1];
+                    }
                 }
             }
             __threadfence();
@@ -561,7 +675,7 @@ constexpr size_t LL_SMEM = (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double
 size_t potrf_ll_flag_bytes(long n_pad)
 {
     const size_t nt = (size_t)(n_pad / TILE);
-    return (nt * nt + 4) * sizeof(int);
+    return (nt * nt + 4 + nt * (TILE / GK)) * sizeof(int);
 }
 
 // flags: potrf_ll_flag_bytes(n_pad) bytes of device scratch
@@ -578,10 +692,10 @@ int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logp
                   "diagonal tile scratch must fit in the operand ring");
     const int nt = (int)(n_pad / TILE);
     const size_t nflags = (size_t)nt * nt;
-    SGP_CUDA(cudaMemsetAsync(flags, 0, (nflags + 4) * sizeof(int), c.stream));
+    SGP_CUDA(cudaMemsetAsync(flags, 0, potrf_ll_flag_bytes(n_pad), c.stream));
     LLArgs a;
     a.A = A; a.lda = lda; a.nt = nt; a.Dinv = Dinv; a.logparts = logparts; a.info = info;
-    a.ready = flags; a.abort = flags + nflags;
+    a.ready = flags; a.abort = flags + nflags; a.slab = flags + nflags + 4;
     a.y = (y && w) ? y : nullptr; a.w = w;
     a.dbg = nullptr;
     // SGP_LL_TRACE=1: per-task time stamps (tools/ll_trace.py), dumped to $SGP_LL_TRACE_FILE after the launch

@@ -186,3 +186,109 @@ def test_quality_statistics_world2():
     res = ens.quality_sharded(q0, p0, ys, 2, _fake_quality)
     ref = _quality_reference(q0, p0, ys, 2)
     assert np.isclose(res["stdgd"], ref["stdgd"], rtol=1e-12) and res["n"] == ref["n"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# failures on one rank must not leave the others waiting in a collective
+# ---------------------------------------------------------------------------------------------------
+def _failure_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sympgpr_b200 import ensemble as ens
+    ok = True
+    # (a) a start that is not positive definite on ONE rank: recorded as +inf / NaN, every rank gets all results
+    thetas = [np.array([0.1 * (i + 1), 0.2 * (i + 1)]) for i in range(5)]
+
+    def evaluate(th):
+        if abs(th[0] - 0.2) < 1e-12:                   # theta 1 -> evaluated by rank 1
+            raise np.linalg.LinAlgError("cholesky: 3-th leading minor of the array is not positive definite")
+        return float(np.sum(th**2)), 2 * th
+    v, g = ens.restarts_sharded(thetas, evaluate)
+    ok &= bool(np.isinf(v[1]) and np.isnan(g[1]).all())
+    ok &= bool(np.allclose(np.delete(v, 1), [np.sum(t**2) for i, t in enumerate(thetas) if i != 1]))
+    ok &= bool(np.allclose(np.delete(g, 1, axis=0), [2 * t for i, t in enumerate(thetas) if i != 1]))
+    # (b) an unexpected exception on ONE rank: EVERY rank raises, nobody hangs in the gather
+    def bad_eval(th):
+        if rank == 0:
+            raise RuntimeError("device fell off the bus")
+        return float(np.sum(th**2)), 2 * th
+    try:
+        ens.restarts_sharded(thetas, bad_eval)
+        ok = False
+    except RuntimeError as e:
+        ok &= ("device fell off the bus" in str(e)) if rank == 0 else ("another rank failed" in str(e))
+    # (c) same for an ensemble step and a Sobol model
+    def bad_step(q0, p0):
+        if rank == 1:
+            raise ValueError("bad shard")
+        return _fake_map(q0, p0)
+    try:
+        ens.applymap_sharded("standard", 4, np.linspace(0, 6, 9), np.linspace(1, 2, 9), bad_step)
+        ok = False
+    except (ValueError, RuntimeError) as e:
+        ok &= ("bad shard" in str(e)) if rank == 1 else ("another rank failed" in str(e))
+
+    def bad_model(X):
+        if rank == 1:
+            raise FloatingPointError("model blew up")
+        return _ishigami(X)
+    try:
+        ens.sobol_indices_sharded(bad_model, [(-np.pi, np.pi)] * 3, 1024)
+        ok = False
+    except (FloatingPointError, RuntimeError) as e:
+        ok &= ("model blew up" in str(e)) if rank == 1 else ("another rank failed" in str(e))
+    # the group is still usable afterwards
+    t = torch.ones(1)
+    dist.all_reduce(t)
+    ok &= bool(t.item() == world)
+    out[rank] = int(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_one_rank_failing_does_not_hang_the_collectives_world2():
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_failure_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0, "a rank hung or crashed"
+    assert list(out) == [1] * world
+
+
+def _sobol_torch_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from sympgpr_b200 import ensemble as ens
+
+    def ish_t(X, a=7.0, b=0.1):
+        return torch.sin(X[:, 0]) + a * torch.sin(X[:, 1])**2 + b * X[:, 2]**4 * torch.sin(X[:, 0])
+    bounds = [(-np.pi, np.pi)] * 3
+    r = ens.sobol_indices_sharded(ish_t, bounds, 1 << 15, device="cpu", on_device=True, block=4096)
+    rh = ens.sobol_indices_sharded(_ishigami, bounds, 1 << 15, block=4096)
+    ok = np.allclose(r["S1"], rh["S1"], atol=1e-10) and np.allclose(r["ST"], rh["ST"], atol=1e-10) and r["n_used"] == 1 << 15
+    out[rank] = int(ok)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sobol_tensor_path_world2():
+    """The on_device=True path of sobol_indices_sharded (rows generated with torch, sums accumulated in a tensor, the
+    all_reduce on that tensor) with CPU tensors over gloo: same indices as the NumPy path, identical on both ranks."""
+    world = 2
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    out = ctx.Array("i", [0] * world)
+    procs = [ctx.Process(target=_sobol_torch_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert list(out) == [1] * world

@@ -249,6 +249,17 @@ int sgp_selftest_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, in
  * `mode` (csrc/dmma_gemm.cuh); al / bl: 0 = element (m,k) at ptr[m + k ld], 1 = at ptr[k + m ld]; Mt, Nt in tiles of 128. */
 int sgp_gemm_host(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, double alpha, double beta, const double* A,
                   long lda, const double* B, long ldb, double* C, long ldc);
+/* ---- opt-in: FP64 products from the INT8 tensor pipe (tcgen05.mma kind::i8, Ozaki splitting; csrc/ozaki.cu) ---------
+ * Not on any default path: north_star asks for DMMA in the Cholesky.  Self test of the tcgen05 plumbing: one 128 x 64 x K
+ * INT8 product (K a multiple of 128) on the tensor pipe against a plain integer kernel; *mismatches = differing outputs. */
+int sgp_i8mma_selftest(sgp_ctx* ctx, int K, int* mismatches, int* probe_ref, int* probe_got);
+/* C (M x N, column-major) = alpha A B^T + beta C with every product formed on the INT8 tensor pipe from ns = 4..8 signed 7-bit
+ * slices per operand (Ozaki splitting; exact integer slice products in TMEM, one FP64 combination per element).  A (M x K) and
+ * B (N x K): element (r, k) at ptr[r + k ld] (host pointers).  ns = 7 reproduces FP64 GEMM to ~1e-14 of sum |a||b|. */
+int sgp_ozaki_gemm_host(sgp_ctx* ctx, int ns, long M, long N, long K, double alpha, const double* A, long lda, const double* B,
+                        long ldb, double beta, double* C, long ldc);
+/* timing on random device operands: ms2[0] = slicing + GEMM per call, ms2[1] = the tensor-pipe GEMM alone (operands sliced) */
+int sgp_ozaki_bench(sgp_ctx* ctx, int ns, long M, long N, long K, int reps, double* ms2);
 /* DMMA GEMM timing: `reps` launches on random operands (alpha = -1, beta = 1), average ms per launch */
 int sgp_bench_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, int reps, double* ms_avg);
 /* timing hooks for bench.py (device pointers, async): the individual stages of one evaluation */

@@ -79,6 +79,9 @@ _PROTOS = {
     "sgp_ath": (c_d, [c_d, c_d, c_d]),
     "sgp_spd_factor": (c_i, [c_vp, c_dp, c_l, c_dp, c_dp, c_dp]),
     "sgp_selftest_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
+    "sgp_i8mma_selftest": (c_i, [c_vp, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
+    "sgp_ozaki_gemm_host": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_d, c_dp, c_l, c_dp, c_l, c_d, c_dp, c_l]),
+    "sgp_ozaki_bench": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_i, c_dp]),
     "sgp_gemm_host": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_d, c_dp, c_l, c_dp, c_l, c_dp, c_l]),
     "sgp_bench_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
     "sgp_fill_sym_dev": (c_i, [c_vp, c_i, c_d, c_i, c_dp, c_vp, c_l, c_vp, c_l]),

@@ -618,3 +618,17 @@ def gemm_host(al, bl, mode, A, B, C, alpha=1.0, beta=0.0):
     check(_lib.lib().sgp_gemm_host(_lib.context().handle, int(al), int(bl), int(mode), M // 128, N // 128, K, float(alpha),
                                    float(beta), dptr(A), A.shape[0], dptr(B), B.shape[0], dptr(C), C.shape[0]), "gemm_host")
     return C
+
+
+def ozaki_gemm(A, B, C=None, alpha=1.0, beta=0.0, slices=7):
+    """OPT-IN: C = alpha A B^T + beta C with the products formed on the INT8 tensor pipe (tcgen05.mma kind::i8) from `slices`
+    signed 7-bit slices per operand (csrc/ozaki.cu).  A (M, K), B (N, K); returns the Fortran-ordered (M, N) result."""
+    A, B = as_f64_fortran(A), as_f64_fortran(B)
+    M, K = A.shape
+    N = B.shape[0]
+    if B.shape[1] != K:
+        raise ValueError("ozaki_gemm: A is (M, K) and B must be (N, K)")
+    out = np.zeros((M, N), order="F") if C is None else np.array(C, dtype=np.float64, order="F")
+    check(_lib.lib().sgp_ozaki_gemm_host(_lib.context().handle, int(slices), M, N, K, float(alpha), dptr(A), M, dptr(B), N, float(beta),
+                                         dptr(out), M), "ozaki_gemm")
+    return out

@@ -10,6 +10,7 @@
 #include "grad.cuh"
 #include "map.cuh"
 #include "nll.cuh"
+#include "ozaki.cuh"
 
 using namespace sgp;
 
@@ -1042,6 +1043,68 @@ int sgp_gemm_host(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K,
     SGP_TRY(dmma_gemm(c, al, bl, g));
     SGP_TRY(download(c, C, dC, szC));
     return sync(c);
+}
+
+int sgp_i8mma_selftest(sgp_ctx* ctx, int K, int* mismatches, int* probe_ref, int* probe_got)
+{
+    SGP_TRY(check_ctx(ctx));
+    return i8mma_selftest(ctx->c, K, mismatches, probe_ref, probe_got);
+}
+
+int sgp_ozaki_gemm_host(sgp_ctx* ctx, int ns, long M, long N, long K, double alpha, const double* A, long lda, const double* B, long ldb,
+                        double beta, double* C, long ldc)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || lda < M || ldb < N || ldc < M) { set_error("ozaki_gemm_host: bad arguments"); return ST_BADARG; }
+    const size_t szA = (size_t)lda * K, szB = (size_t)ldb * K, szC = (size_t)ldc * N;
+    const size_t wb = ozaki_workspace_bytes(M, N, K, ns);
+    SGP_TRY(c.Kmat.reserve((szA + szB + szC + 8) * sizeof(double)));
+    SGP_TRY(c.Wmat.reserve(wb));
+    double* dA = c.Kmat.as<double>();
+    double* dB = dA + szA; double* dC = dB + szB;
+    SGP_TRY(upload(c, dA, A, szA)); SGP_TRY(upload(c, dB, B, szB)); SGP_TRY(upload(c, dC, C, szC));
+    SGP_TRY(ozaki_gemm(c, ns, M, N, K, alpha, dA, lda, dB, ldb, beta, dC, ldc, c.Wmat.p, wb));
+    SGP_TRY(download(c, C, dC, szC));
+    return sync(c);
+}
+
+// timing of the opt-in Ozaki GEMM on random operands: ms_total = slicing of both operands + the INT8 GEMM, ms_gemm = the second
+// call's GEMM alone is not separable from outside, so both are event-timed here: [0] slicing, [1] tensor-map + GEMM kernel
+int sgp_ozaki_bench(sgp_ctx* ctx, int ns, long M, long N, long K, int reps, double* ms2)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (M <= 0 || N <= 0 || K <= 0 || reps <= 0 || !ms2) { set_error("ozaki_bench: bad arguments"); return ST_BADARG; }
+    const size_t szA = (size_t)M * K, szB = (size_t)N * K, szC = (size_t)M * N;
+    const size_t wb = ozaki_workspace_bytes(M, N, K, ns);
+    SGP_TRY(c.Kmat.reserve((szA + szB + szC + 8) * sizeof(double)));
+    SGP_TRY(c.Wmat.reserve(wb));
+    double* dA = c.Kmat.as<double>();
+    double* dB = dA + szA; double* dC = dB + szB;
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dA, (long)szA, 1ull, 1, 0);
+    fill_random_kernel<<<512, 256, 0, c.stream>>>(dB, (long)szB, 2ull, 1, 0);
+    SGP_CUDA(cudaGetLastError());
+    SGP_TRY(ozaki_gemm(c, ns, M, N, K, 1.0, dA, M, dB, N, 0.0, dC, M, c.Wmat.p, wb));        // warm-up
+    cudaEvent_t e0, e1;
+    SGP_CUDA(cudaEventCreate(&e0));
+    SGP_CUDA(cudaEventCreate(&e1));
+    SGP_CUDA(cudaEventRecord(e0, c.stream));
+    for (int r = 0; r < reps; r++) SGP_TRY(ozaki_gemm(c, ns, M, N, K, 1.0, dA, M, dB, N, 0.0, dC, M, c.Wmat.p, wb));
+    SGP_CUDA(cudaEventRecord(e1, c.stream));
+    SGP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    SGP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ms2[0] = (double)ms / reps;
+    // the GEMM kernel alone: slices of the last call are still in the workspace
+    SGP_CUDA(cudaEventRecord(e0, c.stream));
+    for (int r = 0; r < reps; r++) SGP_TRY(ozaki_gemm_presliced(c, ns, M, N, K, 1.0, 0.0, dC, M, c.Wmat.p, wb));
+    SGP_CUDA(cudaEventRecord(e1, c.stream));
+    SGP_CUDA(cudaEventSynchronize(e1));
+    SGP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    ms2[1] = (double)ms / reps;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return ST_OK;
 }
 
 int sgp_bench_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, int reps, double* ms_avg)

@@ -1,0 +1,532 @@
+// FP64 GEMM from the INT8 tensor pipe of sm_100a (Ozaki splitting): an OPT-IN building block, not on any default path.
+//
+// north_star asks for DMMA in the Cholesky (done: potrf_ll.cu / dmma_gemm_ws.cuh run at 91-97 % of the DMMA issue limit),
+// which makes that limit -- 37 TFLOP/s -- the ceiling of the NLL+gradient evaluation.  The only way past it on Blackwell is
+// the 5th-generation tensor core, which has no f64 kind: tcgen05.mma kind::i8 (INT8 x INT8 -> INT32, accumulators in tensor
+// memory).  An FP64 product is recovered EXACTLY up to the slices kept by splitting both operands into signed 7-bit slices
+// of their row-scaled mantissas (Ozaki scheme):
+//     A(m,:) = 2^(ea(m)-6) sum_s As(m,:) 2^(-7 s),   B(n,:) = 2^(eb(n)-6) sum_t Bt(n,:) 2^(-7 t),   |As|,|Bt| <= 64
+//     C(m,n) = 2^(ea(m)+eb(n)-12) sum_d 2^(-7 d) sum_{s+t=d} As(m,:) . Bt(n,:)          (d < NS: the pairs that matter)
+// Every slice product is an integer GEMM without rounding (K 64^2 NS < 2^31 for K <= 65536 / NS), pairs with equal
+// s + t share one INT32 accumulator in tensor memory, and the only floating-point roundings are the final NS-term sum per
+// output element.  tools/ozaki_study.py (round 1) shows 7 slices hold 1e-9 on the benchmark NLL and 9 are needed at
+// cond 1e10.
+//
+// This file: (1) the tcgen05 plumbing (TMEM allocation, shared-memory matrix descriptors for the K-major 128-byte-swizzled
+// canonical layout, the kind::i8 instruction descriptor, tcgen05.commit -> mbarrier, tcgen05.ld) with a self test of one
+// 128 x 64 x K INT8 product against a plain integer kernel; (2) the slicing kernel; (3) the Ozaki GEMM
+// C = alpha A B^T + beta C on FP64 operands, validated against gemm_f64_ws_kernel (tests/test_gpu_ozaki.py).
+#include "ozaki.cuh"
+
+#include <cuda.h>
+#include <float.h>
+#include <stdint.h>
+
+#include "mbar.cuh"
+
+namespace sgp {
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------------------
+// tcgen05 helpers (PTX as CUTLASS 4.x spells it: cute/arch/mma_sm100_umma.hpp, tmem_allocator_sm100.hpp, copy_sm100.hpp)
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// D[tmem] (+)= A[smem] B[smem]^T, INT8 x INT8 -> INT32, issued by ONE thread for the CTA
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+        : "memory");
+}
+// all MMAs issued so far by this thread -> one arrival on the mbarrier when they have completed
+__device__ __forceinline__ void umma_commit(unsigned long long* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes x 32 columns of 32-bit: thread t of warp w (w = warp index % 4) receives columns c .. c+31 of TMEM lane 32 w + t
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, "
+        "%20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
+          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
+          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp, SmemDescriptor) of a K-major operand tile in the canonical
+// 128-byte-swizzled layout: rows of 128 bytes (128 INT8 along K), 8-row atoms of 1024 bytes, the 16-byte chunk index of a
+// row XORed with the row index inside its atom (Swizzle<3,4,3>), tile base 1024-byte aligned.
+//   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (1: unused for swizzled K-major)
+//   bits [32,46) stride byte offset >> 4 (1024 B between 8-row atoms)     bits [46,48) version = 1 (Blackwell)
+//   bits [61,64) layout type = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t umma_desc_k128(const void* smem_tile)
+{
+    const uint64_t addr = (uint64_t)((smem_u32(smem_tile) & 0x3FFFFu) >> 4);
+    return addr | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+// Instruction descriptor (InstrDescriptor) for kind::i8: dense, no saturation, C = S32 (2 at bits [4,6)), A and B signed
+// 8 bit (1 at bits [7,10) and [10,13)), both K-major (0 at bits 15 and 16), N >> 3 at bits [17,23), M >> 4 at bits [24,29)
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int M, int N)
+{
+    return (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// byte offset of (row r, byte k < 128) inside a 128-byte-swizzled K-major tile
+__host__ __device__ inline uint32_t sw128_offset(int r, int k)
+{
+    return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 4) ^ (r & 7)) & 7) << 4) + (k & 15));
+}
+
+constexpr int ST_M = 128, ST_N = 64, ST_KC = 128;     // self test: one 128 x 64 tile, k-chunks of 128 bytes
+
+// ---------------------------------------------------------------------------------------------------------
+// (1) self test: D (128 x 64, INT32) = A (128 x K, INT8, K contiguous) B (64 x K)^T on the INT8 tensor pipe.  One CTA of four
+// warps; every k-chunk is copied to shared memory by all threads in the swizzled layout, four UMMAs (K = 32 each) are issued
+// by thread 0 and committed to an mbarrier that everybody waits on before the chunk is overwritten: the simplest correct
+// pipeline (no overlap), only there to pin descriptors, TMEM addressing and the tcgen05.ld mapping against a plain kernel.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1) i8mma_selftest_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int K,
+                                                                 int32_t* __restrict__ D)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = sA + ST_M * ST_KC;
+    __shared__ unsigned long long bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_base_s, 64);
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        mbar_fence_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    constexpr uint32_t idesc = umma_idesc_i8(ST_M, ST_N);
+    uint32_t phase = 0;
+    for (int k0 = 0; k0 < K; k0 += ST_KC) {
+        for (int c = tid; c < ST_M * 8; c += 128) {
+            const int r = c >> 3, ch = c & 7;
+            *reinterpret_cast<uint4*>(sA + sw128_offset(r, ch * 16)) = *reinterpret_cast<const uint4*>(A + (size_t)r * K + k0 + ch * 16);
+        }
+        for (int c = tid; c < ST_N * 8; c += 128) {
+            const int r = c >> 3, ch = c & 7;
+            *reinterpret_cast<uint4*>(sB + sw128_offset(r, ch * 16)) = *reinterpret_cast<const uint4*>(B + (size_t)r * K + k0 + ch * 16);
+        }
+        fence_async_smem();                      // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int ks = 0; ks < ST_KC / 32; ks++)
+                umma_i8(tmem, umma_desc_k128(sA + ks * 32), umma_desc_k128(sB + ks * 32), idesc, (k0 > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&bar);
+        }
+        mbar_wait(&bar, phase);
+        phase ^= 1u;
+        tc_fence_after();
+    }
+    uint32_t v[32];
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + half * 32, v);
+#pragma unroll
+        for (int i = 0; i < 32; i++) D[(size_t)(32 * warp + lane) * ST_N + half * 32 + i] = (int32_t)v[i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 64);
+}
+
+__global__ void i8_ref_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int M, int N, int K, int32_t* __restrict__ D)
+{
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * N) return;
+    const int m = idx / N, n = idx % N;
+    int s = 0;
+    for (int k = 0; k < K; k++) s += (int)A[(size_t)m * K + k] * (int)B[(size_t)n * K + k];
+    D[idx] = s;
+}
+
+__global__ void i8_fill_kernel(int8_t* __restrict__ a, long n, unsigned long long seed)
+{
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        unsigned long long z = (unsigned long long)i * 0x9E3779B97F4A7C15ull + seed;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        a[i] = (int8_t)((int)((z >> 40) % 129ull) - 64);        // [-64, 64]: the range of the Ozaki slices
+    }
+}
+
+__global__ void i32_diff_kernel(const int32_t* __restrict__ a, const int32_t* __restrict__ b, int n, int* __restrict__ nbad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && a[i] != b[i]) atomicAdd(nbad, 1);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (2) slicing: FP64 operand X (element (r, k) at X[r + k ld], the LAYOUT_MN of the Cholesky operands) ->
+//     exps[r] = e with max_k |X(r,k)| < 2^e,  slices[s][r][k] (INT8, k contiguous, row pitch Kp, slice pitch Rp Kp) with
+//     X(r,k) = 2^(e-6) sum_s slices[s][r][k] 2^(-7 s) + O(2^(e - 6 - 7 NS)),  |slice| <= 64.
+// Every step is exact in FP64 (scaling by powers of two, subtracting the integer just extracted); rows / columns beyond the
+// matrix are zero.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void oz_rowexp_kernel(const double* __restrict__ X, long ld, long R, long K, int* __restrict__ exps)
+{
+    const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double mx = 0.0;
+    for (long k = 0; k < K; k++) mx = fmax(mx, fabs(X[r + k * ld]));
+    int e = 0;
+    if (mx > 0.0 && mx <= DBL_MAX) {
+        frexp(mx, &e);                       // mx = f 2^e, 0.5 <= f < 1  =>  |x| 2^-e < 1
+    }
+    exps[r] = e;
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ X, long ld, long R, long K, const int* __restrict__ exps,
+                                                        int8_t* __restrict__ slices, long Rp, long Kp)
+{
+    __shared__ int8_t tile[NS][32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8 threads
+    const long r0 = (long)blockIdx.x * 32, k0 = (long)blockIdx.y * 32;
+    const long r = r0 + tx;
+    const int e = (r < R) ? exps[r] : 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const long k = k0 + ty + 8 * j;
+        double y = (r < R && k < K) ? scalbn(X[r + k * ld], 6 - e) : 0.0;          // |y| < 64
+        if (!(fabs(y) <= 64.0)) y = 0.0;                                          // NaN / Inf operands: not representable
+#pragma unroll
+        for (int sidx = 0; sidx < NS; sidx++) {
+            const double a = rint(y);
+            tile[sidx][ty + 8 * j][tx] = (int8_t)(int)a;
+            y = (y - a) * 128.0;
+        }
+    }
+    __syncthreads();
+    // transposed write: k contiguous
+#pragma unroll
+    for (int sidx = 0; sidx < NS; sidx++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const long rr = r0 + ty + 8 * j, kk = k0 + tx;
+            if (rr < Rp && kk < Kp) slices[(size_t)sidx * Rp * Kp + (size_t)rr * Kp + kk] = tile[sidx][tx][ty + 8 * j];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (3) the GEMM.  One CTA (four warps) per 128 x 64 output tile, persistent over tiles.  Thread 0 is the whole control
+// flow of the main loop: per k-chunk of 128 it issues 2 NS bulk tensor copies (cp.async.bulk.tensor.3d, 128-byte swizzle:
+// one box per slice of A and of B) onto one mbarrier, waits for the bytes, issues the NS (NS + 1) / 2 x 4 UMMAs
+// (tcgen05.mma kind::i8, M = 128, N = 64, K = 32; the pairs with s + t = d accumulate into TMEM columns [64 d, 64 d + 64)) and
+// commits them to a second mbarrier, whose completion frees the shared-memory stage.  After the last chunk all four warps
+// read their 32 TMEM lanes (tcgen05.ld 32x32b.x32), combine the NS integer accumulators in FP64 from the smallest term up,
+// apply 2^(ea + eb - 12) and write C.  Single stage: 24 KB per slice pair and k-chunk, 192 KB at NS = 8.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int OZ_M = 128, OZ_N = 64, OZ_KC = 128;
+
+__device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(smem_u32(smem_dst)),
+        "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+
+struct OzArgs {
+    const int* ea; const int* eb;       // row exponents of A (M) and B (N)
+    double* C; long ldc;                // column-major output
+    long M, N, K;                       // logical sizes (M, N padded to tiles inside the slices; K padded to 128)
+    int mt, nt, nk;                     // tiles / k-chunks
+    double alpha, beta;
+};
+
+template <int NS>
+__global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a)
+{
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // NS x 16 KB
+    uint8_t* sB = sA + NS * OZ_M * OZ_KC;                                                           // NS x  8 KB
+    __shared__ unsigned long long bar_full, bar_mma;
+    __shared__ uint32_t tmem_base_s;
+    __shared__ int s_eb[OZ_N];
+    constexpr uint32_t TCOLS = (NS * OZ_N <= 64) ? 64 : (NS * OZ_N <= 128) ? 128 : (NS * OZ_N <= 256) ? 256 : 512;
+    static_assert(NS * OZ_N <= 512, "accumulators of all slice-sum classes must fit the 512 TMEM columns");
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
+    if (tid == 0) {
+        mbar_init(&bar_full, 1);
+        mbar_init(&bar_mma, 1);
+        mbar_fence_init();
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+    constexpr uint32_t idesc = umma_idesc_i8(OZ_M, OZ_N);
+    uint32_t ph_full = 0, ph_mma = 0;
+    const long ntiles = (long)a.mt * a.nt;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int tm = (int)(tile % a.mt), tn = (int)(tile / a.mt);
+        if (tid < OZ_N) {
+            const long n = (long)tn * OZ_N + tid;
+            s_eb[tid] = (n < a.N) ? a.eb[n] : 0;
+        }
+        if (tid == 0) {
+            for (int kc = 0; kc < a.nk; kc++) {
+                mbar_arrive_expect_tx(&bar_full, (uint32_t)(NS * (OZ_M + OZ_N) * OZ_KC));
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+                    tma_load_3d(sA + s * OZ_M * OZ_KC, &tmA, kc * OZ_KC, tm * OZ_M, s, &bar_full);
+                    tma_load_3d(sB + s * OZ_N * OZ_KC, &tmB, kc * OZ_KC, tn * OZ_N, s, &bar_full);
+                }
+                mbar_wait(&bar_full, ph_full);
+                ph_full ^= 1u;
+                tc_fence_after();
+#pragma unroll
+                for (int s = 0; s < NS; s++) {
+#pragma unroll
+                    for (int t = 0; t < NS - s; t++) {
+                        const int d = s + t;
+                        // first write of accumulator d in this tile: (kc, ks) = (0, 0) of the pair (s, t) = (0, d)
+#pragma unroll
+                        for (int ks = 0; ks < OZ_KC / 32; ks++)
+                            umma_i8(tmem + d * OZ_N, umma_desc_k128(sA + s * OZ_M * OZ_KC + ks * 32),
+                                    umma_desc_k128(sB + t * OZ_N * OZ_KC + ks * 32), idesc, (kc > 0 || ks > 0 || s > 0) ? 1u : 0u);
+                    }
+                }
+                umma_commit(&bar_mma);
+                mbar_wait(&bar_mma, ph_mma);             // the stage may be overwritten; after the last chunk: accumulators final
+                ph_mma ^= 1u;
+            }
+        }
+        __syncthreads();                                 // thread 0 has seen the last commit complete
+        tc_fence_after();
+        // epilogue: thread = row m of the tile (TMEM lane 32 warp + lane)
+        const long m = (long)tm * OZ_M + 32 * warp + lane;
+        const int eam = (m < a.M) ? a.ea[m] : 0;
+#pragma unroll 1
+        for (int half = 0; half < OZ_N / 32; half++) {
+            double acc[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) acc[i] = 0.0;
+#pragma unroll 1
+            for (int d = NS - 1; d >= 0; d--) {           // smallest contributions first
+                uint32_t v[32];
+                tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + d * OZ_N + half * 32, v);
+                const double w = scalbn(1.0, -7 * d);
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[i] = fma((double)(int32_t)v[i], w, acc[i]);
+            }
+            if (m < a.M) {
+#pragma unroll
+                for (int i = 0; i < 32; i++) {
+                    const long n = (long)tn * OZ_N + half * 32 + i;
+                    if (n < a.N) {
+                        const double val = a.alpha * scalbn(acc[i], eam + s_eb[half * 32 + i] - 12);
+                        double* cp = a.C + m + n * a.ldc;
+                        *cp = (a.beta == 0.0) ? val : fma(a.beta, *cp, val);
+                    }
+                }
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                 // all TMEM reads done before the next tile's first UMMA overwrites
+        tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TCOLS);
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_slice_tmap(CUtensorMap* tm, const int8_t* slices, long Rp, long Kp, int ns, int box_rows)
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        SGP_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+        if (!p || q != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return ST_CUDA; }
+        fn = (EncodeTiledFn)p;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)Kp, (cuuint64_t)Rp, (cuuint64_t)ns};
+    const cuuint64_t strides[2] = {(cuuint64_t)Kp, (cuuint64_t)Kp * (cuuint64_t)Rp};             // bytes, dims 1 and 2
+    const cuuint32_t box[3] = {(cuuint32_t)OZ_KC, (cuuint32_t)box_rows, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)slices, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ST_CUDA; }
+    return ST_OK;
+}
+
+template <int NS>
+int oz_launch(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, const OzArgs& a)
+{
+    const size_t smem = (size_t)NS * (OZ_M + OZ_N) * OZ_KC + 1024;
+    static bool configured = false;
+    if (!configured) {
+        SGP_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    const long ntiles = (long)a.mt * a.nt;
+    const int sms = c.sm_count > 0 ? c.sm_count : 148;
+    oz_gemm_kernel<NS><<<(unsigned)(ntiles < sms ? ntiles : sms), 128, smem, c.stream>>>(tmA, tmB, a);
+    SGP_CUDA(cudaGetLastError());
+    count_launch();
+    return ST_OK;
+}
+
+template <int NS>
+int oz_slice(Ctx& c, const double* X, long ld, long R, long K, int* exps, int8_t* slices, long Rp, long Kp)
+{
+    oz_rowexp_kernel<<<(unsigned)((R + 127) / 128), 128, 0, c.stream>>>(X, ld, R, K, exps);
+    oz_slice_kernel<NS><<<dim3((unsigned)(Rp / 32), (unsigned)(Kp / 32)), 256, 0, c.stream>>>(X, ld, R, K, exps, slices, Rp, Kp);
+    SGP_CUDA(cudaGetLastError());
+    count_launch(2);
+    return ST_OK;
+}
+
+}  // namespace
+
+size_t ozaki_workspace_bytes(long M, long N, long K, int ns)
+{
+    const size_t Mp = (size_t)round_up(M, OZ_M), Np = (size_t)round_up(N, OZ_N), Kp = (size_t)round_up(K, OZ_KC);
+    return (size_t)ns * (Mp + Np) * Kp + (Mp + Np) * sizeof(int) + 1024;
+}
+
+struct OzWork {
+    int8_t *sA, *sB;
+    int *ea, *eb;
+    long Mp, Np, Kp;
+};
+
+static OzWork oz_carve(void* work, long M, long N, long K, int ns)
+{
+    OzWork w;
+    w.Mp = round_up(M, OZ_M); w.Np = round_up(N, OZ_N); w.Kp = round_up(K, OZ_KC);
+    w.sA = reinterpret_cast<int8_t*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
+    w.sB = w.sA + (size_t)ns * w.Mp * w.Kp;
+    w.ea = reinterpret_cast<int*>(w.sB + (size_t)ns * w.Np * w.Kp);
+    w.eb = w.ea + w.Mp;
+    return w;
+}
+
+static int oz_check(int ns, long M, long N, long K, size_t work_bytes)
+{
+    if (ns < 4 || ns > 8 || M <= 0 || N <= 0 || K <= 0) { set_error("ozaki_gemm: bad arguments (ns must be 4..8)"); return ST_BADARG; }
+    if ((long)ns * K * 4096 >= 2147483647L) { set_error("ozaki_gemm: K = %ld too deep for exact INT32 accumulation with %d slices", K, ns); return ST_BADARG; }
+    if (work_bytes < ozaki_workspace_bytes(M, N, K, ns)) { set_error("ozaki_gemm: workspace too small"); return ST_BADARG; }
+    return ST_OK;
+}
+
+// the GEMM on operands that ozaki_slice_operands() has already split into `work`
+int ozaki_gemm_presliced(Ctx& c, int ns, long M, long N, long K, double alpha, double beta, double* C, long ldc, void* work, size_t work_bytes)
+{
+    SGP_TRY(oz_check(ns, M, N, K, work_bytes));
+    const OzWork w = oz_carve(work, M, N, K, ns);
+    CUtensorMap tmA, tmB;
+    SGP_TRY(make_slice_tmap(&tmA, w.sA, w.Mp, w.Kp, ns, OZ_M));
+    SGP_TRY(make_slice_tmap(&tmB, w.sB, w.Np, w.Kp, ns, OZ_N));
+    OzArgs a;
+    a.ea = w.ea; a.eb = w.eb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
+    a.mt = (int)(w.Mp / OZ_M); a.nt = (int)(w.Np / OZ_N); a.nk = (int)(w.Kp / OZ_KC); a.alpha = alpha; a.beta = beta;
+    switch (ns) {
+    case 4: return oz_launch<4>(c, tmA, tmB, a);
+    case 5: return oz_launch<5>(c, tmA, tmB, a);
+    case 6: return oz_launch<6>(c, tmA, tmB, a);
+    case 7: return oz_launch<7>(c, tmA, tmB, a);
+    default: return oz_launch<8>(c, tmA, tmB, a);
+    }
+}
+
+// split A (M x K) and B (N x K) (element (r, k) at ptr[r + k ld]) into ns INT8 slices + row exponents in `work`
+int ozaki_slice_operands(Ctx& c, int ns, long M, long N, long K, const double* A, long lda, const double* B, long ldb, void* work, size_t work_bytes)
+{
+    SGP_TRY(oz_check(ns, M, N, K, work_bytes));
+    const OzWork w = oz_carve(work, M, N, K, ns);
+    switch (ns) {
+    case 4: SGP_TRY(oz_slice<4>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<4>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
+    case 5: SGP_TRY(oz_slice<5>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<5>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
+    case 6: SGP_TRY(oz_slice<6>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<6>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
+    case 7: SGP_TRY(oz_slice<7>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<7>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
+    default: SGP_TRY(oz_slice<8>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<8>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
+    }
+}
+
+// C (M x N, column-major, ldc) = alpha A B^T + beta C with A (M x K) and B (N x K) given as element (r, k) at ptr[r + k ld];
+// ns = 4..8 slices per operand (7: ~2^-49 of the row / column scales; 8: ~2^-56).  ns K 4096 < 2^31 (INT32 headroom).
+int ozaki_gemm(Ctx& c, int ns, long M, long N, long K, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
+               double* C, long ldc, void* work, size_t work_bytes)
+{
+    SGP_TRY(ozaki_slice_operands(c, ns, M, N, K, A, lda, B, ldb, work, work_bytes));
+    return ozaki_gemm_presliced(c, ns, M, N, K, alpha, beta, C, ldc, work, work_bytes);
+}
+
+int i8mma_selftest(Ctx& c, int K, int* mismatches, int* first_bad_ref, int* first_bad_got)
+{
+    if (K <= 0 || K % ST_KC) { set_error("i8mma_selftest: K must be a positive multiple of %d", ST_KC); return ST_BADARG; }
+    const size_t szA = (size_t)ST_M * K, szB = (size_t)ST_N * K, szD = (size_t)ST_M * ST_N;
+    SGP_TRY(c.io.reserve(szA + szB + 2 * szD * sizeof(int32_t) + 64));
+    int8_t* dA = c.io.as<int8_t>();
+    int8_t* dB = dA + szA;
+    int32_t* dD = reinterpret_cast<int32_t*>(c.io.as<char>() + ((szA + szB + 15) & ~(size_t)15));
+    int32_t* dR = dD + szD;
+    int* dbad = reinterpret_cast<int*>(dR + szD);
+    i8_fill_kernel<<<64, 256, 0, c.stream>>>(dA, (long)szA, 11ull);
+    i8_fill_kernel<<<64, 256, 0, c.stream>>>(dB, (long)szB, 23ull);
+    SGP_CUDA(cudaMemsetAsync(dD, 0xff, szD * sizeof(int32_t), c.stream));
+    SGP_CUDA(cudaMemsetAsync(dbad, 0, sizeof(int), c.stream));
+    const size_t smem = (size_t)(ST_M + ST_N) * ST_KC + 1024;
+    i8mma_selftest_kernel<<<1, 128, smem, c.stream>>>(dA, dB, K, dD);
+    SGP_CUDA(cudaGetLastError());
+    i8_ref_kernel<<<(unsigned)((szD + 127) / 128), 128, 0, c.stream>>>(dA, dB, ST_M, ST_N, K, dR);
+    i32_diff_kernel<<<(unsigned)((szD + 127) / 128), 128, 0, c.stream>>>(dD, dR, (int)szD, dbad);
+    SGP_CUDA(cudaGetLastError());
+    count_launch(5);
+    int bad = -1;
+    SGP_CUDA(cudaMemcpyAsync(&bad, dbad, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    int32_t r0[2] = {0, 0};
+    SGP_CUDA(cudaMemcpyAsync(&r0[0], dR + 5 * ST_N + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    SGP_CUDA(cudaMemcpyAsync(&r0[1], dD + 5 * ST_N + 3, sizeof(int32_t), cudaMemcpyDeviceToHost, c.stream));
+    SGP_CUDA(cudaStreamSynchronize(c.stream));
+    if (mismatches) *mismatches = bad;
+    if (first_bad_ref) *first_bad_ref = r0[0];
+    if (first_bad_got) *first_bad_got = r0[1];
+    return ST_OK;
+}
+
+}  // namespace sgp

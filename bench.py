@@ -434,6 +434,50 @@ def leg_headline(B):
                 h2d=int(x_h.numel() * 8 + z_h.numel() * 8), d2h=16 * 8, t_fill=t_fill, fill_gbs=8.0 * n * n / t_fill / 1e9)
 
 
+def leg_ozaki(B, head_ms, head_res, dgemm):
+    """OPT-IN route past the DMMA ceiling (not the headline: north_star asks for DMMA in the Cholesky): FP64 products from the
+    INT8 tensor pipe (tcgen05.mma kind::i8, TMEM accumulators, Ozaki slicing; csrc/ozaki.cu).  (a) the raw GEMM at 8192^3
+    against the DMMA GEMM, (b) the headline evaluation with the lauum stage (W = X^T X) on the INT8 pipe, same inputs."""
+    a, torch, W = B.a, B.torch, B.W
+    out = {"note": "opt-in (sgp_set_ozaki); headline value/roofline above are the DMMA path north_star names"}
+    g = {}
+    for ns in (7, 8):
+        ms = (ctypes.c_double * 2)()
+        B._lib.check(B.L.sgp_ozaki_bench(B.ctx.handle, ns, 8192, 8192, 8192, 3, ms), "sgp_ozaki_bench")
+        g[f"{ns}_slices"] = {"ms_slicing_plus_gemm": ms[0], "ms_gemm": ms[1], "fp64_equiv_TFLOP/s": 2 * 8192.0**3 / ms[0] / 1e9,
+                             "fp64_equiv_TFLOP/s_gemm_only": 2 * 8192.0**3 / ms[1] / 1e9,
+                             "int8_TOP/s_gemm_only": ns * (ns + 1) / 2 * 2 * 8192.0**3 / ms[1] / 1e9}
+    msd = ctypes.c_double(0.0)
+    B._lib.check(B.L.sgp_bench_gemm(B.ctx.handle, 0, 0, 0, 64, 64, 8192, 3, ctypes.byref(msd)), "sgp_bench_gemm")
+    g["dmma_gemm_f64_ws"] = {"ms": msd.value, "TFLOP/s": 2 * 8192.0**3 / msd.value / 1e9}
+    g["cublas_dgemm_TFLOP/s"] = dgemm
+    out["gemm_8192"] = g
+    B.free()
+    N = a.n_train
+    n = 2 * N
+    d = W.standard_map_training(N)
+    hyp = W.timing_hyp(N, d["sig"], 1e-8)
+    hyp[:2] *= (1.0 + 0.02 * B.rank)
+    x_d = torch.from_numpy(d["xtrain"].copy()).to(B.dev)
+    z_d = torch.from_numpy(d["ztrain"].copy()).to(B.dev)
+    step, res_d = B.nll_dev_fn(hyp, x_d, z_d, n)
+    B.ctx.set_ozaki(8)
+    try:
+        step(); step()
+        ms = B.timed(step, 3)
+        st = B.stage_times()
+        res = res_d.cpu().numpy()
+    finally:
+        B.ctx.set_ozaki(0)
+        B.free()
+    out["nll_grad_lauum_int8"] = {"slices": 8, "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "speedup_vs_dmma_path": head_ms / ms,
+                                  "stages_ms": {k: round(v, 3) for k, v in st.items()},
+                                  "lauum_fp64_equiv_TFLOP/s": float(n)**3 / 3.0 / st["lauum"] / 1e9,
+                                  "nll": float(res[0]), "grad": [float(res[1]), float(res[2])],
+                                  "grad_rel_diff_vs_dmma_path": [abs(float(res[1 + k]) - float(head_res[1 + k])) / abs(float(head_res[1 + k])) for k in range(2)]}
+    return out
+
+
 def leg_sweep(B, dgemm):
     """BASELINE config 5: NLL+gradient at N = 2048 ... sweep-max (n up to 65 536), device resident, with stage times."""
     a, torch, W = B.a, B.torch, B.W
@@ -846,6 +890,7 @@ def main():
     head = leg_headline(B)
     n = head["n"]
     single = world == 1
+    ozaki = leg_ozaki(B, head["ms_per_step"], head["res"], dgemm_tflops) if (single and not a.no_configs) else None
     sweep = leg_sweep(B, dgemm_tflops) if (single and not a.no_sweep) else None
     configs = {}
     if not a.no_configs:
@@ -914,6 +959,8 @@ def main():
                 "peaks": {"dgemm_tflops": dgemm_tflops, "hbm_write_gbs": write_gbs, "hbm_copy_gbs": hbm},
                 "result": {"nll": float(head["res"][0]), "grad": [float(head["res"][1]), float(head["res"][2])]},
                 }
+        if ozaki:
+            line["ozaki_opt_in"] = ozaki
         if sweep:
             line["sweep"] = sweep
         if configs:

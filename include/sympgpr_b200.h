@@ -253,6 +253,9 @@ int sgp_gemm_host(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K,
  * Not on any default path: north_star asks for DMMA in the Cholesky.  Self test of the tcgen05 plumbing: one 128 x 64 x K
  * INT8 product (K a multiple of 128) on the tensor pipe against a plain integer kernel; *mismatches = differing outputs. */
 int sgp_i8mma_selftest(sgp_ctx* ctx, int K, int* mismatches, int* probe_ref, int* probe_got);
+/* OPT-IN switch of a context: nslices = 4..8 routes the lauum stage (W = X^T X, a third of an NLL+gradient evaluation) of
+ * sgp_nll / sgp_nll_dev / sgp_fit / sgp_spd_factor's inverse through the INT8 tensor pipe; 0 (default) = DMMA everywhere. */
+int sgp_set_ozaki(sgp_ctx* ctx, int nslices);
 /* C (M x N, column-major) = alpha A B^T + beta C with every product formed on the INT8 tensor pipe from ns = 4..8 signed 7-bit
  * slices per operand (Ozaki splitting; exact integer slice products in TMEM, one FP64 combination per element).  A (M x K) and
  * B (N x K): element (r, k) at ptr[r + k ld] (host pointers).  ns = 7 reproduces FP64 GEMM to ~1e-14 of sum |a||b|. */

@@ -80,6 +80,7 @@ _PROTOS = {
     "sgp_spd_factor": (c_i, [c_vp, c_dp, c_l, c_dp, c_dp, c_dp]),
     "sgp_selftest_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
     "sgp_i8mma_selftest": (c_i, [c_vp, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
+    "sgp_set_ozaki": (c_i, [c_vp, c_i]),
     "sgp_ozaki_gemm_host": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_d, c_dp, c_l, c_dp, c_l, c_d, c_dp, c_l]),
     "sgp_ozaki_bench": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_i, c_dp]),
     "sgp_gemm_host": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_d, c_dp, c_l, c_dp, c_l, c_dp, c_l]),
@@ -154,6 +155,10 @@ class Context:
 
     def synchronize(self):
         check(lib().sgp_synchronize(self.handle), "sgp_synchronize")
+
+    def set_ozaki(self, nslices):
+        """OPT-IN: 4..8 = the lauum stage of the inverse runs on the INT8 tensor pipe (csrc/ozaki.cu); 0 = DMMA (default)."""
+        check(lib().sgp_set_ozaki(self.handle, int(nslices)), "sgp_set_ozaki")
 
     def release_workspace(self):
         check(lib().sgp_release_workspace(self.handle), "sgp_release_workspace")

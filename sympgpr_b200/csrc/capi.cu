@@ -172,7 +172,7 @@ int sgp_release_workspace(sgp_ctx* ctx)
     Ctx& c = ctx->c;
     cudaStreamSynchronize(c.stream);
     c.Kmat.release(); c.Wmat.release(); c.Tmat.release(); c.Dinv.release(); c.vecs.release();
-    c.pts.release(); c.partial.release(); c.small.release(); c.mapbuf.release(); c.io.release(); c.flags.release();
+    c.pts.release(); c.partial.release(); c.small.release(); c.mapbuf.release(); c.io.release(); c.flags.release(); c.ozbuf.release();
     for (auto& e : c.acache) { e.buf.release(); e.kyinv = nullptr; e.z = nullptr; e.n = 0; }
     return ST_OK;
 }
@@ -1043,6 +1043,15 @@ int sgp_gemm_host(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K,
     SGP_TRY(dmma_gemm(c, al, bl, g));
     SGP_TRY(download(c, C, dC, szC));
     return sync(c);
+}
+
+int sgp_set_ozaki(sgp_ctx* ctx, int nslices)
+{
+    SGP_TRY(check_ctx(ctx));
+    if (nslices != 0 && (nslices < 4 || nslices > 8)) { set_error("set_ozaki: 0 (off) or 4..8 slices"); return ST_BADARG; }
+    ctx->c.ozaki_slices = nslices;
+    if (nslices == 0) { cudaStreamSynchronize(ctx->c.stream); ctx->c.ozbuf.release(); }
+    return ST_OK;
 }
 
 int sgp_i8mma_selftest(sgp_ctx* ctx, int K, int* mismatches, int* probe_ref, int* probe_got)

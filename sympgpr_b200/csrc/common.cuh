@@ -86,7 +86,8 @@ struct Ctx {
     int device = 0;
     cudaStream_t stream = nullptr;    // main stream (borrowed or owned)
     bool own_stream = false;
-    DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io, flags;
+    DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io, flags, ozbuf;
+    int ozaki_slices = 0;             // > 0: OPT-IN, the lauum stage of the inverse runs on the INT8 tensor pipe (ozaki.cu)
     AlphaEntry acache[ALPHA_CACHE];
     unsigned long long aclock = 0ull, ahits = 0ull, amisses = 0ull;
     double* h_res = nullptr;          // pinned host staging (RES_DOUBLES + spare)

@@ -14,6 +14,7 @@
 #include "fill.cuh"
 #include "dof2.cuh"
 #include "grad.cuh"
+#include "ozaki.cuh"
 
 namespace sgp {
 
@@ -176,7 +177,14 @@ int nll_enqueue(Ctx& c, const NllJob& job)
         // K now holds X = L^-1: alpha = L^-T w = X^T w is one pass over its columns
         if (need_alpha) SGP_TRY(gemv_t_lower(c, K, n_pad, n_pad, wv, av));
         SGP_TRY(c.mark(4));
-        SGP_TRY(lauum(c, K, n_pad, n_pad, W, n_pad));
+        if (c.ozaki_slices > 0 && (long)c.ozaki_slices * n_pad * 4096 < 2147483647L) {
+            // opt-in: W = X^T X from INT8 slice products on the 5th-generation tensor core (sgp_set_ozaki)
+            const size_t wb = ozaki_lauum_workspace_bytes(n_pad, c.ozaki_slices);
+            SGP_TRY(c.ozbuf.reserve(wb));
+            SGP_TRY(ozaki_lauum(c, c.ozaki_slices, K, n_pad, n_pad, W, n_pad, c.ozbuf.p, wb));
+        } else {
+            SGP_TRY(lauum(c, K, n_pad, n_pad, W, n_pad));
+        }
         SGP_TRY(c.mark(5));
         if (job.ngrad > 0) {
             if (dof2) SGP_TRY(grad4_contract(c, job.d_x, N, job.hyp[0], job.hyp[1], job.hyp[2], W, n_pad, av, partial));

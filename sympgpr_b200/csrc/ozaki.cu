@@ -101,6 +101,7 @@ __host__ __device__ inline uint32_t sw128_offset(int r, int k)
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((((k >> 4) ^ (r & 7)) & 7) << 4) + (k & 15));
 }
 
+constexpr int OZ_KC_ = 128;                            // k-chunk (bytes of one swizzled row)
 constexpr int ST_M = 128, ST_N = 64, ST_KC = 128;     // self test: one 128 x 64 tile, k-chunks of 128 bytes
 
 // ---------------------------------------------------------------------------------------------------------
@@ -242,6 +243,56 @@ __global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict_
     }
 }
 
+// K-major input: element (r, k) at X[k + r ld] (a COLUMN-major matrix whose columns are the operand rows: A = X^T).
+// tri != 0: X is lower triangular (entries with k < r are zero and are not read); only k >= 128 floor(r / 128) is written
+// (the GEMM of a triangular product never loads the chunks before that).
+__global__ void __launch_bounds__(256) oz_rowexp_kmajor_kernel(const double* __restrict__ X, long ld, long R, long K, int tri, int* __restrict__ exps)
+{
+    const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= R) return;
+    const double* row = X + r * ld;
+    double mx = 0.0;
+    for (long k = (tri ? r : 0) + lane; k < K; k += 32) mx = fmax(mx, fabs(row[k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) {
+        int e = 0;
+        if (mx > 0.0 && mx <= DBL_MAX) frexp(mx, &e);
+        exps[r] = e;
+    }
+}
+
+template <int NS>
+__global__ void __launch_bounds__(256) oz_slice_kmajor_kernel(const double* __restrict__ X, long ld, long R, long K, int tri,
+                                                               const int* __restrict__ exps, int8_t* __restrict__ slices, long Rp, long Kp)
+{
+    // one thread = 16 consecutive k of one row: 128 bytes in, NS x 16 bytes out
+    const long kb = (long)blockIdx.x * blockDim.x + threadIdx.x;       // 16-element block index along k
+    const long r = blockIdx.y;
+    if (kb * 16 >= Kp) return;
+    const long k0 = kb * 16;
+    if (tri && k0 + 16 <= (r / OZ_KC_) * OZ_KC_) return;                // never loaded
+    const int e = (r < R) ? exps[r] : 0;
+    int8_t out[NS][16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) {
+        const long k = k0 + i;
+        double y = 0.0;
+        if (r < R && k < K && (!tri || k >= r)) y = scalbn(X[k + r * ld], 6 - e);
+        if (!(fabs(y) <= 64.0)) y = 0.0;
+#pragma unroll
+        for (int sidx = 0; sidx < NS; sidx++) {
+            const double a = rint(y);
+            out[sidx][i] = (int8_t)(int)a;
+            y = (y - a) * 128.0;
+        }
+    }
+#pragma unroll
+    for (int sidx = 0; sidx < NS; sidx++)
+        *reinterpret_cast<uint4*>(slices + (size_t)sidx * Rp * Kp + (size_t)r * Kp + k0) = *reinterpret_cast<const uint4*>(out[sidx]);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // (3) the GEMM.  One CTA (four warps) per 128 x 64 output tile, persistent over tiles.  Thread 0 is the whole control
 // flow of the main loop: per k-chunk of 128 it issues 2 NS bulk tensor copies (cp.async.bulk.tensor.3d, 128-byte swizzle:
@@ -266,6 +317,7 @@ struct OzArgs {
     double* C; long ldc;                // column-major output
     long M, N, K;                       // logical sizes (M, N padded to tiles inside the slices; K padded to 128)
     int mt, nt, nk;                     // tiles / k-chunks
+    int tri;                            // 1: C = X^T X with X lower triangular: tiles with 64 tn <= 128 tm + 127 only, k-chunks >= tm
     double alpha, beta;
 };
 
@@ -295,15 +347,27 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     const uint32_t tmem = tmem_base_s;
     constexpr uint32_t idesc = umma_idesc_i8(OZ_M, OZ_N);
     uint32_t ph_full = 0, ph_mma = 0;
-    const long ntiles = (long)a.mt * a.nt;
+    const long ntiles = a.tri ? (long)a.mt * (a.mt + 1) : (long)a.mt * a.nt;
     for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int tm = (int)(tile % a.mt), tn = (int)(tile / a.mt);
+        int tm, tn, kc0 = 0;
+        if (a.tri) {
+            // tile = tm (tm + 1) + tn, 0 <= tn < 2 tm + 2 (lower triangle in 128 x 64 tiles; small tm = long k-ranges first)
+            long r = (long)((sqrt(4.0 * (double)tile + 1.0) - 1.0) * 0.5);
+            while ((r + 1) * (r + 2) <= tile) r++;
+            while (r * (r + 1) > tile) r--;
+            tm = (int)r;
+            tn = (int)(tile - r * (r + 1));
+            kc0 = tm;
+        } else {
+            tm = (int)(tile % a.mt);
+            tn = (int)(tile / a.mt);
+        }
         if (tid < OZ_N) {
             const long n = (long)tn * OZ_N + tid;
             s_eb[tid] = (n < a.N) ? a.eb[n] : 0;
         }
         if (tid == 0) {
-            for (int kc = 0; kc < a.nk; kc++) {
+            for (int kc = kc0; kc < a.nk; kc++) {
                 mbar_arrive_expect_tx(&bar_full, (uint32_t)(NS * (OZ_M + OZ_N) * OZ_KC));
 #pragma unroll
                 for (int s = 0; s < NS; s++) {
@@ -322,7 +386,7 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
 #pragma unroll
                         for (int ks = 0; ks < OZ_KC / 32; ks++)
                             umma_i8(tmem + d * OZ_N, umma_desc_k128(sA + s * OZ_M * OZ_KC + ks * 32),
-                                    umma_desc_k128(sB + t * OZ_N * OZ_KC + ks * 32), idesc, (kc > 0 || ks > 0 || s > 0) ? 1u : 0u);
+                                    umma_desc_k128(sB + t * OZ_N * OZ_KC + ks * 32), idesc, (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u);
                     }
                 }
                 umma_commit(&bar_mma);
@@ -402,7 +466,7 @@ int oz_launch(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, const OzAr
         SGP_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const long ntiles = (long)a.mt * a.nt;
+    const long ntiles = a.tri ? (long)a.mt * (a.mt + 1) : (long)a.mt * a.nt;
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     oz_gemm_kernel<NS><<<(unsigned)(ntiles < sms ? ntiles : sms), 128, smem, c.stream>>>(tmA, tmB, a);
     SGP_CUDA(cudaGetLastError());
@@ -463,7 +527,7 @@ int ozaki_gemm_presliced(Ctx& c, int ns, long M, long N, long K, double alpha, d
     SGP_TRY(make_slice_tmap(&tmB, w.sB, w.Np, w.Kp, ns, OZ_N));
     OzArgs a;
     a.ea = w.ea; a.eb = w.eb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-    a.mt = (int)(w.Mp / OZ_M); a.nt = (int)(w.Np / OZ_N); a.nk = (int)(w.Kp / OZ_KC); a.alpha = alpha; a.beta = beta;
+    a.mt = (int)(w.Mp / OZ_M); a.nt = (int)(w.Np / OZ_N); a.nk = (int)(w.Kp / OZ_KC); a.alpha = alpha; a.beta = beta; a.tri = 0;
     switch (ns) {
     case 4: return oz_launch<4>(c, tmA, tmB, a);
     case 5: return oz_launch<5>(c, tmA, tmB, a);
@@ -484,6 +548,47 @@ int ozaki_slice_operands(Ctx& c, int ns, long M, long N, long K, const double* A
     case 6: SGP_TRY(oz_slice<6>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<6>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
     case 7: SGP_TRY(oz_slice<7>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<7>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
     default: SGP_TRY(oz_slice<8>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<8>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
+    }
+}
+
+size_t ozaki_lauum_workspace_bytes(long n_pad, int ns)
+{
+    return (size_t)ns * (size_t)n_pad * (size_t)n_pad + (size_t)n_pad * sizeof(int) + 1024;
+}
+
+// W (lower tiles, column-major, ldw) = X^T X for the lower-triangular X (n_pad x n_pad, column-major, ldx; n_pad a multiple of
+// 128) -- the lauum stage of the inverse -- on the INT8 tensor pipe: ONE operand is sliced (A = B = X^T, whose rows are the
+// contiguous columns of X), the tile set is the lower triangle and every tile skips the k-chunks above its rows.
+int ozaki_lauum(Ctx& c, int ns, const double* X, long n_pad, long ldx, double* W, long ldw, void* work, size_t work_bytes)
+{
+    if (ns < 4 || ns > 8 || n_pad <= 0 || n_pad % OZ_M) { set_error("ozaki_lauum: bad arguments"); return ST_BADARG; }
+    if ((long)ns * n_pad * 4096 >= 2147483647L) { set_error("ozaki_lauum: order %ld too large for exact INT32 accumulation with %d slices", n_pad, ns); return ST_BADARG; }
+    if (work_bytes < ozaki_lauum_workspace_bytes(n_pad, ns)) { set_error("ozaki_lauum: workspace too small"); return ST_BADARG; }
+    int8_t* sl = reinterpret_cast<int8_t*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
+    int* ex = reinterpret_cast<int*>(sl + (size_t)ns * n_pad * n_pad);
+    oz_rowexp_kmajor_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex);
+    const dim3 grid((unsigned)((n_pad / 16 + 255) / 256), (unsigned)n_pad);
+    switch (ns) {
+    case 4: oz_slice_kmajor_kernel<4><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
+    case 5: oz_slice_kmajor_kernel<5><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
+    case 6: oz_slice_kmajor_kernel<6><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
+    case 7: oz_slice_kmajor_kernel<7><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
+    default: oz_slice_kmajor_kernel<8><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
+    }
+    SGP_CUDA(cudaGetLastError());
+    count_launch(2);
+    CUtensorMap tmA, tmB;
+    SGP_TRY(make_slice_tmap(&tmA, sl, n_pad, n_pad, ns, OZ_M));
+    SGP_TRY(make_slice_tmap(&tmB, sl, n_pad, n_pad, ns, OZ_N));
+    OzArgs a;
+    a.ea = ex; a.eb = ex; a.C = W; a.ldc = ldw; a.M = n_pad; a.N = n_pad; a.K = n_pad;
+    a.mt = (int)(n_pad / OZ_M); a.nt = (int)(n_pad / OZ_N); a.nk = (int)(n_pad / OZ_KC); a.alpha = 1.0; a.beta = 0.0; a.tri = 1;
+    switch (ns) {
+    case 4: return oz_launch<4>(c, tmA, tmB, a);
+    case 5: return oz_launch<5>(c, tmA, tmB, a);
+    case 6: return oz_launch<6>(c, tmA, tmB, a);
+    case 7: return oz_launch<7>(c, tmA, tmB, a);
+    default: return oz_launch<8>(c, tmA, tmB, a);
     }
 }
 

@@ -16,4 +16,8 @@ int ozaki_gemm_presliced(Ctx& c, int ns, long M, long N, long K, double alpha, d
 int ozaki_gemm(Ctx& c, int ns, long M, long N, long K, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
                double* C, long ldc, void* work, size_t work_bytes);
 
+// lauum on the INT8 pipe: W = X^T X (lower tiles) for the lower-triangular inverse factor X; work: ozaki_lauum_workspace_bytes
+size_t ozaki_lauum_workspace_bytes(long n_pad, int ns);
+int ozaki_lauum(Ctx& c, int ns, const double* X, long n_pad, long ldx, double* W, long ldw, void* work, size_t work_bytes);
+
 }  // namespace sgp

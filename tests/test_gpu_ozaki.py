@@ -78,3 +78,51 @@ def test_ozaki_gemm_against_the_dmma_gemm(api):
     scale = np.abs(A) @ np.abs(B).T
     assert np.max(np.abs(Cd - A @ B.T) / scale) < 1e-14
     assert np.max(np.abs(Co - Cd) / scale) < 1e-14
+
+
+@pytest.fixture()
+def ozaki_ctx():
+    """Switch the default context's lauum stage to the INT8 pipe for one test, and back."""
+    from sympgpr_b200 import _lib
+    ctx = _lib.context()
+    yield ctx
+    ctx.set_ozaki(0)
+
+
+@pytest.mark.parametrize("ns", [7, 8])
+@pytest.mark.parametrize("N", [100, 1024])
+def test_nll_gradient_with_lauum_on_the_int8_pipe(api, ozaki_ctx, N, ns):
+    """Opt-in route past the DMMA ceiling on the real path: K^-1 = X^T X (a third of an NLL+gradient evaluation) from INT8
+    slice products, judged on the SAME oracle values and tolerance (1e-9) as the DMMA path; the inverse itself against SciPy."""
+    import scipy.linalg
+    from oracle import oracle as O
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    vr, grr = O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    v0, g0 = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    ozaki_ctx.set_ozaki(ns)
+    v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    assert np.isclose(v, vr, rtol=1e-9) and v == v0                      # the value does not depend on the inverse
+    assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr, g0)
+    if N <= 200:
+        f = api.fit(hyp, d["xtrain"], d["ztrain"], 2 * N, want_inverse=True)
+        xt = d["xtrain"]
+        K = O.build_k_vec(xt[:N], xt[N:], xt[:N], xt[N:], hyp[:3]) + hyp[3] * np.eye(2 * N)
+        Kir = scipy.linalg.inv(K)
+        assert np.allclose(f["Kyinv"], Kir, rtol=1e-8, atol=1e-9 * np.abs(Kir).max())
+
+
+def test_full_size_gradient_with_lauum_on_the_int8_pipe(api, ozaki_ctx):
+    """BASELINE's headline size (N = 16 384, n = 32 768) with the lauum stage on the INT8 pipe (8 slices) against the CPU
+    golden (tests/golden/fullsize_nll_N16384.json), 1e-9 as for the DMMA path."""
+    import json
+    import os
+    from oracle import oracle as O
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_nll_N16384.json")))
+    N = g["N"]
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    ozaki_ctx.set_ozaki(8)
+    v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    assert abs(v - g["nll"]) <= 1e-9 * abs(g["nll"])
+    assert np.allclose(gr, g["grad"], rtol=1e-9, atol=1e-9 * np.abs(g["grad"]).max()), (gr, g["grad"])

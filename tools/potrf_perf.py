@@ -10,6 +10,9 @@ L = _lib.lib(); ctx = _lib.context(0)
 dev = torch.device("cuda", 0)
 st = torch.cuda.Stream(device=dev); torch.cuda.set_stream(st); ctx.set_stream(st.cuda_stream)
 _lib.check(L.sgp_set_profiling(ctx.handle, 1), "prof")
+import os
+OZ = int(os.environ.get("SGP_OZAKI", "0"))
+ctx.set_ozaki(OZ)
 for N in Ns:
     d = W.standard_map_training(N); hyp = W.timing_hyp(N, d["sig"], 1e-8)
     x = torch.from_numpy(d["xtrain"].copy()).to(dev); z = torch.from_numpy(d["ztrain"].copy()).to(dev)
@@ -25,6 +28,6 @@ for N in Ns:
     ms = e0.elapsed_time(e1) / reps
     sm = (ctypes.c_double * 7)(); _lib.check(L.sgp_stage_times(ctx.handle, sm), "st")
     n = 2.0 * N
-    print(json.dumps({"lib": _lib.LIB_PATH.split("/")[-1], "N": N, "n": 2 * N, "ms": round(ms, 4), "TF": round(n**3 / ms / 1e9, 2),
+    print(json.dumps({"lib": _lib.LIB_PATH.split("/")[-1], "ozaki": OZ, "N": N, "n": 2 * N, "ms": round(ms, 4), "TF": round(n**3 / ms / 1e9, 2),
                       "potrf": round(sm[1], 4), "trtri": round(sm[3], 4), "lauum": round(sm[4], 4), "us_per_tile_col": round(1e3 * sm[1] / max(1, (2 * N + 127) // 128), 1),
                       "nll": float(res[0].item()), "g": [float(res[1].item()), float(res[2].item())]}), flush=True)

@@ -22,6 +22,8 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <vector>
+
 #include "mbar.cuh"
 
 namespace sgp {
@@ -302,7 +304,7 @@ __global__ void __launch_bounds__(256) oz_slice_kmajor_kernel(const double* __re
 // read their 32 TMEM lanes (tcgen05.ld 32x32b.x32), combine the NS integer accumulators in FP64 from the smallest term up,
 // apply 2^(ea + eb - 12) and write C.  Single stage: 24 KB per slice pair and k-chunk, 192 KB at NS = 8.
 // ---------------------------------------------------------------------------------------------------------
-constexpr int OZ_M = 128, OZ_N = 64, OZ_KC = 128;
+constexpr int OZ_M = 128, OZ_N = 64, OZ_KC = 64, OZ_STAGES = 2;
 
 __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar)
 {
@@ -312,22 +314,40 @@ __device__ __forceinline__ void tma_load_3d(void* smem_dst, const CUtensorMap* t
         : "memory");
 }
 
+// K-major operand tile with 64-byte rows in the canonical 64-byte-swizzled layout (8-row atoms of 512 bytes): layout type 4,
+// stride byte offset 512; written by the tensor-map copies with CU_TENSOR_MAP_SWIZZLE_64B, tile base 512-byte aligned
+__device__ __forceinline__ uint64_t umma_desc_k64(const void* smem_tile)
+{
+    const uint64_t addr = (uint64_t)((smem_u32(smem_tile) & 0x3FFFFu) >> 4);
+    return addr | (1ull << 16) | ((uint64_t)(512 >> 4) << 32) | (1ull << 46) | (4ull << 61);
+}
+
 struct OzArgs {
     const int* ea; const int* eb;       // row exponents of A (M) and B (N)
     double* C; long ldc;                // column-major output
     long M, N, K;                       // logical sizes (M, N padded to tiles inside the slices; K padded to 128)
-    int mt, nt, nk;                     // tiles / k-chunks
-    int tri;                            // 1: C = X^T X with X lower triangular: tiles with 64 tn <= 128 tm + 127 only, k-chunks >= tm
+    int mt, nt, nk;                     // tiles / k-chunks of OZ_KC
+    int tri;                            // 1: C = X^T X with X lower triangular: tiles with 64 tn <= 128 tm + 127 only, k >= 128 tm
+    const int2* tiles; long ntiles;     // (tm, tn) of every tile in processing order (oz_tile_list)
     double alpha, beta;
 };
 
+// One CTA (four warps) per 128 x 64 output tile, persistent over tiles; warp-specialised main loop on a two-stage ring:
+//   warp 0, one lane: TMA producer -- per k-chunk of 64 it waits for the stage to be free and issues 2 NS bulk tensor copies
+//                     (cp.async.bulk.tensor.3d, 64-byte swizzle: one box per slice of A and of B) onto the stage's full barrier;
+//   warp 1, one lane: MMA issuer -- waits for the bytes, issues NS (NS + 1) / 2 x 2 UMMAs (tcgen05.mma kind::i8, M = 128,
+//                     N = 64, K = 32; the pairs with s + t = d accumulate into TMEM columns [64 d, 64 d + 64)) and commits them
+//                     to the stage's empty barrier (and, after the last chunk, to the accumulator barrier);
+//   all four warps:   epilogue -- tcgen05.ld of their 32 TMEM lanes, the NS integer accumulators combined in FP64 from the
+//                     smallest term up, 2^(ea + eb - 12), C written.
+// 12 KB per slice and stage: 192 KB of shared memory at NS = 8; all 512 TMEM columns at NS = 8.
 template <int NS>
 __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* sA = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);     // NS x 16 KB
-    uint8_t* sB = sA + NS * OZ_M * OZ_KC;                                                           // NS x  8 KB
-    __shared__ unsigned long long bar_full, bar_mma;
+    uint8_t* sbase = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    constexpr int A_BYTES = OZ_M * OZ_KC, B_BYTES = OZ_N * OZ_KC, STAGE_BYTES = NS * (A_BYTES + B_BYTES);
+    __shared__ unsigned long long bar_full[OZ_STAGES], bar_empty[OZ_STAGES], bar_acc;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_eb[OZ_N];
     constexpr uint32_t TCOLS = (NS * OZ_N <= 64) ? 64 : (NS * OZ_N <= 128) ? 128 : (NS * OZ_N <= 256) ? 256 : 512;
@@ -335,8 +355,8 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
     if (tid == 0) {
-        mbar_init(&bar_full, 1);
-        mbar_init(&bar_mma, 1);
+        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        mbar_init(&bar_acc, 1);
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -346,55 +366,59 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     constexpr uint32_t idesc = umma_idesc_i8(OZ_M, OZ_N);
-    uint32_t ph_full = 0, ph_mma = 0;
-    const long ntiles = a.tri ? (long)a.mt * (a.mt + 1) : (long)a.mt * a.nt;
-    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        int tm, tn, kc0 = 0;
-        if (a.tri) {
-            // tile = tm (tm + 1) + tn, 0 <= tn < 2 tm + 2 (lower triangle in 128 x 64 tiles; small tm = long k-ranges first)
-            long r = (long)((sqrt(4.0 * (double)tile + 1.0) - 1.0) * 0.5);
-            while ((r + 1) * (r + 2) <= tile) r++;
-            while (r * (r + 1) > tile) r--;
-            tm = (int)r;
-            tn = (int)(tile - r * (r + 1));
-            kc0 = tm;
-        } else {
-            tm = (int)(tile % a.mt);
-            tn = (int)(tile / a.mt);
+    uint32_t it = 0, ph_acc = 0;                         // `it`: chunks handled so far by this thread's role (ring position)
+    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+        const int2 tt = a.tiles[tile];
+        const int tm = tt.x, tn = tt.y;
+        const int kc0 = a.tri ? tm * (OZ_M / OZ_KC) : 0;
+        if (tid >= 64) {
+            const long n = (long)tn * OZ_N + (tid - 64);
+            s_eb[tid - 64] = (n < a.N) ? a.eb[n] : 0;
         }
-        if (tid < OZ_N) {
-            const long n = (long)tn * OZ_N + tid;
-            s_eb[tid] = (n < a.N) ? a.eb[n] : 0;
-        }
-        if (tid == 0) {
-            for (int kc = kc0; kc < a.nk; kc++) {
-                mbar_arrive_expect_tx(&bar_full, (uint32_t)(NS * (OZ_M + OZ_N) * OZ_KC));
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int kc = kc0; kc < a.nk; kc++, it++) {
+                    const uint32_t st = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
+                    mbar_wait(&bar_empty[st], ph ^ 1u);
+                    mbar_arrive_expect_tx(&bar_full[st], (uint32_t)STAGE_BYTES);
+                    uint8_t* sA = sbase + st * STAGE_BYTES;
+                    uint8_t* sB = sA + NS * A_BYTES;
 #pragma unroll
-                for (int s = 0; s < NS; s++) {
-                    tma_load_3d(sA + s * OZ_M * OZ_KC, &tmA, kc * OZ_KC, tm * OZ_M, s, &bar_full);
-                    tma_load_3d(sB + s * OZ_N * OZ_KC, &tmB, kc * OZ_KC, tn * OZ_N, s, &bar_full);
-                }
-                mbar_wait(&bar_full, ph_full);
-                ph_full ^= 1u;
-                tc_fence_after();
-#pragma unroll
-                for (int s = 0; s < NS; s++) {
-#pragma unroll
-                    for (int t = 0; t < NS - s; t++) {
-                        const int d = s + t;
-                        // first write of accumulator d in this tile: (kc, ks) = (0, 0) of the pair (s, t) = (0, d)
-#pragma unroll
-                        for (int ks = 0; ks < OZ_KC / 32; ks++)
-                            umma_i8(tmem + d * OZ_N, umma_desc_k128(sA + s * OZ_M * OZ_KC + ks * 32),
-                                    umma_desc_k128(sB + t * OZ_N * OZ_KC + ks * 32), idesc, (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u);
+                    for (int s = 0; s < NS; s++) {
+                        tma_load_3d(sA + s * A_BYTES, &tmA, kc * OZ_KC, tm * OZ_M, s, &bar_full[st]);
+                        tma_load_3d(sB + s * B_BYTES, &tmB, kc * OZ_KC, tn * OZ_N, s, &bar_full[st]);
                     }
                 }
-                umma_commit(&bar_mma);
-                mbar_wait(&bar_mma, ph_mma);             // the stage may be overwritten; after the last chunk: accumulators final
-                ph_mma ^= 1u;
             }
+            __syncwarp();
+        } else if (warp == 1) {
+            if (lane == 0) {
+                for (int kc = kc0; kc < a.nk; kc++, it++) {
+                    const uint32_t st = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
+                    mbar_wait(&bar_full[st], ph);
+                    tc_fence_after();
+                    const uint8_t* sA = sbase + st * STAGE_BYTES;
+                    const uint8_t* sB = sA + NS * A_BYTES;
+#pragma unroll
+                    for (int s = 0; s < NS; s++) {
+#pragma unroll
+                        for (int t = 0; t < NS - s; t++) {
+                            // first write of accumulator d = s + t in this tile: chunk kc0, k-step 0 of the pair (0, d)
+#pragma unroll
+                            for (int ks = 0; ks < OZ_KC / 32; ks++)
+                                umma_i8(tmem + (s + t) * OZ_N, umma_desc_k64(sA + s * A_BYTES + ks * 32), umma_desc_k64(sB + t * B_BYTES + ks * 32),
+                                        idesc, (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&bar_empty[st]);             // the stage is free once these UMMAs have read it
+                }
+                umma_commit(&bar_acc);                       // all accumulators of this tile final
+            }
+            __syncwarp();
         }
-        __syncthreads();                                 // thread 0 has seen the last commit complete
+        __syncthreads();                                 // s_eb visible; roles done issuing
+        mbar_wait(&bar_acc, ph_acc);
+        ph_acc ^= 1u;
         tc_fence_after();
         // epilogue: thread = row m of the tile (TMEM lane 32 warp + lane)
         const long m = (long)tm * OZ_M + 32 * warp + lane;
@@ -433,6 +457,40 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
+// Processing order of the output tiles.  Operand bytes per tile and k-chunk are 2 NS x 12 KB against 2 NS (NS + 1) UMMAs, i.e.
+// ~340 INT8 ops per byte -- below the ~730 ops/byte the tensor pipe needs from HBM -- so the tiles that run at the same time
+// must share their operand panels in L2: super-tiles of 8 (tm) x 16 (tn) = 128 tiles (about one wave of 148 CTAs) touch 8 A
+// panels and 16 B panels instead of 64 + 2.  Triangular products: the same blocks over the lower triangle, top block rows
+// (longest k-ranges) first.  The list lives in device memory, one per (mt, nt, tri) and device.
+struct OzTileList { int mt = 0, nt = 0, tri = -1; long n = 0; DBuf buf; };
+
+int oz_tile_list(Ctx& c, int mt, int nt, int tri, const int2** d_tiles, long* ntiles)
+{
+    static OzTileList lists[64][2];
+    if (c.device < 0 || c.device >= 64) { set_error("ozaki: device index out of range"); return ST_BADARG; }
+    OzTileList& L = lists[c.device][tri ? 1 : 0];
+    if (L.mt != mt || L.nt != nt || L.tri != tri || !L.buf.p) {
+        std::vector<int2> v;
+        constexpr int BM = 8, BN = 16;
+        for (int TM = 0; TM * BM < mt; TM++)
+            for (int TN = 0; TN * BN < nt; TN++)
+                for (int j = 0; j < BN; j++)
+                    for (int i = 0; i < BM; i++) {
+                        const int tm = TM * BM + i, tn = TN * BN + j;
+                        if (tm >= mt || tn >= nt) continue;
+                        if (tri && tn > 2 * tm + 1) continue;
+                        v.push_back(make_int2(tm, tn));
+                    }
+        SGP_TRY(L.buf.reserve((v.size() + 1) * sizeof(int2)));
+        SGP_CUDA(cudaMemcpyAsync(L.buf.p, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
+        SGP_CUDA(cudaStreamSynchronize(c.stream));
+        L.mt = mt; L.nt = nt; L.tri = tri; L.n = (long)v.size();
+    }
+    *d_tiles = L.buf.as<int2>();
+    *ntiles = L.n;
+    return ST_OK;
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no link against libcuda)
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -452,7 +510,7 @@ int make_slice_tmap(CUtensorMap* tm, const int8_t* slices, long Rp, long Kp, int
     const cuuint32_t box[3] = {(cuuint32_t)OZ_KC, (cuuint32_t)box_rows, 1u};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
     const CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, (void*)slices, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return ST_CUDA; }
     return ST_OK;
 }
@@ -460,13 +518,13 @@ int make_slice_tmap(CUtensorMap* tm, const int8_t* slices, long Rp, long Kp, int
 template <int NS>
 int oz_launch(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, const OzArgs& a)
 {
-    const size_t smem = (size_t)NS * (OZ_M + OZ_N) * OZ_KC + 1024;
+    const size_t smem = (size_t)OZ_STAGES * NS * (OZ_M + OZ_N) * OZ_KC + 1024;
     static bool configured = false;
     if (!configured) {
         SGP_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const long ntiles = a.tri ? (long)a.mt * (a.mt + 1) : (long)a.mt * a.nt;
+    const long ntiles = a.ntiles;
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     oz_gemm_kernel<NS><<<(unsigned)(ntiles < sms ? ntiles : sms), 128, smem, c.stream>>>(tmA, tmB, a);
     SGP_CUDA(cudaGetLastError());
@@ -488,7 +546,7 @@ int oz_slice(Ctx& c, const double* X, long ld, long R, long K, int* exps, int8_t
 
 size_t ozaki_workspace_bytes(long M, long N, long K, int ns)
 {
-    const size_t Mp = (size_t)round_up(M, OZ_M), Np = (size_t)round_up(N, OZ_N), Kp = (size_t)round_up(K, OZ_KC);
+    const size_t Mp = (size_t)round_up(M, OZ_M), Np = (size_t)round_up(N, OZ_N), Kp = (size_t)round_up(K, OZ_KC_);
     return (size_t)ns * (Mp + Np) * Kp + (Mp + Np) * sizeof(int) + 1024;
 }
 
@@ -501,7 +559,7 @@ struct OzWork {
 static OzWork oz_carve(void* work, long M, long N, long K, int ns)
 {
     OzWork w;
-    w.Mp = round_up(M, OZ_M); w.Np = round_up(N, OZ_N); w.Kp = round_up(K, OZ_KC);
+    w.Mp = round_up(M, OZ_M); w.Np = round_up(N, OZ_N); w.Kp = round_up(K, OZ_KC_);
     w.sA = reinterpret_cast<int8_t*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
     w.sB = w.sA + (size_t)ns * w.Mp * w.Kp;
     w.ea = reinterpret_cast<int*>(w.sB + (size_t)ns * w.Np * w.Kp);
@@ -528,6 +586,7 @@ int ozaki_gemm_presliced(Ctx& c, int ns, long M, long N, long K, double alpha, d
     OzArgs a;
     a.ea = w.ea; a.eb = w.eb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
     a.mt = (int)(w.Mp / OZ_M); a.nt = (int)(w.Np / OZ_N); a.nk = (int)(w.Kp / OZ_KC); a.alpha = alpha; a.beta = beta; a.tri = 0;
+    SGP_TRY(oz_tile_list(c, a.mt, a.nt, 0, &a.tiles, &a.ntiles));
     switch (ns) {
     case 4: return oz_launch<4>(c, tmA, tmB, a);
     case 5: return oz_launch<5>(c, tmA, tmB, a);
@@ -583,6 +642,7 @@ int ozaki_lauum(Ctx& c, int ns, const double* X, long n_pad, long ldx, double* W
     OzArgs a;
     a.ea = ex; a.eb = ex; a.C = W; a.ldc = ldw; a.M = n_pad; a.N = n_pad; a.K = n_pad;
     a.mt = (int)(n_pad / OZ_M); a.nt = (int)(n_pad / OZ_N); a.nk = (int)(n_pad / OZ_KC); a.alpha = 1.0; a.beta = 0.0; a.tri = 1;
+    SGP_TRY(oz_tile_list(c, a.mt, a.nt, 1, &a.tiles, &a.ntiles));
     switch (ns) {
     case 4: return oz_launch<4>(c, tmA, tmB, a);
     case 5: return oz_launch<5>(c, tmA, tmB, a);

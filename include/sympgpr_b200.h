@@ -256,6 +256,17 @@ int sgp_i8mma_selftest(sgp_ctx* ctx, int K, int* mismatches, int* probe_ref, int
 /* OPT-IN switch of a context: nslices = 4..8 routes the lauum stage (W = X^T X, a third of an NLL+gradient evaluation) of
  * sgp_nll / sgp_nll_dev / sgp_fit / sgp_spd_factor's inverse through the INT8 tensor pipe; 0 (default) = DMMA everywhere. */
 int sgp_set_ozaki(sgp_ctx* ctx, int nslices);
+/* The same switch with the stages named: stages = 1 lauum (what sgp_set_ozaki selects), 2 = Cholesky factor + triangular
+ * inverse as ONE recursion whose products are sliced INT8 GEMMs (csrc/ozaki_chol.cu; blocks of <= leaf_n rows stay on the DMMA
+ * kernels; leaf_n <= 0: 4096), 3 = both: then all three n^3/3 stages of an NLL+gradient evaluation leave the DMMA pipe.
+ * Applies to evaluations that form the inverse and do not return the factor L (the recursion never holds L). */
+int sgp_set_ozaki_ex(sgp_ctx* ctx, int nslices, int stages, long leaf_n);
+/* Sliced product with every option the recursion uses, on HOST operands (test hook): la / lb = storage order of A (M x K) / B
+ * (N x K): 0 element (r, k) at ptr[r + k ld], 1 at ptr[k + r ld]; ta / tb: 0 all entries valid, 1 only k <= r, 2 only k >= r (the
+ * rest is never read); kmode: 1 k >= 128 tm, 2 k >= 64 tn, 4 k < 128 (tm + 1), 8 k < 64 (tn + 1) for the output tile (tm, tn) of
+ * 128 x 64; lower != 0: only tiles with 64 tn <= 128 tm + 127 are written. */
+int sgp_ozaki_gemm_host_ex(sgp_ctx* ctx, int ns, long M, long N, long K, double alpha, const double* A, long lda, int la, int ta,
+                           const double* B, long ldb, int lb, int tb, double beta, double* C, long ldc, int kmode, int lower);
 /* C (M x N, column-major) = alpha A B^T + beta C with every product formed on the INT8 tensor pipe from ns = 4..8 signed 7-bit
  * slices per operand (Ozaki splitting; exact integer slice products in TMEM, one FP64 combination per element).  A (M x K) and
  * B (N x K): element (r, k) at ptr[r + k ld] (host pointers).  ns = 7 reproduces FP64 GEMM to ~1e-14 of sum |a||b|. */

@@ -81,6 +81,8 @@ _PROTOS = {
     "sgp_selftest_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
     "sgp_i8mma_selftest": (c_i, [c_vp, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
     "sgp_set_ozaki": (c_i, [c_vp, c_i]),
+    "sgp_set_ozaki_ex": (c_i, [c_vp, c_i, c_i, c_l]),
+    "sgp_ozaki_gemm_host_ex": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_d, c_dp, c_l, c_i, c_i, c_dp, c_l, c_i, c_i, c_d, c_dp, c_l, c_i, c_i]),
     "sgp_ozaki_gemm_host": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_d, c_dp, c_l, c_dp, c_l, c_d, c_dp, c_l]),
     "sgp_ozaki_bench": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_i, c_dp]),
     "sgp_gemm_host": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_d, c_d, c_dp, c_l, c_dp, c_l, c_dp, c_l]),
@@ -159,6 +161,11 @@ class Context:
     def set_ozaki(self, nslices):
         """OPT-IN: 4..8 = the lauum stage of the inverse runs on the INT8 tensor pipe (csrc/ozaki.cu); 0 = DMMA (default)."""
         check(lib().sgp_set_ozaki(self.handle, int(nslices)), "sgp_set_ozaki")
+
+    def set_ozaki_ex(self, nslices, stages=3, leaf_n=0):
+        """OPT-IN with the stages named: 1 = lauum, 2 = Cholesky factor + triangular inverse as one recursion of sliced INT8
+        products (csrc/ozaki_chol.cu; blocks of <= leaf_n rows stay on the DMMA kernels), 3 = both; nslices = 0 switches off."""
+        check(lib().sgp_set_ozaki_ex(self.handle, int(nslices), int(stages), int(leaf_n)), "sgp_set_ozaki_ex")
 
     def release_workspace(self):
         check(lib().sgp_release_workspace(self.handle), "sgp_release_workspace")

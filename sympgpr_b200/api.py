@@ -632,3 +632,15 @@ def ozaki_gemm(A, B, C=None, alpha=1.0, beta=0.0, slices=7):
     check(_lib.lib().sgp_ozaki_gemm_host(_lib.context().handle, int(slices), M, N, K, float(alpha), dptr(A), M, dptr(B), N, float(beta),
                                          dptr(out), M), "ozaki_gemm")
     return out
+
+
+def ozaki_gemm_ex(A, B, M, N, K, la=0, ta=0, lb=0, tb=0, C=None, alpha=1.0, beta=0.0, kmode=0, lower=0, slices=7):
+    """Test hook of the sliced product the INT8 recursion is made of (sgp_ozaki_gemm_host_ex): A, B are Fortran-ordered 2-D
+    arrays holding the operands in storage order la / lb (0: A[r, k]; 1: A[k, r]) with validity ta / tb (1: k <= r, 2: k >= r;
+    the other half may hold anything) -- returns the Fortran-ordered (M, N) result."""
+    A, B = as_f64_fortran(A), as_f64_fortran(B)
+    out = np.zeros((M, N), order="F") if C is None else np.array(C, dtype=np.float64, order="F")
+    check(_lib.lib().sgp_ozaki_gemm_host_ex(_lib.context().handle, int(slices), M, N, K, float(alpha), dptr(A), A.shape[0], int(la), int(ta),
+                                            dptr(B), B.shape[0], int(lb), int(tb), float(beta), dptr(out), M, int(kmode), int(lower)),
+          "ozaki_gemm_ex")
+    return out

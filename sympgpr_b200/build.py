@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libsympgpr_b200.so")
-SOURCES = ["common.cu", "fill.cu", "dof2.cu", "chol.cu", "potrf_ll.cu", "grad.cu", "nll.cu", "map.cu", "ozaki.cu", "capi.cu"]
+SOURCES = ["common.cu", "fill.cu", "dof2.cu", "chol.cu", "potrf_ll.cu", "grad.cu", "nll.cu", "map.cu", "ozaki.cu", "ozaki_chol.cu", "capi.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-Xcompiler", "-fno-strict-aliasing"]
 

@@ -963,7 +963,17 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
     embed_spd_kernel<<<1024, 256, 0, c.stream>>>(dA, n, K, n_pad);
     SGP_CUDA(cudaGetLastError());
     SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), c.stream));
-    SGP_TRY(potrf(c, K, n_pad, n_pad, c.Dinv.as<double>(), logparts, info));
+    // opt-in INT8 route (sgp_set_ozaki_ex, stages bit 1): factor and inverse factor in one recursion; it never holds L
+    const bool oz_ok = c.ozaki_slices > 0 && (long)c.ozaki_slices * n_pad * 4096 < 2147483647L;
+    const bool oz_fact = oz_ok && (c.ozaki_stages & 2) && Ainv && !L && n_pad > c.ozaki_leaf;
+    if (oz_fact) {
+        const size_t wb = ozaki_factinv_workspace_bytes(n_pad, c.ozaki_slices);
+        SGP_TRY(c.ozbuf.reserve(wb));
+        SGP_TRY(c.Tmat.reserve((trtri_workspace_doubles(n_pad) + 2) * sizeof(double)));
+        SGP_TRY(ozaki_factinv(c, c.ozaki_slices, c.ozaki_leaf, K, n_pad, n_pad, c.Dinv.as<double>(), logparts, info, c.Tmat.as<double>(), c.ozbuf.p, wb));
+    } else {
+        SGP_TRY(potrf(c, K, n_pad, n_pad, c.Dinv.as<double>(), logparts, info));
+    }
     sum_logs_kernel<<<1, 32, 0, c.stream>>>(logparts, nt, info, dres);
     SGP_CUDA(cudaGetLastError());
     if (L) {
@@ -974,8 +984,14 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
     if (Ainv) {
         SGP_TRY(c.Wmat.reserve((size_t)n_pad * n_pad * sizeof(double)));
         SGP_TRY(c.Tmat.reserve((trtri_workspace_doubles(n_pad) + 2) * sizeof(double)));
-        SGP_TRY(trtri(c, K, n_pad, n_pad, c.Dinv.as<double>(), c.Tmat.as<double>()));
-        SGP_TRY(lauum(c, K, n_pad, n_pad, c.Wmat.as<double>(), n_pad));
+        if (!oz_fact) SGP_TRY(trtri(c, K, n_pad, n_pad, c.Dinv.as<double>(), c.Tmat.as<double>()));
+        if (oz_ok && (c.ozaki_stages & 1)) {
+            const size_t wb = ozaki_lauum_workspace_bytes(n_pad, c.ozaki_slices);
+            SGP_TRY(c.ozbuf.reserve(wb));
+            SGP_TRY(ozaki_lauum(c, c.ozaki_slices, K, n_pad, n_pad, c.Wmat.as<double>(), n_pad, c.ozbuf.p, wb));
+        } else {
+            SGP_TRY(lauum(c, K, n_pad, n_pad, c.Wmat.as<double>(), n_pad));
+        }
         extract_sym_kernel<<<1024, 256, 0, c.stream>>>(c.Wmat.as<double>(), n_pad, dA, n, 1);
         SGP_CUDA(cudaGetLastError());
         SGP_TRY(download(c, Ainv, dA, (size_t)n * n));
@@ -1050,8 +1066,48 @@ int sgp_set_ozaki(sgp_ctx* ctx, int nslices)
     SGP_TRY(check_ctx(ctx));
     if (nslices != 0 && (nslices < 4 || nslices > 8)) { set_error("set_ozaki: 0 (off) or 4..8 slices"); return ST_BADARG; }
     ctx->c.ozaki_slices = nslices;
+    ctx->c.ozaki_stages = 1;
     if (nslices == 0) { cudaStreamSynchronize(ctx->c.stream); ctx->c.ozbuf.release(); }
     return ST_OK;
+}
+
+int sgp_set_ozaki_ex(sgp_ctx* ctx, int nslices, int stages, long leaf_n)
+{
+    SGP_TRY(check_ctx(ctx));
+    if (nslices != 0 && (nslices < 4 || nslices > 8)) { set_error("set_ozaki_ex: 0 (off) or 4..8 slices"); return ST_BADARG; }
+    if (stages < 0 || stages > 3) { set_error("set_ozaki_ex: stages is a mask of 1 (lauum) and 2 (factor + triangular inverse)"); return ST_BADARG; }
+    if (leaf_n <= 0) leaf_n = 4096;
+    if (leaf_n % TILE) { set_error("set_ozaki_ex: leaf_n must be a multiple of %d", TILE); return ST_BADARG; }
+    ctx->c.ozaki_slices = nslices;
+    ctx->c.ozaki_stages = stages;
+    ctx->c.ozaki_leaf = leaf_n;
+    if (nslices == 0) { cudaStreamSynchronize(ctx->c.stream); ctx->c.ozbuf.release(); }
+    return ST_OK;
+}
+
+// The sliced product with every option of ozaki_slice / ozaki_gemm_sliced on HOST operands (tests compare it with NumPy):
+// la / lb: storage order of A / B (0: element (r, k) at ptr[r + k ld]; 1: at ptr[k + r ld]); ta / tb: 0, 1 (only k <= r valid),
+// 2 (only k >= r valid); kmode: OZ_KLO_* / OZ_KHI_* bits; lower: only the tiles that touch the lower triangle are written.
+int sgp_ozaki_gemm_host_ex(sgp_ctx* ctx, int ns, long M, long N, long K, double alpha, const double* A, long lda, int la, int ta,
+                           const double* B, long ldb, int lb, int tb, double beta, double* C, long ldc, int kmode, int lower)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || ldc < M) { set_error("ozaki_gemm_host_ex: bad arguments"); return ST_BADARG; }
+    if (lda < (la == OZ_MN ? M : K) || ldb < (lb == OZ_MN ? N : K)) { set_error("ozaki_gemm_host_ex: leading dimension too small"); return ST_BADARG; }
+    const size_t szA = (size_t)lda * (la == OZ_MN ? K : M), szB = (size_t)ldb * (lb == OZ_MN ? K : N), szC = (size_t)ldc * N;
+    const size_t bA = ozaki_sliced_bytes(M, K, ns) + 256, bB = ozaki_sliced_bytes(N, K, ns) + 256;
+    SGP_TRY(c.Kmat.reserve((szA + szB + szC + 8) * sizeof(double)));
+    SGP_TRY(c.Wmat.reserve(bA + bB));
+    double* dA = c.Kmat.as<double>();
+    double* dB = dA + szA; double* dC = dB + szB;
+    SGP_TRY(upload(c, dA, A, szA)); SGP_TRY(upload(c, dB, B, szB)); SGP_TRY(upload(c, dC, C, szC));
+    const OzSliced SA = ozaki_carve(c.Wmat.p, M, K, ns), SB = ozaki_carve((char*)c.Wmat.p + bA, N, K, ns);
+    SGP_TRY(ozaki_slice(c, ns, dA, lda, M, K, la, ta, SA));
+    SGP_TRY(ozaki_slice(c, ns, dB, ldb, N, K, lb, tb, SB));
+    SGP_TRY(ozaki_gemm_sliced(c, ns, SA, SB, M, N, alpha, beta, dC, ldc, kmode, lower));
+    SGP_TRY(download(c, C, dC, szC));
+    return sync(c);
 }
 
 int sgp_i8mma_selftest(sgp_ctx* ctx, int K, int* mismatches, int* probe_ref, int* probe_got)

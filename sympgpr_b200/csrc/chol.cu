@@ -174,6 +174,66 @@ gemv_t_lower_kernel(const double* __restrict__ X, long ld, const double* __restr
     if (lane == 0) alpha[c] = s;
 }
 
+// w = X z for the explicit lower-triangular X = L^-1 (the forward substitution L w = z, once the inverse factor exists and
+// the factor itself was never kept: the INT8 route, ozaki_chol.cu).  Block (i, j) = 128 rows x 512 columns on or below the
+// diagonal, rows down the threads (coalesced), partial sums per column chunk written to `part` and added in chunk order by
+// the second kernel: fixed summation order.  4 n^2 bytes, HBM-read bound.
+constexpr int TRMV_CW = 512;
+__global__ void __launch_bounds__(256)
+trmv_lower_part_kernel(const double* __restrict__ X, long ld, const double* __restrict__ z, double* __restrict__ part, long n)
+{
+    __shared__ double zs[TRMV_CW];
+    __shared__ double hi[TILE];
+    const int i = blockIdx.x, j = blockIdx.y, tid = threadIdx.x;
+    const long c0 = (long)j * TRMV_CW, rend = (long)(i + 1) * TILE;
+    if (c0 >= rend) return;
+    const long c1 = c0 + TRMV_CW < rend ? c0 + TRMV_CW : rend;
+    for (int k = tid; k < TRMV_CW; k += 256) zs[k] = (c0 + k < c1) ? z[c0 + k] : 0.0;
+    __syncthreads();
+    const int r = tid & (TILE - 1), half = tid >> 7;
+    const long row = (long)i * TILE + r;
+    const long hb = c0 + half * (TRMV_CW / 2);
+    long he = hb + TRMV_CW / 2;
+    if (he > c1) he = c1;
+    if (he > row + 1) he = row + 1;
+    const double* Xr = X + row;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    long cc = hb;
+    for (; cc + 3 < he; cc += 4) {
+        a0 = fma(Xr[cc * ld], zs[cc - c0], a0);
+        a1 = fma(Xr[(cc + 1) * ld], zs[cc + 1 - c0], a1);
+        a2 = fma(Xr[(cc + 2) * ld], zs[cc + 2 - c0], a2);
+        a3 = fma(Xr[(cc + 3) * ld], zs[cc + 3 - c0], a3);
+    }
+    for (; cc < he; cc++) a0 = fma(Xr[cc * ld], zs[cc - c0], a0);
+    const double s = (a0 + a1) + (a2 + a3);
+    if (half) hi[r] = s;
+    __syncthreads();
+    if (!half) part[(long)j * n + row] = s + hi[r];
+}
+
+__global__ void trmv_lower_sum_kernel(const double* __restrict__ part, double* __restrict__ w, long n)
+{
+    const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n) return;
+    const long rend = (row / TILE + 1) * TILE;
+    double s = 0.0;
+    for (long j = 0; j * TRMV_CW < rend; j++) s += part[j * n + row];
+    w[row] = s;
+}
+
+size_t trmv_lower_scratch_doubles(long n_pad) { return (size_t)((n_pad + TRMV_CW - 1) / TRMV_CW) * (size_t)n_pad; }
+
+int trmv_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* z, double* w, double* part)
+{
+    const dim3 grid((unsigned)(n_pad / TILE), (unsigned)((n_pad + TRMV_CW - 1) / TRMV_CW));
+    trmv_lower_part_kernel<<<grid, 256, 0, c.stream>>>(X, ldx, z, part, n_pad);
+    trmv_lower_sum_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, c.stream>>>(part, w, n_pad);
+    SGP_CUDA(cudaGetLastError());
+    count_launch(2);
+    return ST_OK;
+}
+
 int gemv_t_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* w, double* alpha)
 {
     gemv_t_lower_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, c.stream>>>(X, ldx, w, alpha, n_pad);
@@ -273,11 +333,23 @@ int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T
     SGP_CUDA(cudaGetLastError());
     count_launch();
     if (nt == 1) return ST_OK;
-    // the plan (per-depth problem lists in device memory) depends only on the pointers and the order: one per device
-    static TrtriPlan plans[64];
-    if (c.device < 0 || c.device >= 64) { set_error("trtri: device index %d out of range", c.device); return ST_BADARG; }
-    TrtriPlan& pl = plans[c.device];
-    if (pl.A != A || pl.lda != lda || pl.nt != nt || pl.T != T) SGP_TRY(trtri_build_plan(c, pl, A, lda, nt, T));
+    // the plan (per-depth problem lists in device memory) depends only on the pointers and the order; a few are kept (the
+    // INT8 route inverts its leaf blocks one after the other, ozaki_chol.cu)
+    constexpr int NPLAN = 48;
+    static TrtriPlan plans[NPLAN];
+    static int plan_dev[NPLAN];
+    static int next_plan = 0;
+    TrtriPlan* found = nullptr;
+    for (int i = 0; i < NPLAN && !found; i++)
+        if (plans[i].A == A && plans[i].lda == lda && plans[i].nt == nt && plans[i].T == T && plan_dev[i] == c.device) found = &plans[i];
+    if (!found) {
+        found = &plans[next_plan];
+        plan_dev[next_plan] = c.device;
+        next_plan = (next_plan + 1) % NPLAN;
+        if (found->d_e1.p) SGP_CUDA(cudaDeviceSynchronize());        // the entry being replaced may still be in use
+        SGP_TRY(trtri_build_plan(c, *found, A, lda, nt, T));
+    }
+    TrtriPlan& pl = *found;
     const GemmGroupEntry* e1 = pl.d_e1.as<GemmGroupEntry>();
     const GemmGroupEntry* e2 = pl.d_e2.as<GemmGroupEntry>();
     for (int d = (int)pl.tiles1.size() - 1; d >= 0; d--) {          // deepest nodes first

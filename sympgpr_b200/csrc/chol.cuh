@@ -16,6 +16,9 @@ size_t potrf_ll_flag_bytes(long n_pad);
 int trsv_bwd(Ctx& c, const double* L, long n_pad, long lda, const double* Dinv, double* w, double* alpha);
 // alpha = X^T w for the explicit lower-triangular inverse factor X (entries above the diagonal are not read)
 int gemv_t_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* w, double* alpha);
+// w = X z for the explicit lower-triangular X; part: trmv_lower_scratch_doubles(n_pad) doubles of device scratch
+int trmv_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* z, double* w, double* part);
+size_t trmv_lower_scratch_doubles(long n_pad);
 // alpha = W y for the symmetric W given by its lower triangle (tiles on and below the diagonal complete)
 int symv_lower(Ctx& c, const double* W, long n_pad, long ldw, const double* y, double* alpha);
 int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T);

@@ -87,7 +87,9 @@ struct Ctx {
     cudaStream_t stream = nullptr;    // main stream (borrowed or owned)
     bool own_stream = false;
     DBuf Kmat, Wmat, Tmat, Dinv, vecs, pts, partial, small, mapbuf, io, flags, ozbuf;
-    int ozaki_slices = 0;             // > 0: OPT-IN, the lauum stage of the inverse runs on the INT8 tensor pipe (ozaki.cu)
+    int ozaki_slices = 0;             // > 0: OPT-IN, stages of the inverse run on the INT8 tensor pipe (ozaki.cu, ozaki_chol.cu)
+    int ozaki_stages = 1;             // bit 0: lauum (W = X^T X); bit 1: factor + triangular inverse (ozaki_factinv)
+    long ozaki_leaf = 4096;           // blocks of at most this many rows stay on the DMMA kernels
     AlphaEntry acache[ALPHA_CACHE];
     unsigned long long aclock = 0ull, ahits = 0ull, amisses = 0ull;
     double* h_res = nullptr;          // pinned host staging (RES_DOUBLES + spare)

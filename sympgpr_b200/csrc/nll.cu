@@ -151,10 +151,16 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), st));
     SGP_TRY(c.mark(1));
 
-    // factor + forward substitution L w = z in one kernel (potrf_ll.cu).  0.5 z'alpha = 0.5 w'w, so the value
-    // needs nothing else; alpha itself comes from the backward substitution, or -- when the inverse is formed
-    // anyway -- from one transposed matrix-vector product with the explicit inverse factor.
-    SGP_TRY(potrf(c, K, n_pad, n_pad, Dinv, logparts, info, yv, wv));
+    // opt-in (sgp_set_ozaki_ex): factor and inverse factor in one recursion whose products run on the INT8 tensor pipe
+    // (ozaki_chol.cu).  It leaves X = L^-1 and never L, so it serves the evaluations that form the inverse and do not hand L out.
+    const bool oz_ok = c.ozaki_slices > 0 && (long)c.ozaki_slices * n_pad * 4096 < 2147483647L;
+    const bool oz_fact = oz_ok && (c.ozaki_stages & 2) && need_inv && !job.d_L && n_pad > c.ozaki_leaf;
+    if (!oz_fact) {
+        // factor + forward substitution L w = z in one kernel (potrf_ll.cu).  0.5 z'alpha = 0.5 w'w, so the value
+        // needs nothing else; alpha itself comes from the backward substitution, or -- when the inverse is formed
+        // anyway -- from one transposed matrix-vector product with the explicit inverse factor.
+        SGP_TRY(potrf(c, K, n_pad, n_pad, Dinv, logparts, info, yv, wv));
+    }
     SGP_TRY(c.mark(2));
     if (job.d_L) {
         tril_out_kernel<<<1024, 256, 0, st>>>(K, n_pad, job.d_L, n);
@@ -173,11 +179,18 @@ int nll_enqueue(Ctx& c, const NllJob& job)
     double* partial = c.partial.as<double>();
     if (need_inv) {
         double* W = c.Wmat.as<double>();
-        SGP_TRY(trtri(c, K, n_pad, n_pad, Dinv, c.Tmat.as<double>()));
+        if (oz_fact) {
+            const size_t wb = ozaki_factinv_workspace_bytes(n_pad, c.ozaki_slices);
+            SGP_TRY(c.ozbuf.reserve(wb > trmv_lower_scratch_doubles(n_pad) * sizeof(double) ? wb : trmv_lower_scratch_doubles(n_pad) * sizeof(double)));
+            SGP_TRY(ozaki_factinv(c, c.ozaki_slices, c.ozaki_leaf, K, n_pad, n_pad, Dinv, logparts, info, c.Tmat.as<double>(), c.ozbuf.p, wb));
+            SGP_TRY(trmv_lower(c, K, n_pad, n_pad, yv, wv, c.ozbuf.as<double>()));          // w = L^-1 z
+        } else {
+            SGP_TRY(trtri(c, K, n_pad, n_pad, Dinv, c.Tmat.as<double>()));
+        }
         // K now holds X = L^-1: alpha = L^-T w = X^T w is one pass over its columns
         if (need_alpha) SGP_TRY(gemv_t_lower(c, K, n_pad, n_pad, wv, av));
         SGP_TRY(c.mark(4));
-        if (c.ozaki_slices > 0 && (long)c.ozaki_slices * n_pad * 4096 < 2147483647L) {
+        if (oz_ok && (c.ozaki_stages & 1)) {
             // opt-in: W = X^T X from INT8 slice products on the 5th-generation tensor core (sgp_set_ozaki)
             const size_t wb = ozaki_lauum_workspace_bytes(n_pad, c.ozaki_slices);
             SGP_TRY(c.ozbuf.reserve(wb));

@@ -193,116 +193,168 @@ __global__ void i32_diff_kernel(const int32_t* __restrict__ a, const int32_t* __
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// (2) slicing: FP64 operand X (element (r, k) at X[r + k ld], the LAYOUT_MN of the Cholesky operands) ->
-//     exps[r] = e with max_k |X(r,k)| < 2^e,  slices[s][r][k] (INT8, k contiguous, row pitch Kp, slice pitch Rp Kp) with
+// (2) slicing: FP64 operand X (R rows x K) -> row exponents e(r) with max_k |X(r,k)| < 2^e(r) and NS INT8 slices
+//     slices[s][r][k] (k contiguous, row pitch Kp, slice pitch Rp Kp) with
 //     X(r,k) = 2^(e-6) sum_s slices[s][r][k] 2^(-7 s) + O(2^(e - 6 - 7 NS)),  |slice| <= 64.
-// Every step is exact in FP64 (scaling by powers of two, subtracting the integer just extracted); rows / columns beyond the
-// matrix are zero.
+// Every step is exact in FP64 (scaling by a power of two, round-to-nearest-integer by the 1.5 * 2^52 trick -- whose sum also
+// holds the integer in its low mantissa bits --, subtracting the integer just extracted).  Two storage orders of X:
+//     OZ_MN: element (r, k) at X[r + k ld]   (operand rows run down the columns of a column-major matrix)
+//     OZ_K:  element (r, k) at X[k + r ld]   (operand rows ARE the columns of a column-major matrix: the operand is X^T)
+// and triangular operands whose other half holds unrelated numbers (the Cholesky works in the lower triangle only):
+//     tri = 1: only k <= r is valid (OZ_MN view of a lower-triangular matrix),  tri = 2: only k >= r (OZ_K view of one);
+// invalid entries become zeros, and k-chunks that no GEMM tile of a triangular product loads are not written at all.
+// Rows / columns beyond R / K are zero.
 // ---------------------------------------------------------------------------------------------------------
-__global__ void oz_rowexp_kernel(const double* __restrict__ X, long ld, long R, long K, int* __restrict__ exps)
+constexpr double OZ_MAGIC = 6755399441055744.0;        // 1.5 * 2^52
+
+// y (|y| <= 64, or anything else -> treated as 0) -> NS signed slices through `put(s, byte)`
+template <int NS, class Put>
+__device__ __forceinline__ void oz_split(double y, Put put)
+{
+    if (!(fabs(y) <= 64.0)) y = 0.0;                   // NaN / Inf / out of range: not representable
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const double t = y + OZ_MAGIC;                 // low mantissa bits of t = rint(y) (two's complement)
+        put(s, (int8_t)__double2loint(t));
+        y = (y - (t - OZ_MAGIC)) * 128.0;
+    }
+}
+// 2^(6 - e) for -1000 < e <= 1024 (oz_exp_kernel keeps e in that range)
+__device__ __forceinline__ double oz_scale(int e) { return __hiloint2double((1023 + 6 - e) << 20, 0); }
+
+__device__ __forceinline__ int oz_exp_of(double mx)
+{
+    int e = 0;
+    if (mx >= 1e-290 && mx <= DBL_MAX) frexp(mx, &e);  // mx = f 2^e, 0.5 <= f < 1  =>  |x| 2^-e < 1; tiny rows count as zero rows
+    return e;
+}
+
+constexpr int OZ_RMK = 512;                            // columns per block of the row-maximum pass
+__global__ void __launch_bounds__(128) oz_rowmax_mn_kernel(const double* __restrict__ X, long ld, long R, long K, int tri,
+                                                           unsigned long long* __restrict__ rowmax)
+{
+    const long r = (long)blockIdx.x * 128 + threadIdx.x;
+    const long k0 = (long)blockIdx.y * OZ_RMK;
+    if (r >= R) return;
+    long k1 = k0 + OZ_RMK < K ? k0 + OZ_RMK : K;
+    if (tri == 1 && k1 > r + 1) k1 = r + 1;
+    double m0 = 0.0, m1 = 0.0, m2 = 0.0, m3 = 0.0;
+    long k = k0;
+    for (; k + 3 < k1; k += 4) {
+        m0 = fmax(m0, fabs(X[r + k * ld]));
+        m1 = fmax(m1, fabs(X[r + (k + 1) * ld]));
+        m2 = fmax(m2, fabs(X[r + (k + 2) * ld]));
+        m3 = fmax(m3, fabs(X[r + (k + 3) * ld]));
+    }
+    for (; k < k1; k++) m0 = fmax(m0, fabs(X[r + k * ld]));
+    const double mx = fmax(fmax(m0, m1), fmax(m2, m3));
+    if (mx > 0.0) atomicMax(rowmax + r, (unsigned long long)__double_as_longlong(mx));     // non-negative doubles order like integers
+}
+
+__global__ void oz_exp_kernel(const unsigned long long* __restrict__ rowmax, long R, long Rp, int* __restrict__ exps)
 {
     const long r = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    double mx = 0.0;
-    for (long k = 0; k < K; k++) mx = fmax(mx, fabs(X[r + k * ld]));
-    int e = 0;
-    if (mx > 0.0 && mx <= DBL_MAX) {
-        frexp(mx, &e);                       // mx = f 2^e, 0.5 <= f < 1  =>  |x| 2^-e < 1
-    }
-    exps[r] = e;
+    if (r >= Rp) return;
+    exps[r] = (r < R) ? oz_exp_of(__longlong_as_double((long long)rowmax[r])) : 0;
 }
 
+// OZ_MN slicing: block = 32 rows x 128 k.  Phase 1: thread (row tx, k = ty + 8 j) loads coalesced along the rows, splits, and
+// stores the bytes into a [slice][row][k] tile (pitch 132: conflict-free both ways); phase 2: 8 threads per row write 128
+// contiguous bytes per slice with 16-byte stores.
 template <int NS>
-__global__ void __launch_bounds__(256) oz_slice_kernel(const double* __restrict__ X, long ld, long R, long K, const int* __restrict__ exps,
-                                                        int8_t* __restrict__ slices, long Rp, long Kp)
+__global__ void __launch_bounds__(256) oz_slice_mn_kernel(const double* __restrict__ X, long ld, long R, long K, int tri,
+                                                           const int* __restrict__ exps, int8_t* __restrict__ slices, long Rp, long Kp)
 {
-    __shared__ int8_t tile[NS][32][33];
-    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;        // 32 x 8 threads
-    const long r0 = (long)blockIdx.x * 32, k0 = (long)blockIdx.y * 32;
+    constexpr int PITCH = 132;
+    __shared__ __align__(16) int8_t tile[NS][32][PITCH];
+    const long r0 = (long)blockIdx.x * 32, k0 = (long)blockIdx.y * 128;
+    if (tri == 1 && k0 >= (r0 / 128 + 1) * 128) return;             // beyond every k-range that reads these rows
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long r = r0 + tx;
-    const int e = (r < R) ? exps[r] : 0;
+    const double sc = oz_scale((r < R) ? exps[r] : 0);
+    double x[16];
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
+    for (int j = 0; j < 16; j++) {
         const long k = k0 + ty + 8 * j;
-        double y = (r < R && k < K) ? scalbn(X[r + k * ld], 6 - e) : 0.0;          // |y| < 64
-        if (!(fabs(y) <= 64.0)) y = 0.0;                                          // NaN / Inf operands: not representable
-#pragma unroll
-        for (int sidx = 0; sidx < NS; sidx++) {
-            const double a = rint(y);
-            tile[sidx][ty + 8 * j][tx] = (int8_t)(int)a;
-            y = (y - a) * 128.0;
-        }
+        x[j] = (r < R && k < K && (tri != 1 || k <= r)) ? X[r + k * ld] : 0.0;
     }
+#pragma unroll
+    for (int j = 0; j < 16; j++) oz_split<NS>(x[j] * sc, [&](int s, int8_t b) { tile[s][tx][ty + 8 * j] = b; });
     __syncthreads();
-    // transposed write: k contiguous
+    const int row = threadIdx.x >> 3, kq = threadIdx.x & 7;
 #pragma unroll
-    for (int sidx = 0; sidx < NS; sidx++) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const long rr = r0 + ty + 8 * j, kk = k0 + tx;
-            if (rr < Rp && kk < Kp) slices[(size_t)sidx * Rp * Kp + (size_t)rr * Kp + kk] = tile[sidx][tx][ty + 8 * j];
-        }
+    for (int s = 0; s < NS; s++) {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&tile[s][row][kq * 16]);
+        const uint4 v = make_uint4(src[0], src[1], src[2], src[3]);
+        *reinterpret_cast<uint4*>(slices + (size_t)s * Rp * Kp + (size_t)(r0 + row) * Kp + k0 + kq * 16) = v;
     }
 }
 
-// K-major input: element (r, k) at X[k + r ld] (a COLUMN-major matrix whose columns are the operand rows: A = X^T).
-// tri != 0: X is lower triangular (entries with k < r are zero and are not read); only k >= 128 floor(r / 128) is written
-// (the GEMM of a triangular product never loads the chunks before that).
-__global__ void __launch_bounds__(256) oz_rowexp_kmajor_kernel(const double* __restrict__ X, long ld, long R, long K, int tri, int* __restrict__ exps)
+// OZ_K input, one warp per operand row (a contiguous column of the matrix)
+__global__ void __launch_bounds__(256) oz_rowexp_k_kernel(const double* __restrict__ X, long ld, long R, long Rp, long K, int tri, int* __restrict__ exps)
 {
     const long r = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (r >= R) return;
-    const double* row = X + r * ld;
+    if (r >= Rp) return;
     double mx = 0.0;
-    for (long k = (tri ? r : 0) + lane; k < K; k += 32) mx = fmax(mx, fabs(row[k]));
+    if (r < R) {
+        const double* row = X + r * ld;
+        for (long k = (tri == 2 ? r : 0) + lane; k < K; k += 32) mx = fmax(mx, fabs(row[k]));
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) {
-        int e = 0;
-        if (mx > 0.0 && mx <= DBL_MAX) frexp(mx, &e);
-        exps[r] = e;
-    }
+    if (lane == 0) exps[r] = oz_exp_of(mx);
 }
 
+// OZ_K slicing: one thread = 16 consecutive k of one row: 128 bytes in, NS x 16 bytes out
 template <int NS>
-__global__ void __launch_bounds__(256) oz_slice_kmajor_kernel(const double* __restrict__ X, long ld, long R, long K, int tri,
-                                                               const int* __restrict__ exps, int8_t* __restrict__ slices, long Rp, long Kp)
+__global__ void __launch_bounds__(256) oz_slice_k_kernel(const double* __restrict__ X, long ld, long R, long K, int tri,
+                                                          const int* __restrict__ exps, int8_t* __restrict__ slices, long Rp, long Kp)
 {
-    // one thread = 16 consecutive k of one row: 128 bytes in, NS x 16 bytes out
     const long kb = (long)blockIdx.x * blockDim.x + threadIdx.x;       // 16-element block index along k
     const long r = blockIdx.y;
     if (kb * 16 >= Kp) return;
     const long k0 = kb * 16;
-    if (tri && k0 + 16 <= (r / OZ_KC_) * OZ_KC_) return;                // never loaded
-    const int e = (r < R) ? exps[r] : 0;
-    int8_t out[NS][16];
+    if (tri == 2 && k0 + 16 <= (r / 128) * 128) return;                 // never loaded
+    const double sc = oz_scale((r < R) ? exps[r] : 0);
+    const double* row = X + r * ld;
+    double x[16];
+    if (r < R && k0 + 16 <= K && (tri != 2 || k0 >= r)) {
 #pragma unroll
-    for (int i = 0; i < 16; i++) {
-        const long k = k0 + i;
-        double y = 0.0;
-        if (r < R && k < K && (!tri || k >= r)) y = scalbn(X[k + r * ld], 6 - e);
-        if (!(fabs(y) <= 64.0)) y = 0.0;
+        for (int i = 0; i < 16; i += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(row + k0 + i);          // ld even, k0 % 16 == 0
+            x[i] = v.x; x[i + 1] = v.y;
+        }
+    } else {
 #pragma unroll
-        for (int sidx = 0; sidx < NS; sidx++) {
-            const double a = rint(y);
-            out[sidx][i] = (int8_t)(int)a;
-            y = (y - a) * 128.0;
+        for (int i = 0; i < 16; i++) {
+            const long k = k0 + i;
+            x[i] = (r < R && k < K && (tri != 2 || k >= r)) ? row[k] : 0.0;
         }
     }
+    union { int8_t b[NS][16]; uint4 v[NS]; } out;
 #pragma unroll
-    for (int sidx = 0; sidx < NS; sidx++)
-        *reinterpret_cast<uint4*>(slices + (size_t)sidx * Rp * Kp + (size_t)r * Kp + k0) = *reinterpret_cast<const uint4*>(out[sidx]);
+    for (int i = 0; i < 16; i++) oz_split<NS>(x[i] * sc, [&](int s, int8_t b) { out.b[s][i] = b; });
+#pragma unroll
+    for (int s = 0; s < NS; s++) *reinterpret_cast<uint4*>(slices + (size_t)s * Rp * Kp + (size_t)r * Kp + k0) = out.v[s];
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// (3) the GEMM.  One CTA (four warps) per 128 x 64 output tile, persistent over tiles.  Thread 0 is the whole control
-// flow of the main loop: per k-chunk of 128 it issues 2 NS bulk tensor copies (cp.async.bulk.tensor.3d, 128-byte swizzle:
-// one box per slice of A and of B) onto one mbarrier, waits for the bytes, issues the NS (NS + 1) / 2 x 4 UMMAs
-// (tcgen05.mma kind::i8, M = 128, N = 64, K = 32; the pairs with s + t = d accumulate into TMEM columns [64 d, 64 d + 64)) and
-// commits them to a second mbarrier, whose completion frees the shared-memory stage.  After the last chunk all four warps
-// read their 32 TMEM lanes (tcgen05.ld 32x32b.x32), combine the NS integer accumulators in FP64 from the smallest term up,
-// apply 2^(ea + eb - 12) and write C.  Single stage: 24 KB per slice pair and k-chunk, 192 KB at NS = 8.
+// (3) the GEMM  C = alpha A B^T + beta C  on sliced operands.
+// One CTA (four warps) per 128 x 64 output tile, persistent, tiles handed out in list order by an atomic ticket (the k-ranges
+// of triangular products differ per tile; the lists put the longest first).  Warp-specialised main loop on a two-stage ring:
+//   warp 0, one lane: TMA producer -- per k-chunk of 64 it waits for the stage to be free and issues 2 NS bulk tensor copies
+//                     (cp.async.bulk.tensor.3d, 64-byte swizzle: one box per slice of A and of B) onto the stage's full barrier;
+//   warp 1, one lane: MMA issuer -- waits for the bytes and issues tcgen05.mma kind::i8 (M = 128, K = 32).  The slice pairs
+//                     (s, t) with s + t = d accumulate into TMEM columns [64 d, 64 d + 64), so for a fixed s the pairs
+//                     t = 0 .. NS-1-s are ONE product of A_s with the row-stacked slices [B_0; B_1; ...] (contiguous in shared
+//                     memory) into the contiguous columns [64 s, 64 NS): issued as MMAs of N <= 256 -- 10 instead of 28
+//                     per k-step at NS = 7, and 4 KB of A read from shared memory per 256 instead of per 64 columns (a
+//                     128 x 64 x 32 MMA reads 6 KB per 32 clocks of tensor time and is bound by shared-memory bandwidth);
+//                     then tcgen05.commit to the stage's empty barrier (after the last chunk: to the accumulator barrier);
+//   all four warps:   epilogue -- tcgen05.ld of their 32 TMEM lanes, the NS integer accumulators combined in FP64 from the
+//                     smallest term up, 2^(ea + eb - 12), C written.
+// 12 KB per slice and stage: 192 KB of shared memory at NS = 8; all 512 TMEM columns at NS = 8.
 // ---------------------------------------------------------------------------------------------------------
 constexpr int OZ_M = 128, OZ_N = 64, OZ_KC = 64, OZ_STAGES = 2;
 
@@ -325,22 +377,14 @@ __device__ __forceinline__ uint64_t umma_desc_k64(const void* smem_tile)
 struct OzArgs {
     const int* ea; const int* eb;       // row exponents of A (M) and B (N)
     double* C; long ldc;                // column-major output
-    long M, N, K;                       // logical sizes (M, N padded to tiles inside the slices; K padded to 128)
-    int mt, nt, nk;                     // tiles / k-chunks of OZ_KC
-    int tri;                            // 1: C = X^T X with X lower triangular: tiles with 64 tn <= 128 tm + 127 only, k >= 128 tm
-    const int2* tiles; long ntiles;     // (tm, tn) of every tile in processing order (oz_tile_list)
+    long M, N;                          // logical sizes (rows beyond them exist, zero, inside the slices)
+    int nk;                             // k-chunks of OZ_KC in the sliced operands
+    int kmode;                          // OZ_KLO_* / OZ_KHI_* bits: the k-range of a tile
+    const int2* tiles; int ntiles;      // (tm, tn) of every tile in processing order (oz_tile_list)
+    int* ticket;                        // zeroed before the launch
     double alpha, beta;
 };
 
-// One CTA (four warps) per 128 x 64 output tile, persistent over tiles; warp-specialised main loop on a two-stage ring:
-//   warp 0, one lane: TMA producer -- per k-chunk of 64 it waits for the stage to be free and issues 2 NS bulk tensor copies
-//                     (cp.async.bulk.tensor.3d, 64-byte swizzle: one box per slice of A and of B) onto the stage's full barrier;
-//   warp 1, one lane: MMA issuer -- waits for the bytes, issues NS (NS + 1) / 2 x 2 UMMAs (tcgen05.mma kind::i8, M = 128,
-//                     N = 64, K = 32; the pairs with s + t = d accumulate into TMEM columns [64 d, 64 d + 64)) and commits them
-//                     to the stage's empty barrier (and, after the last chunk, to the accumulator barrier);
-//   all four warps:   epilogue -- tcgen05.ld of their 32 TMEM lanes, the NS integer accumulators combined in FP64 from the
-//                     smallest term up, 2^(ea + eb - 12), C written.
-// 12 KB per slice and stage: 192 KB of shared memory at NS = 8; all 512 TMEM columns at NS = 8.
 template <int NS>
 __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a)
 {
@@ -350,6 +394,7 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     __shared__ unsigned long long bar_full[OZ_STAGES], bar_empty[OZ_STAGES], bar_acc;
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_eb[OZ_N];
+    __shared__ int s_tile;
     constexpr uint32_t TCOLS = (NS * OZ_N <= 64) ? 64 : (NS * OZ_N <= 128) ? 128 : (NS * OZ_N <= 256) ? 256 : 512;
     static_assert(NS * OZ_N <= 512, "accumulators of all slice-sum classes must fit the 512 TMEM columns");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -365,19 +410,27 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    constexpr uint32_t idesc = umma_idesc_i8(OZ_M, OZ_N);
     uint32_t it = 0, ph_acc = 0;                         // `it`: chunks handled so far by this thread's role (ring position)
-    for (long tile = blockIdx.x; tile < a.ntiles; tile += gridDim.x) {
+    for (;;) {
+        if (tid == 0) s_tile = atomicAdd(a.ticket, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= a.ntiles) break;
         const int2 tt = a.tiles[tile];
         const int tm = tt.x, tn = tt.y;
-        const int kc0 = a.tri ? tm * (OZ_M / OZ_KC) : 0;
+        int kc0 = 0, kc1 = a.nk;
+        if (a.kmode & OZ_KLO_TM) kc0 = tm * (OZ_M / OZ_KC);
+        if (a.kmode & OZ_KLO_TN) kc0 = max(kc0, tn * (OZ_N / OZ_KC));
+        if (a.kmode & OZ_KHI_TM) kc1 = min(kc1, (tm + 1) * (OZ_M / OZ_KC));
+        if (a.kmode & OZ_KHI_TN) kc1 = min(kc1, (tn + 1) * (OZ_N / OZ_KC));
+        const bool empty = kc0 >= kc1;
         if (tid >= 64) {
             const long n = (long)tn * OZ_N + (tid - 64);
             s_eb[tid - 64] = (n < a.N) ? a.eb[n] : 0;
         }
         if (warp == 0) {
             if (lane == 0) {
-                for (int kc = kc0; kc < a.nk; kc++, it++) {
+                for (int kc = kc0; kc < kc1; kc++, it++) {
                     const uint32_t st = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     mbar_wait(&bar_empty[st], ph ^ 1u);
                     mbar_arrive_expect_tx(&bar_full[st], (uint32_t)STAGE_BYTES);
@@ -393,7 +446,7 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
             __syncwarp();
         } else if (warp == 1) {
             if (lane == 0) {
-                for (int kc = kc0; kc < a.nk; kc++, it++) {
+                for (int kc = kc0; kc < kc1; kc++, it++) {
                     const uint32_t st = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
                     mbar_wait(&bar_full[st], ph);
                     tc_fence_after();
@@ -401,13 +454,16 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
                     const uint8_t* sB = sA + NS * A_BYTES;
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
+                        // A_s x [B_0; ...; B_{NS-1-s}] -> accumulators s .. NS-1; the first write of every accumulator of this tile
+                        // is chunk kc0, k-step 0 of s = 0
 #pragma unroll
-                        for (int t = 0; t < NS - s; t++) {
-                            // first write of accumulator d = s + t in this tile: chunk kc0, k-step 0 of the pair (0, d)
+                        for (int c0 = 0; c0 < (NS - s) * OZ_N; c0 += 256) {
+                            const int nn = ((NS - s) * OZ_N - c0 < 256) ? (NS - s) * OZ_N - c0 : 256;
+                            const uint32_t idesc = umma_idesc_i8(OZ_M, nn);
 #pragma unroll
                             for (int ks = 0; ks < OZ_KC / 32; ks++)
-                                umma_i8(tmem + (s + t) * OZ_N, umma_desc_k64(sA + s * A_BYTES + ks * 32), umma_desc_k64(sB + t * B_BYTES + ks * 32),
-                                        idesc, (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u);
+                                umma_i8(tmem + s * OZ_N + c0, umma_desc_k64(sA + s * A_BYTES + ks * 32),
+                                        umma_desc_k64(sB + (c0 / OZ_N) * B_BYTES + ks * 32), idesc, (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u);
                         }
                     }
                     umma_commit(&bar_empty[st]);             // the stage is free once these UMMAs have read it
@@ -428,13 +484,15 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
             double acc[32];
 #pragma unroll
             for (int i = 0; i < 32; i++) acc[i] = 0.0;
+            if (!empty) {
 #pragma unroll 1
-            for (int d = NS - 1; d >= 0; d--) {           // smallest contributions first
-                uint32_t v[32];
-                tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + d * OZ_N + half * 32, v);
-                const double w = scalbn(1.0, -7 * d);
+                for (int d = NS - 1; d >= 0; d--) {           // smallest contributions first
+                    uint32_t v[32];
+                    tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + d * OZ_N + half * 32, v);
+                    const double w = scalbn(1.0, -7 * d);
 #pragma unroll
-                for (int i = 0; i < 32; i++) acc[i] = fma((double)(int32_t)v[i], w, acc[i]);
+                    for (int i = 0; i < 32; i++) acc[i] = fma((double)(int32_t)v[i], w, acc[i]);
+                }
             }
             if (m < a.M) {
 #pragma unroll
@@ -457,37 +515,60 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     if (warp == 0) tmem_dealloc(tmem, TCOLS);
 }
 
-// Processing order of the output tiles.  Operand bytes per tile and k-chunk are 2 NS x 12 KB against 2 NS (NS + 1) UMMAs, i.e.
-// ~340 INT8 ops per byte -- below the ~730 ops/byte the tensor pipe needs from HBM -- so the tiles that run at the same time
-// must share their operand panels in L2: super-tiles of 8 (tm) x 16 (tn) = 128 tiles (about one wave of 148 CTAs) touch 8 A
-// panels and 16 B panels instead of 64 + 2.  Triangular products: the same blocks over the lower triangle, top block rows
-// (longest k-ranges) first.  The list lives in device memory, one per (mt, nt, tri) and device.
-struct OzTileList { int mt = 0, nt = 0, tri = -1; long n = 0; DBuf buf; };
+// Processing order of the output tiles.  Operand bytes per tile and k-chunk are 2 NS x 12 KB against 2 NS (NS + 1) MMA units,
+// i.e. ~340 INT8 ops per byte -- below the ~730 ops/byte the tensor pipe needs from HBM -- so the tiles that run at the same
+// time must share their operand panels in L2: super-tiles of 8 (tm) x 16 (tn) = 128 tiles (about one wave of 148 CTAs) touch
+// 8 A panels and 16 B panels instead of 64 + 2.  `order` puts the tiles with the longest k-range first (the ticket hands them
+// out in list order): 0 = block rows top down, 1 = bottom up, 2 = block columns left to right, 3 = right to left.
+struct OzTileList { int device = -1, mt = 0, nt = 0, lower = 0, order = 0; int n = 0; DBuf buf; };
 
-int oz_tile_list(Ctx& c, int mt, int nt, int tri, const int2** d_tiles, long* ntiles)
+int oz_tile_list(Ctx& c, int mt, int nt, int lower, int order, const int2** d_tiles, int* ntiles)
 {
-    static OzTileList lists[64][2];
-    if (c.device < 0 || c.device >= 64) { set_error("ozaki: device index out of range"); return ST_BADARG; }
-    OzTileList& L = lists[c.device][tri ? 1 : 0];
-    if (L.mt != mt || L.nt != nt || L.tri != tri || !L.buf.p) {
-        std::vector<int2> v;
-        constexpr int BM = 8, BN = 16;
-        for (int TM = 0; TM * BM < mt; TM++)
-            for (int TN = 0; TN * BN < nt; TN++)
-                for (int j = 0; j < BN; j++)
-                    for (int i = 0; i < BM; i++) {
-                        const int tm = TM * BM + i, tn = TN * BN + j;
-                        if (tm >= mt || tn >= nt) continue;
-                        if (tri && tn > 2 * tm + 1) continue;
-                        v.push_back(make_int2(tm, tn));
-                    }
-        SGP_TRY(L.buf.reserve((v.size() + 1) * sizeof(int2)));
-        SGP_CUDA(cudaMemcpyAsync(L.buf.p, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
-        SGP_CUDA(cudaStreamSynchronize(c.stream));
-        L.mt = mt; L.nt = nt; L.tri = tri; L.n = (long)v.size();
+    constexpr int NLIST = 64;
+    static OzTileList lists[NLIST];
+    static int next = 0;
+    for (int i = 0; i < NLIST; i++) {
+        OzTileList& L = lists[i];
+        if (L.device == c.device && L.mt == mt && L.nt == nt && L.lower == lower && L.order == order && L.buf.p) {
+            *d_tiles = L.buf.as<int2>(); *ntiles = L.n;
+            return ST_OK;
+        }
     }
-    *d_tiles = L.buf.as<int2>();
-    *ntiles = L.n;
+    std::vector<int2> v;
+    constexpr int BM = 8, BN = 16;
+    const int nTM = (mt + BM - 1) / BM, nTN = (nt + BN - 1) / BN;
+    auto block = [&](int TM, int TN) {
+        for (int j = 0; j < BN; j++)
+            for (int i = 0; i < BM; i++) {
+                const int tm = TM * BM + i, tn = TN * BN + j;
+                if (tm >= mt || tn >= nt) continue;
+                if (lower && tn > 2 * tm + 1) continue;
+                v.push_back(make_int2(tm, tn));
+            }
+    };
+    if (order == 0) { for (int TM = 0; TM < nTM; TM++) for (int TN = 0; TN < nTN; TN++) block(TM, TN); }
+    else if (order == 1) { for (int TM = nTM - 1; TM >= 0; TM--) for (int TN = 0; TN < nTN; TN++) block(TM, TN); }
+    else if (order == 2) { for (int TN = 0; TN < nTN; TN++) for (int TM = 0; TM < nTM; TM++) block(TM, TN); }
+    else { for (int TN = nTN - 1; TN >= 0; TN--) for (int TM = 0; TM < nTM; TM++) block(TM, TN); }
+    OzTileList& L = lists[next];
+    next = (next + 1) % NLIST;
+    // a list that is replaced may still be read by a kernel in flight on this or another device's stream
+    if (L.buf.p) SGP_CUDA(cudaDeviceSynchronize());
+    SGP_TRY(L.buf.reserve((v.size() + 1) * sizeof(int2)));
+    SGP_CUDA(cudaMemcpyAsync(L.buf.p, v.data(), v.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
+    SGP_CUDA(cudaStreamSynchronize(c.stream));
+    L.device = c.device; L.mt = mt; L.nt = nt; L.lower = lower; L.order = order; L.n = (int)v.size();
+    *d_tiles = L.buf.as<int2>(); *ntiles = L.n;
+    return ST_OK;
+}
+
+int oz_ticket(Ctx& c, int** ticket)
+{
+    static DBuf tickets[64];
+    if (c.device < 0 || c.device >= 64) { set_error("ozaki: device index out of range"); return ST_BADARG; }
+    SGP_TRY(tickets[c.device].reserve(256));
+    *ticket = tickets[c.device].as<int>();
+    SGP_CUDA(cudaMemsetAsync(*ticket, 0, sizeof(int), c.stream));
     return ST_OK;
 }
 
@@ -524,53 +605,107 @@ int oz_launch(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, const OzAr
         SGP_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = true;
     }
-    const long ntiles = a.ntiles;
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
-    oz_gemm_kernel<NS><<<(unsigned)(ntiles < sms ? ntiles : sms), 128, smem, c.stream>>>(tmA, tmB, a);
+    oz_gemm_kernel<NS><<<(unsigned)(a.ntiles < sms ? a.ntiles : sms), 128, smem, c.stream>>>(tmA, tmB, a);
     SGP_CUDA(cudaGetLastError());
     count_launch();
     return ST_OK;
 }
 
 template <int NS>
-int oz_slice(Ctx& c, const double* X, long ld, long R, long K, int* exps, int8_t* slices, long Rp, long Kp)
+int oz_slice_t(Ctx& c, const double* X, long ld, long R, long K, int layout, int tri, const OzSliced& o)
 {
-    oz_rowexp_kernel<<<(unsigned)((R + 127) / 128), 128, 0, c.stream>>>(X, ld, R, K, exps);
-    oz_slice_kernel<NS><<<dim3((unsigned)(Rp / 32), (unsigned)(Kp / 32)), 256, 0, c.stream>>>(X, ld, R, K, exps, slices, Rp, Kp);
+    if (layout == OZ_MN) {
+        SGP_CUDA(cudaMemsetAsync(o.rowmax, 0, (size_t)o.Rp * sizeof(unsigned long long), c.stream));
+        oz_rowmax_mn_kernel<<<dim3((unsigned)((R + 127) / 128), (unsigned)((K + OZ_RMK - 1) / OZ_RMK)), 128, 0, c.stream>>>(X, ld, R, K, tri, o.rowmax);
+        oz_exp_kernel<<<(unsigned)((o.Rp + 255) / 256), 256, 0, c.stream>>>(o.rowmax, R, o.Rp, o.ex);
+        oz_slice_mn_kernel<NS><<<dim3((unsigned)(o.Rp / 32), (unsigned)(o.Kp / 128)), 256, 0, c.stream>>>(X, ld, R, K, tri, o.ex, o.sl, o.Rp, o.Kp);
+        count_launch(3);
+    } else {
+        oz_rowexp_k_kernel<<<(unsigned)((o.Rp + 7) / 8), 256, 0, c.stream>>>(X, ld, R, o.Rp, K, tri, o.ex);
+        oz_slice_k_kernel<NS><<<dim3((unsigned)((o.Kp / 16 + 255) / 256), (unsigned)o.Rp), 256, 0, c.stream>>>(X, ld, R, K, tri, o.ex, o.sl, o.Rp, o.Kp);
+        count_launch(2);
+    }
     SGP_CUDA(cudaGetLastError());
-    count_launch(2);
     return ST_OK;
 }
 
 }  // namespace
 
-size_t ozaki_workspace_bytes(long M, long N, long K, int ns)
+// ---------------------------------------------------------------------------------------------------------
+// host interface
+// ---------------------------------------------------------------------------------------------------------
+size_t ozaki_sliced_bytes(long R, long K, int ns)
 {
-    const size_t Mp = (size_t)round_up(M, OZ_M), Np = (size_t)round_up(N, OZ_N), Kp = (size_t)round_up(K, OZ_KC_);
-    return (size_t)ns * (Mp + Np) * Kp + (Mp + Np) * sizeof(int) + 1024;
+    const size_t Rp = (size_t)round_up(R, OZ_M), Kp = (size_t)round_up(K, OZ_KC_);
+    return (size_t)ns * Rp * Kp + Rp * (sizeof(int) + sizeof(unsigned long long)) + 256;
 }
 
-struct OzWork {
-    int8_t *sA, *sB;
-    int *ea, *eb;
-    long Mp, Np, Kp;
-};
-
-static OzWork oz_carve(void* work, long M, long N, long K, int ns)
+OzSliced ozaki_carve(void* buf, long R, long K, int ns)
 {
-    OzWork w;
-    w.Mp = round_up(M, OZ_M); w.Np = round_up(N, OZ_N); w.Kp = round_up(K, OZ_KC_);
-    w.sA = reinterpret_cast<int8_t*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
-    w.sB = w.sA + (size_t)ns * w.Mp * w.Kp;
-    w.ea = reinterpret_cast<int*>(w.sB + (size_t)ns * w.Np * w.Kp);
-    w.eb = w.ea + w.Mp;
-    return w;
+    OzSliced o;
+    o.Rp = round_up(R, OZ_M); o.Kp = round_up(K, OZ_KC_);
+    o.sl = reinterpret_cast<int8_t*>(((uintptr_t)buf + 255) & ~(uintptr_t)255);
+    o.rowmax = reinterpret_cast<unsigned long long*>(o.sl + (size_t)ns * o.Rp * o.Kp);
+    o.ex = reinterpret_cast<int*>(o.rowmax + o.Rp);
+    return o;
+}
+
+static int oz_check_ns(int ns, long K)
+{
+    if (ns < 4 || ns > 8) { set_error("ozaki: 4..8 slices per operand, got %d", ns); return ST_BADARG; }
+    if ((long)ns * K * 4096 >= 2147483647L) { set_error("ozaki: K = %ld too deep for exact INT32 accumulation with %d slices", K, ns); return ST_BADARG; }
+    return ST_OK;
+}
+
+int ozaki_slice(Ctx& c, int ns, const double* X, long ld, long R, long K, int layout, int tri, const OzSliced& out)
+{
+    SGP_TRY(oz_check_ns(ns, K));
+    if (R <= 0 || K <= 0 || (layout != OZ_MN && layout != OZ_K) || (layout == OZ_MN && tri == 2) || (layout == OZ_K && tri == 1) || (ld & 1)) {
+        set_error("ozaki_slice: bad arguments"); return ST_BADARG;
+    }
+    switch (ns) {
+    case 4: return oz_slice_t<4>(c, X, ld, R, K, layout, tri, out);
+    case 5: return oz_slice_t<5>(c, X, ld, R, K, layout, tri, out);
+    case 6: return oz_slice_t<6>(c, X, ld, R, K, layout, tri, out);
+    case 7: return oz_slice_t<7>(c, X, ld, R, K, layout, tri, out);
+    default: return oz_slice_t<8>(c, X, ld, R, K, layout, tri, out);
+    }
+}
+
+int ozaki_gemm_sliced(Ctx& c, int ns, const OzSliced& A, const OzSliced& B, long M, long N, double alpha, double beta, double* C, long ldc,
+                      int kmode, int lower)
+{
+    SGP_TRY(oz_check_ns(ns, A.Kp));
+    if (M <= 0 || N <= 0 || A.Kp != B.Kp || M > A.Rp || N > B.Rp) { set_error("ozaki_gemm_sliced: operand shapes do not match"); return ST_BADARG; }
+    CUtensorMap tmA, tmB;
+    SGP_TRY(make_slice_tmap(&tmA, A.sl, A.Rp, A.Kp, ns, OZ_M));
+    SGP_TRY(make_slice_tmap(&tmB, B.sl, B.Rp, B.Kp, ns, OZ_N));
+    OzArgs a;
+    a.ea = A.ex; a.eb = B.ex; a.C = C; a.ldc = ldc; a.M = M; a.N = N;
+    a.nk = (int)(A.Kp / OZ_KC); a.kmode = kmode; a.alpha = alpha; a.beta = beta;
+    const int mt = (int)((M + OZ_M - 1) / OZ_M), nt = (int)((N + OZ_N - 1) / OZ_N);
+    const int order = (kmode & OZ_KHI_TM) ? 1 : (kmode & OZ_KLO_TN) ? 2 : (kmode & OZ_KHI_TN) ? 3 : 0;
+    SGP_TRY(oz_tile_list(c, mt, nt, lower, order, &a.tiles, &a.ntiles));
+    SGP_TRY(oz_ticket(c, &a.ticket));
+    switch (ns) {
+    case 4: return oz_launch<4>(c, tmA, tmB, a);
+    case 5: return oz_launch<5>(c, tmA, tmB, a);
+    case 6: return oz_launch<6>(c, tmA, tmB, a);
+    case 7: return oz_launch<7>(c, tmA, tmB, a);
+    default: return oz_launch<8>(c, tmA, tmB, a);
+    }
+}
+
+size_t ozaki_workspace_bytes(long M, long N, long K, int ns)
+{
+    return ozaki_sliced_bytes(M, K, ns) + ozaki_sliced_bytes(N, K, ns) + 512;
 }
 
 static int oz_check(int ns, long M, long N, long K, size_t work_bytes)
 {
-    if (ns < 4 || ns > 8 || M <= 0 || N <= 0 || K <= 0) { set_error("ozaki_gemm: bad arguments (ns must be 4..8)"); return ST_BADARG; }
-    if ((long)ns * K * 4096 >= 2147483647L) { set_error("ozaki_gemm: K = %ld too deep for exact INT32 accumulation with %d slices", K, ns); return ST_BADARG; }
+    if (M <= 0 || N <= 0 || K <= 0) { set_error("ozaki_gemm: bad arguments"); return ST_BADARG; }
+    SGP_TRY(oz_check_ns(ns, K));
     if (work_bytes < ozaki_workspace_bytes(M, N, K, ns)) { set_error("ozaki_gemm: workspace too small"); return ST_BADARG; }
     return ST_OK;
 }
@@ -579,77 +714,34 @@ static int oz_check(int ns, long M, long N, long K, size_t work_bytes)
 int ozaki_gemm_presliced(Ctx& c, int ns, long M, long N, long K, double alpha, double beta, double* C, long ldc, void* work, size_t work_bytes)
 {
     SGP_TRY(oz_check(ns, M, N, K, work_bytes));
-    const OzWork w = oz_carve(work, M, N, K, ns);
-    CUtensorMap tmA, tmB;
-    SGP_TRY(make_slice_tmap(&tmA, w.sA, w.Mp, w.Kp, ns, OZ_M));
-    SGP_TRY(make_slice_tmap(&tmB, w.sB, w.Np, w.Kp, ns, OZ_N));
-    OzArgs a;
-    a.ea = w.ea; a.eb = w.eb; a.C = C; a.ldc = ldc; a.M = M; a.N = N; a.K = K;
-    a.mt = (int)(w.Mp / OZ_M); a.nt = (int)(w.Np / OZ_N); a.nk = (int)(w.Kp / OZ_KC); a.alpha = alpha; a.beta = beta; a.tri = 0;
-    SGP_TRY(oz_tile_list(c, a.mt, a.nt, 0, &a.tiles, &a.ntiles));
-    switch (ns) {
-    case 4: return oz_launch<4>(c, tmA, tmB, a);
-    case 5: return oz_launch<5>(c, tmA, tmB, a);
-    case 6: return oz_launch<6>(c, tmA, tmB, a);
-    case 7: return oz_launch<7>(c, tmA, tmB, a);
-    default: return oz_launch<8>(c, tmA, tmB, a);
-    }
+    const OzSliced A = ozaki_carve(work, M, K, ns);
+    const OzSliced B = ozaki_carve((char*)work + ozaki_sliced_bytes(M, K, ns), N, K, ns);
+    return ozaki_gemm_sliced(c, ns, A, B, M, N, alpha, beta, C, ldc, 0, 0);
 }
 
 // split A (M x K) and B (N x K) (element (r, k) at ptr[r + k ld]) into ns INT8 slices + row exponents in `work`
 int ozaki_slice_operands(Ctx& c, int ns, long M, long N, long K, const double* A, long lda, const double* B, long ldb, void* work, size_t work_bytes)
 {
     SGP_TRY(oz_check(ns, M, N, K, work_bytes));
-    const OzWork w = oz_carve(work, M, N, K, ns);
-    switch (ns) {
-    case 4: SGP_TRY(oz_slice<4>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<4>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
-    case 5: SGP_TRY(oz_slice<5>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<5>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
-    case 6: SGP_TRY(oz_slice<6>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<6>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
-    case 7: SGP_TRY(oz_slice<7>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<7>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
-    default: SGP_TRY(oz_slice<8>(c, A, lda, M, K, w.ea, w.sA, w.Mp, w.Kp)); return oz_slice<8>(c, B, ldb, N, K, w.eb, w.sB, w.Np, w.Kp);
-    }
+    const OzSliced sA = ozaki_carve(work, M, K, ns);
+    const OzSliced sB = ozaki_carve((char*)work + ozaki_sliced_bytes(M, K, ns), N, K, ns);
+    SGP_TRY(ozaki_slice(c, ns, A, lda, M, K, OZ_MN, 0, sA));
+    return ozaki_slice(c, ns, B, ldb, N, K, OZ_MN, 0, sB);
 }
 
-size_t ozaki_lauum_workspace_bytes(long n_pad, int ns)
-{
-    return (size_t)ns * (size_t)n_pad * (size_t)n_pad + (size_t)n_pad * sizeof(int) + 1024;
-}
+size_t ozaki_lauum_workspace_bytes(long n_pad, int ns) { return ozaki_sliced_bytes(n_pad, n_pad, ns) + 256; }
 
 // W (lower tiles, column-major, ldw) = X^T X for the lower-triangular X (n_pad x n_pad, column-major, ldx; n_pad a multiple of
 // 128) -- the lauum stage of the inverse -- on the INT8 tensor pipe: ONE operand is sliced (A = B = X^T, whose rows are the
 // contiguous columns of X), the tile set is the lower triangle and every tile skips the k-chunks above its rows.
 int ozaki_lauum(Ctx& c, int ns, const double* X, long n_pad, long ldx, double* W, long ldw, void* work, size_t work_bytes)
 {
-    if (ns < 4 || ns > 8 || n_pad <= 0 || n_pad % OZ_M) { set_error("ozaki_lauum: bad arguments"); return ST_BADARG; }
-    if ((long)ns * n_pad * 4096 >= 2147483647L) { set_error("ozaki_lauum: order %ld too large for exact INT32 accumulation with %d slices", n_pad, ns); return ST_BADARG; }
+    if (n_pad <= 0 || n_pad % OZ_M) { set_error("ozaki_lauum: bad arguments"); return ST_BADARG; }
+    SGP_TRY(oz_check_ns(ns, n_pad));
     if (work_bytes < ozaki_lauum_workspace_bytes(n_pad, ns)) { set_error("ozaki_lauum: workspace too small"); return ST_BADARG; }
-    int8_t* sl = reinterpret_cast<int8_t*>(((uintptr_t)work + 255) & ~(uintptr_t)255);
-    int* ex = reinterpret_cast<int*>(sl + (size_t)ns * n_pad * n_pad);
-    oz_rowexp_kmajor_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex);
-    const dim3 grid((unsigned)((n_pad / 16 + 255) / 256), (unsigned)n_pad);
-    switch (ns) {
-    case 4: oz_slice_kmajor_kernel<4><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
-    case 5: oz_slice_kmajor_kernel<5><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
-    case 6: oz_slice_kmajor_kernel<6><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
-    case 7: oz_slice_kmajor_kernel<7><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
-    default: oz_slice_kmajor_kernel<8><<<grid, 256, 0, c.stream>>>(X, ldx, n_pad, n_pad, 1, ex, sl, n_pad, n_pad); break;
-    }
-    SGP_CUDA(cudaGetLastError());
-    count_launch(2);
-    CUtensorMap tmA, tmB;
-    SGP_TRY(make_slice_tmap(&tmA, sl, n_pad, n_pad, ns, OZ_M));
-    SGP_TRY(make_slice_tmap(&tmB, sl, n_pad, n_pad, ns, OZ_N));
-    OzArgs a;
-    a.ea = ex; a.eb = ex; a.C = W; a.ldc = ldw; a.M = n_pad; a.N = n_pad; a.K = n_pad;
-    a.mt = (int)(n_pad / OZ_M); a.nt = (int)(n_pad / OZ_N); a.nk = (int)(n_pad / OZ_KC); a.alpha = 1.0; a.beta = 0.0; a.tri = 1;
-    SGP_TRY(oz_tile_list(c, a.mt, a.nt, 1, &a.tiles, &a.ntiles));
-    switch (ns) {
-    case 4: return oz_launch<4>(c, tmA, tmB, a);
-    case 5: return oz_launch<5>(c, tmA, tmB, a);
-    case 6: return oz_launch<6>(c, tmA, tmB, a);
-    case 7: return oz_launch<7>(c, tmA, tmB, a);
-    default: return oz_launch<8>(c, tmA, tmB, a);
-    }
+    const OzSliced S = ozaki_carve(work, n_pad, n_pad, ns);
+    SGP_TRY(ozaki_slice(c, ns, X, ldx, n_pad, n_pad, OZ_K, 2, S));
+    return ozaki_gemm_sliced(c, ns, S, S, n_pad, n_pad, 1.0, 0.0, W, ldw, OZ_KLO_TM, 1);
 }
 
 // C (M x N, column-major, ldc) = alpha A B^T + beta C with A (M x K) and B (N x K) given as element (r, k) at ptr[r + k ld];

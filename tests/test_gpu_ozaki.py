@@ -126,3 +126,149 @@ def test_full_size_gradient_with_lauum_on_the_int8_pipe(api, ozaki_ctx):
     v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
     assert abs(v - g["nll"]) <= 1e-9 * abs(g["nll"])
     assert np.allclose(gr, g["grad"], rtol=1e-9, atol=1e-9 * np.abs(g["grad"]).max()), (gr, g["grad"])
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the sliced products the INT8 factor-and-inverse recursion is made of (csrc/ozaki_chol.cu), one by one against NumPy
+# ---------------------------------------------------------------------------------------------------------------------
+def _lower_with_garbage(rng, n, scale_rows=False):
+    """(valid lower-triangular matrix, the same with unrelated numbers above the diagonal): the Cholesky works in the lower
+    triangle of a matrix whose upper triangle was never initialised."""
+    X = np.tril(rng.standard_normal((n, n)))
+    if scale_rows:
+        X *= 10.0 ** rng.integers(-6, 6, size=(n, 1))
+    G = X + np.triu(1e30 * rng.standard_normal((n, n)), 1)
+    return X, np.asfortranarray(G)
+
+
+def _bound(A, B, ns):
+    """A-priori error bound of the sliced product, elementwise: the slice pairs with s + t >= ns are dropped, each at most
+    64 x 64 x 2^(-7 (s + t)) x 2^(ea + eb - 12) per k with 2^ea <= 2 max_k |a|, plus the final FP64 roundings of the ns-term
+    sum: it is relative to the ROW MAXIMA of the operands (the Ozaki scheme scales rows), not to sum |a||b|."""
+    K = A.shape[1]
+    dropped = sum((2 * ns - 1 - d) * 2.0 ** (-7 * d) for d in range(ns, 2 * ns - 1))
+    return (4.0 * dropped * K) * np.outer(np.abs(A).max(axis=1), np.abs(B).max(axis=1)) + 5e-15 * (np.abs(A) @ np.abs(B).T)
+
+
+def _check(C, A, B, sign=1.0, mask=None):
+    """C against sign * A B^T (A, B = the valid parts of the operands) within _bound; returns the worst error / bound."""
+    ns = _check.ns
+    r = np.abs(C - sign * (A @ B.T)) / np.maximum(_bound(A, B, ns), 1e-300)
+    if mask is not None:
+        r = r[mask]
+    assert r.max() < 1.0, r.max()
+    return float(r.max())
+
+
+@pytest.mark.parametrize("ns", [7, 8])
+@pytest.mark.parametrize("h1,h2", [(128, 128), (384, 256), (256, 640)])
+def test_sliced_products_of_the_recursion(api, ns, h1, h2):
+    """Steps 2, 3, 4 and 6 of ozaki_chol.cu's node and the lauum product, with the k-ranges, storage orders and triangular
+    validity flags the recursion passes, on operands whose unused triangle holds 1e30 and whose rows differ by 12 orders of
+    magnitude: each against the FP64 product of the valid parts within the a-priori bound of the scheme."""
+    rng = np.random.default_rng(100 * ns + h1 + h2)
+    _check.ns = ns
+    A21 = np.asfortranarray(rng.standard_normal((h2, h1)))
+    X11, X11g = _lower_with_garbage(rng, h1, scale_rows=True)
+    X22, X22g = _lower_with_garbage(rng, h2, scale_rows=True)
+    # 2. L21 = A21 X11^T : B = X11 (rows r, k <= r valid), k < 64 (tn + 1)
+    C = api.ozaki_gemm_ex(A21, X11g, h2, h1, h1, la=0, ta=0, lb=0, tb=1, kmode=8, slices=ns)
+    w = [_check(C, A21, X11)]
+    # 3. A22 - L21 L21^T on the lower tiles; tiles entirely above the diagonal keep their contents
+    S0 = np.asfortranarray(rng.standard_normal((h2, h2)))
+    C = api.ozaki_gemm_ex(A21, A21, h2, h2, h1, C=S0, alpha=-1.0, beta=1.0, lower=1, slices=ns)
+    low = np.tril(np.ones((h2, h2), dtype=bool))
+    w.append(_check(C - S0, A21, A21, sign=-1.0, mask=low))
+    tm, tn = np.arange(h2)[:, None] // 128, np.arange(h2)[None, :] // 64
+    untouched = tn > 2 * tm + 1
+    assert np.array_equal(C[untouched], S0[untouched])
+    # 4. L21 X11 : B = X11^T stored as X11 (element (n, k) at X11[k, n], k >= n valid), k >= 64 tn
+    C = api.ozaki_gemm_ex(A21, X11g, h2, h1, h1, la=0, ta=0, lb=1, tb=2, kmode=2, slices=ns)
+    w.append(_check(C, A21, X11.T))
+    # 6. -X22 T2 : A = X22 (k <= r valid), k < 128 (tm + 1); B = T2^T stored as T2 (h2 x h1)
+    T2 = np.asfortranarray(rng.standard_normal((h2, h1)))
+    C = api.ozaki_gemm_ex(X22g, T2, h2, h1, h2, la=0, ta=1, lb=1, tb=0, alpha=-1.0, kmode=4, slices=ns)
+    w.append(_check(C, X22, T2.T, sign=-1.0))
+    # lauum: X^T X, A = B = X^T stored as X (k >= r valid), k >= 128 tm, lower tiles
+    C = api.ozaki_gemm_ex(X22g, X22g, h2, h2, h2, la=1, ta=2, lb=1, tb=2, kmode=1, lower=1, slices=ns)
+    w.append(_check(C, X22.T, X22.T, mask=low))
+    print(f"\nns={ns} h1={h1} h2={h2}: worst error / bound per product {[f'{x:.2e}' for x in w]}")
+
+
+@pytest.fixture()
+def ozaki_all():
+    """All three n^3/3 stages on the INT8 pipe for one test, and back to the DMMA default."""
+    from sympgpr_b200 import _lib
+    ctx = _lib.context()
+    yield ctx
+    ctx.set_ozaki_ex(0, 1, 0)
+
+
+@pytest.mark.parametrize("ns,leaf", [(7, 128), (8, 256), (7, 512)])
+@pytest.mark.parametrize("n", [700, 1536])
+def test_spd_inverse_and_logdet_on_the_int8_route(api, ozaki_all, n, ns, leaf):
+    """sgp_spd_factor with factor + triangular inverse + lauum all on the INT8 pipe (leaves of `leaf` rows on DMMA): inverse
+    and log-determinant of a random SPD matrix (condition ~1e6) against SciPy."""
+    import scipy.linalg
+    rng = np.random.default_rng(n + ns + leaf)
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    A = (Q * np.logspace(0, -6, n)) @ Q.T
+    A = 0.5 * (A + A.T)
+    _, Ai0, ld0 = api.spd_factor(A, want_factor=False, want_inverse=True)
+    ozaki_all.set_ozaki_ex(ns, 3, leaf)
+    _, Ai, ld = api.spd_factor(A, want_factor=False, want_inverse=True)
+    ref = scipy.linalg.inv(A)
+    ldr = 0.5 * np.linalg.slogdet(A)[1]
+    assert abs(ld - ldr) < 1e-10 * max(1.0, abs(ldr)) and abs(ld0 - ldr) < 1e-10 * max(1.0, abs(ldr))
+    e = np.abs(Ai - ref).max() / np.abs(ref).max()
+    e0 = np.abs(Ai0 - ref).max() / np.abs(ref).max()
+    print(f"\nn={n} ns={ns} leaf={leaf}: max|Ainv - ref| / max|ref| = {e:.2e} (DMMA route {e0:.2e})")
+    assert e < max(20 * e0, 1e-9), (e, e0)
+    # the residual A Ainv - I does not depend on the comparison inverse
+    r = np.abs(A @ Ai - np.eye(n)).max()
+    r0 = np.abs(A @ Ai0 - np.eye(n)).max()
+    assert r < max(20 * r0, 1e-9), (r, r0)
+
+
+@pytest.mark.parametrize("ns,leaf", [(7, 256), (8, 512)])
+@pytest.mark.parametrize("N", [600, 1024])
+def test_nll_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all, N, ns, leaf):
+    """NLL + gradient with potrf, trtri and lauum replaced by the INT8 recursion + INT8 lauum, judged on the SAME oracle
+    values and tolerance (1e-9) as the DMMA path."""
+    from oracle import oracle as O
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    vr, grr = O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    ozaki_all.set_ozaki_ex(ns, 3, leaf)
+    v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    assert np.isclose(v, vr, rtol=1e-9), (v, vr)
+    assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr)
+
+
+def test_int8_route_reports_a_matrix_that_is_not_positive_definite(api, ozaki_all):
+    """The leaf factorisations carry the info word: a negative pivot in the SECOND half of the recursion (after sliced updates)
+    still raises LinAlgError, as the reference's bare `except` around scipy.linalg.cholesky expects."""
+    n = 1024
+    A = np.eye(n) * 2.0
+    A[900, 900] = -1.0
+    ozaki_all.set_ozaki_ex(7, 3, 256)
+    with pytest.raises(np.linalg.LinAlgError):
+        api.spd_factor(A, want_factor=False, want_inverse=True)
+
+
+def test_full_size_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all):
+    """BASELINE's headline size (N = 16 384, n = 32 768): all three stages on the INT8 pipe (7 slices, leaves of 4096) against
+    the CPU golden (tests/golden/fullsize_nll_N16384.json), 1e-9 as for the DMMA path."""
+    import json
+    import os
+    from oracle import oracle as O
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "fullsize_nll_N16384.json")))
+    N = g["N"]
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    ozaki_all.set_ozaki_ex(7, 3, 4096)
+    v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    print(f"\nfull size, INT8 route: nll rel err {abs(v - g['nll']) / abs(g['nll']):.2e}, grad rel err "
+          f"{np.max(np.abs(np.asarray(gr) - np.asarray(g['grad'])) / np.abs(g['grad'])):.2e}")
+    assert abs(v - g["nll"]) <= 1e-9 * abs(g["nll"])
+    assert np.allclose(gr, g["grad"], rtol=1e-9, atol=1e-9 * np.abs(g["grad"]).max()), (gr, g["grad"])

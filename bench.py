@@ -434,12 +434,14 @@ def leg_headline(B):
                 h2d=int(x_h.numel() * 8 + z_h.numel() * 8), d2h=16 * 8, t_fill=t_fill, fill_gbs=8.0 * n * n / t_fill / 1e9)
 
 
-def leg_ozaki(B, head_ms, head_res, dgemm):
+def leg_ozaki(B, head_ms, head_res, dgemm, bf16_peak):
     """OPT-IN route past the DMMA ceiling (not the headline: north_star asks for DMMA in the Cholesky): FP64 products from the
-    INT8 tensor pipe (tcgen05.mma kind::i8, TMEM accumulators, Ozaki slicing; csrc/ozaki.cu).  (a) the raw GEMM at 8192^3
-    against the DMMA GEMM, (b) the headline evaluation with the lauum stage (W = X^T X) on the INT8 pipe, same inputs."""
+    INT8 tensor pipe (tcgen05.mma kind::i8, TMEM accumulators, Ozaki slicing; csrc/ozaki.cu, csrc/ozaki_chol.cu).  (a) the raw
+    GEMM at 8192^3 against the DMMA GEMM, (b) the headline evaluation with ALL THREE n^3/3 stages on the INT8 pipe (factor +
+    triangular inverse as one recursion of sliced products, lauum as one sliced product; 7 slices), device resident and end to
+    end from host buffers, with the SM clock sampled during the run, (c) the lauum-only variant of round-2 state "e"."""
     a, torch, W = B.a, B.torch, B.W
-    out = {"note": "opt-in (sgp_set_ozaki); headline value/roofline above are the DMMA path north_star names"}
+    out = {"note": "opt-in (sgp_set_ozaki_ex); headline value/roofline above are the DMMA path north_star names"}
     g = {}
     for ns in (7, 8):
         ms = (ctypes.c_double * 2)()
@@ -451,6 +453,14 @@ def leg_ozaki(B, head_ms, head_res, dgemm):
     B._lib.check(B.L.sgp_bench_gemm(B.ctx.handle, 0, 0, 0, 64, 64, 8192, 3, ctypes.byref(msd)), "sgp_bench_gemm")
     g["dmma_gemm_f64_ws"] = {"ms": msd.value, "TFLOP/s": 2 * 8192.0**3 / msd.value / 1e9}
     g["cublas_dgemm_TFLOP/s"] = dgemm
+    # INT8 has no entry in MEASURED_PEAKS.json; the dense INT8 rate of the tensor core is twice its bf16 rate (nominal 4.5 POP/s
+    # against 2.25 PFLOP/s), so 2 x the MEASURED bf16 burst figure is the denominator
+    if bf16_peak:
+        tops = g["7_slices"]["int8_TOP/s_gemm_only"]
+        g["roofline"] = {"kernel": "oz_gemm_kernel<7>", "bound": "tensor", "achieved": tops, "peak": 2.0 * bf16_peak, "unit": "INT8 TOP/s",
+                         "frac": tops / (2.0 * bf16_peak),
+                         "note": "28 slice-pair products of 128 x 64 x K per output tile; peak = 2 x bf16_tflops of MEASURED_PEAKS.json "
+                                 "(no INT8 entry there; burst figure, the kernel is timed alone)"}
     out["gemm_8192"] = g
     B.free()
     N = a.n_train
@@ -461,6 +471,48 @@ def leg_ozaki(B, head_ms, head_res, dgemm):
     x_d = torch.from_numpy(d["xtrain"].copy()).to(B.dev)
     z_d = torch.from_numpy(d["ztrain"].copy()).to(B.dev)
     step, res_d = B.nll_dev_fn(hyp, x_d, z_d, n)
+
+    def rel(res):
+        return [abs(float(res[1 + k]) - float(head_res[1 + k])) / abs(float(head_res[1 + k])) for k in range(2)]
+
+    # (b) all stages
+    B.ctx.set_ozaki_ex(7, 3, 4096)
+    try:
+        step(); step(); step()
+        reps = max(3, a.steps)
+        t0 = time.time()
+        ms = B.timed(step, reps)
+        t1 = time.time()
+        st = B.stage_times()
+        res = res_d.cpu().numpy()
+        # end to end through the public API from pinned host buffers, as the headline's e2e
+        x_h = torch.from_numpy(d["xtrain"].copy()).pin_memory()
+        z_h = torch.from_numpy(d["ztrain"].copy()).pin_memory()
+        xn, zn = x_h.numpy(), z_h.numpy()
+        B.api.nll_grad(hyp, xn, zn, n)
+        te = time.perf_counter()
+        for _ in range(3):
+            ve, ge = B.api.nll_grad(hyp, xn, zn, n)
+        te = (time.perf_counter() - te) / 3
+    finally:
+        B.ctx.set_ozaki_ex(0, 1, 0)
+        B.free()
+    t3 = st["potrf"] + st["trtri"] + st["lauum"]
+    out["nll_grad_all_stages_int8"] = {
+        "slices": 7, "leaf_rows_on_dmma": 4096, "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "speedup_vs_dmma_path": head_ms / ms,
+        "e2e": {"value": 1.0 / te, "unit": "evals/s", "ms_per_eval": 1e3 * te, "h2d_bytes_per_step": int(x_h.numel() * 8 + z_h.numel() * 8),
+                "d2h_bytes_per_step": 16 * 8},
+        "stages_ms": {k: round(v, 3) for k, v in st.items()},
+        "stage_note": "potrf + trtri run as ONE recursion (ozaki_factinv) timed under 'trtri', with w = X z and alpha = X^T w",
+        "fp64_equiv_TFLOP/s": float(n)**3 / t3 / 1e9, "frac_of_dgemm": float(n)**3 / t3 / 1e9 / dgemm,
+        "lauum_fp64_equiv_TFLOP/s": float(n)**3 / 3.0 / st["lauum"] / 1e9,
+        "clocks": B.sampler.summary(t0, t1),
+        "nll": float(res[0]), "grad": [float(res[1]), float(res[2])],
+        "nll_rel_diff_vs_dmma_path": abs(float(res[0]) - float(head_res[0])) / abs(float(head_res[0])),
+        "grad_rel_diff_vs_dmma_path": rel(res),
+        "parity": "tests/test_gpu_ozaki.py::test_full_size_gradient_with_all_stages_on_the_int8_pipe: this route against the CPU golden "
+                  "(tests/golden/fullsize_nll_N16384.json) at 1e-9"}
+    # (c) lauum only (8 slices)
     B.ctx.set_ozaki(8)
     try:
         step(); step()
@@ -474,7 +526,7 @@ def leg_ozaki(B, head_ms, head_res, dgemm):
                                   "stages_ms": {k: round(v, 3) for k, v in st.items()},
                                   "lauum_fp64_equiv_TFLOP/s": float(n)**3 / 3.0 / st["lauum"] / 1e9,
                                   "nll": float(res[0]), "grad": [float(res[1]), float(res[2])],
-                                  "grad_rel_diff_vs_dmma_path": [abs(float(res[1 + k]) - float(head_res[1 + k])) / abs(float(head_res[1 + k])) for k in range(2)]}
+                                  "grad_rel_diff_vs_dmma_path": rel(res)}
     return out
 
 
@@ -890,7 +942,7 @@ def main():
     head = leg_headline(B)
     n = head["n"]
     single = world == 1
-    ozaki = leg_ozaki(B, head["ms_per_step"], head["res"], dgemm_tflops) if (single and not a.no_configs) else None
+    ozaki = leg_ozaki(B, head["ms_per_step"], head["res"], dgemm_tflops, read_bf16_peak()) if (single and not a.no_configs) else None
     sweep = leg_sweep(B, dgemm_tflops) if (single and not a.no_sweep) else None
     configs = {}
     if not a.no_configs:
@@ -1008,6 +1060,15 @@ def read_traffic(n):
         except Exception:
             continue
     return None, "no capture committed for this order"
+
+
+def read_bf16_peak():
+    """Measured cuBLAS bf16 burst rate (TFLOP/s) of this pool's B200s, else the fallback B200_PROFILING.md states."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["bf16_tflops"])
+    except Exception:
+        return 1590.0
 
 
 def read_hbm_peak():

@@ -385,23 +385,34 @@ struct OzArgs {
     double alpha, beta;
 };
 
+// 2^e as a double for -1022 <= e <= 1023
+__device__ __forceinline__ double oz_pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+
+constexpr int OZ_THREADS = 192;     // warps 0-3: epilogue (TMEM lanes 32 w ..), warp 4: TMA producer, warp 5: MMA issuer
+
 template <int NS>
-__global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a)
+__global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, OzArgs a)
 {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* sbase = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     constexpr int A_BYTES = OZ_M * OZ_KC, B_BYTES = OZ_N * OZ_KC, STAGE_BYTES = NS * (A_BYTES + B_BYTES);
-    __shared__ unsigned long long bar_full[OZ_STAGES], bar_empty[OZ_STAGES], bar_acc;
+    // ring of operand slices: 2 k-chunks x NS slots for the A slices (8 KB each, handed back one by one as soon as the MMAs of
+    // their s are done, so the refill of a slot has ~2 chunk times to land), 2 buffers for the NS B slices of a chunk
+    __shared__ unsigned long long fullA[OZ_STAGES * NS], emptyA[OZ_STAGES * NS], fullB[OZ_STAGES], emptyB[OZ_STAGES];
+    __shared__ unsigned long long tq_full[2], tq_empty[2], tmem_full, tmem_empty;
+    __shared__ int tileq[2];
     __shared__ uint32_t tmem_base_s;
     __shared__ int s_eb[OZ_N];
-    __shared__ int s_tile;
     constexpr uint32_t TCOLS = (NS * OZ_N <= 64) ? 64 : (NS * OZ_N <= 128) ? 128 : (NS * OZ_N <= 256) ? 256 : 512;
     static_assert(NS * OZ_N <= 512, "accumulators of all slice-sum classes must fit the 512 TMEM columns");
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
-    if (tid == 0) {
-        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-        mbar_init(&bar_acc, 1);
+    if (tid == 32) {
+        for (int i = 0; i < OZ_STAGES * NS; i++) { mbar_init(&fullA[i], 1); mbar_init(&emptyA[i], 1); }
+        for (int i = 0; i < OZ_STAGES; i++) { mbar_init(&fullB[i], 1); mbar_init(&emptyB[i], 1); }
+        for (int i = 0; i < 2; i++) { mbar_init(&tq_full[i], 1); mbar_init(&tq_empty[i], 129); }
+        mbar_init(&tmem_full, 1);
+        mbar_init(&tmem_empty, 128);
         mbar_fence_init();
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
@@ -410,52 +421,74 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
-    uint32_t it = 0, ph_acc = 0;                         // `it`: chunks handled so far by this thread's role (ring position)
-    for (;;) {
-        if (tid == 0) s_tile = atomicAdd(a.ticket, 1);
-        __syncthreads();
-        const int tile = s_tile;
-        if (tile >= a.ntiles) break;
-        const int2 tt = a.tiles[tile];
-        const int tm = tt.x, tn = tt.y;
-        int kc0 = 0, kc1 = a.nk;
+    // k-chunk range of a tile
+    auto krange = [&](int tm, int tn, int& kc0, int& kc1) {
+        kc0 = 0; kc1 = a.nk;
         if (a.kmode & OZ_KLO_TM) kc0 = tm * (OZ_M / OZ_KC);
         if (a.kmode & OZ_KLO_TN) kc0 = max(kc0, tn * (OZ_N / OZ_KC));
         if (a.kmode & OZ_KHI_TM) kc1 = min(kc1, (tm + 1) * (OZ_M / OZ_KC));
         if (a.kmode & OZ_KHI_TN) kc1 = min(kc1, (tn + 1) * (OZ_N / OZ_KC));
-        const bool empty = kc0 >= kc1;
-        if (tid >= 64) {
-            const long n = (long)tn * OZ_N + (tid - 64);
-            s_eb[tid - 64] = (n < a.N) ? a.eb[n] : 0;
-        }
-        if (warp == 0) {
-            if (lane == 0) {
+    };
+    if (warp == 4) {
+        // ---- TMA producer: takes the tickets, announces every tile to the other roles and runs ahead of them by the depth of
+        // the ring (the first chunks of the next tile are in flight while the epilogue of the current one runs)
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t nt = 0;; nt++) {
+                const int tile = atomicAdd(a.ticket, 1);
+                const uint32_t q = nt & 1u;
+                mbar_wait(&tq_empty[q], ((nt >> 1) & 1u) ^ 1u);
+                tileq[q] = tile;
+                mbar_arrive(&tq_full[q]);
+                if (tile >= a.ntiles) break;
+                const int2 tt = a.tiles[tile];
+                const int tm = tt.x, tn = tt.y;
+                int kc0, kc1;
+                krange(tm, tn, kc0, kc1);
                 for (int kc = kc0; kc < kc1; kc++, it++) {
                     const uint32_t st = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
-                    mbar_wait(&bar_empty[st], ph ^ 1u);
-                    mbar_arrive_expect_tx(&bar_full[st], (uint32_t)STAGE_BYTES);
                     uint8_t* sA = sbase + st * STAGE_BYTES;
                     uint8_t* sB = sA + NS * A_BYTES;
+                    mbar_wait(&emptyB[st], ph ^ 1u);
+                    mbar_arrive_expect_tx(&fullB[st], (uint32_t)(NS * B_BYTES));
+#pragma unroll
+                    for (int s = 0; s < NS; s++) tma_load_3d(sB + s * B_BYTES, &tmB, kc * OZ_KC, tn * OZ_N, s, &fullB[st]);
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
-                        tma_load_3d(sA + s * A_BYTES, &tmA, kc * OZ_KC, tm * OZ_M, s, &bar_full[st]);
-                        tma_load_3d(sB + s * B_BYTES, &tmB, kc * OZ_KC, tn * OZ_N, s, &bar_full[st]);
+                        mbar_wait(&emptyA[st * NS + s], ph ^ 1u);
+                        mbar_arrive_expect_tx(&fullA[st * NS + s], (uint32_t)A_BYTES);
+                        tma_load_3d(sA + s * A_BYTES, &tmA, kc * OZ_KC, tm * OZ_M, s, &fullA[st * NS + s]);
                     }
                 }
             }
-            __syncwarp();
-        } else if (warp == 1) {
-            if (lane == 0) {
+        }
+        __syncwarp();
+    } else if (warp == 5) {
+        // ---- MMA issuer
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t nt = 0;; nt++) {
+                const uint32_t q = nt & 1u;
+                mbar_wait(&tq_full[q], (nt >> 1) & 1u);
+                const int tile = tileq[q];
+                mbar_arrive(&tq_empty[q]);
+                if (tile >= a.ntiles) break;
+                const int2 tt = a.tiles[tile];
+                int kc0, kc1;
+                krange(tt.x, tt.y, kc0, kc1);
+                mbar_wait(&tmem_empty, (nt & 1u) ^ 1u);      // the epilogue of the previous tile has read the accumulators
+                tc_fence_after();
                 for (int kc = kc0; kc < kc1; kc++, it++) {
                     const uint32_t st = it % OZ_STAGES, ph = (it / OZ_STAGES) & 1u;
-                    mbar_wait(&bar_full[st], ph);
-                    tc_fence_after();
+                    mbar_wait(&fullB[st], ph);
                     const uint8_t* sA = sbase + st * STAGE_BYTES;
                     const uint8_t* sB = sA + NS * A_BYTES;
 #pragma unroll
                     for (int s = 0; s < NS; s++) {
                         // A_s x [B_0; ...; B_{NS-1-s}] -> accumulators s .. NS-1; the first write of every accumulator of this tile
                         // is chunk kc0, k-step 0 of s = 0
+                        mbar_wait(&fullA[st * NS + s], ph);
+                        tc_fence_after();
 #pragma unroll
                         for (int c0 = 0; c0 < (NS - s) * OZ_N; c0 += 256) {
                             const int nn = ((NS - s) * OZ_N - c0 < 256) ? (NS - s) * OZ_N - c0 : 256;
@@ -465,50 +498,71 @@ __global__ void __launch_bounds__(128, 1) oz_gemm_kernel(const __grid_constant__
                                 umma_i8(tmem + s * OZ_N + c0, umma_desc_k64(sA + s * A_BYTES + ks * 32),
                                         umma_desc_k64(sB + (c0 / OZ_N) * B_BYTES + ks * 32), idesc, (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u);
                         }
+                        umma_commit(&emptyA[st * NS + s]);   // this A slot is free once the MMAs issued so far have read it
                     }
-                    umma_commit(&bar_empty[st]);             // the stage is free once these UMMAs have read it
+                    umma_commit(&emptyB[st]);                // and the chunk's B slices
                 }
-                umma_commit(&bar_acc);                       // all accumulators of this tile final
-            }
-            __syncwarp();
-        }
-        __syncthreads();                                 // s_eb visible; roles done issuing
-        mbar_wait(&bar_acc, ph_acc);
-        ph_acc ^= 1u;
-        tc_fence_after();
-        // epilogue: thread = row m of the tile (TMEM lane 32 warp + lane)
-        const long m = (long)tm * OZ_M + 32 * warp + lane;
-        const int eam = (m < a.M) ? a.ea[m] : 0;
-#pragma unroll 1
-        for (int half = 0; half < OZ_N / 32; half++) {
-            double acc[32];
-#pragma unroll
-            for (int i = 0; i < 32; i++) acc[i] = 0.0;
-            if (!empty) {
-#pragma unroll 1
-                for (int d = NS - 1; d >= 0; d--) {           // smallest contributions first
-                    uint32_t v[32];
-                    tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + d * OZ_N + half * 32, v);
-                    const double w = scalbn(1.0, -7 * d);
-#pragma unroll
-                    for (int i = 0; i < 32; i++) acc[i] = fma((double)(int32_t)v[i], w, acc[i]);
-                }
-            }
-            if (m < a.M) {
-#pragma unroll
-                for (int i = 0; i < 32; i++) {
-                    const long n = (long)tn * OZ_N + half * 32 + i;
-                    if (n < a.N) {
-                        const double val = a.alpha * scalbn(acc[i], eam + s_eb[half * 32 + i] - 12);
-                        double* cp = a.C + m + n * a.ldc;
-                        *cp = (a.beta == 0.0) ? val : fma(a.beta, *cp, val);
-                    }
-                }
+                umma_commit(&tmem_full);                     // all accumulators of this tile final
             }
         }
-        tc_fence_before();
-        __syncthreads();                                 // all TMEM reads done before the next tile's first UMMA overwrites
-        tc_fence_after();
+        __syncwarp();
+    } else {
+        // ---- epilogue warps: thread = row m of the tile (TMEM lane 32 warp + lane)
+        for (uint32_t nt = 0;; nt++) {
+            const uint32_t q = nt & 1u;
+            mbar_wait(&tq_full[q], (nt >> 1) & 1u);
+            const int tile = tileq[q];
+            mbar_arrive(&tq_empty[q]);
+            if (tile >= a.ntiles) break;
+            const int2 tt = a.tiles[tile];
+            const int tm = tt.x, tn = tt.y;
+            int kc0, kc1;
+            krange(tm, tn, kc0, kc1);
+            const bool empty = kc0 >= kc1;
+            if (tid < OZ_N) {
+                const long n = (long)tn * OZ_N + tid;
+                s_eb[tid] = (n < a.N) ? a.eb[n] : 0;
+            }
+            const long m = (long)tm * OZ_M + 32 * warp + lane;
+            const int eam = ((m < a.M) ? a.ea[m] : 0) - 6;
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // s_eb visible to the four epilogue warps
+            mbar_wait(&tmem_full, nt & 1u);
+            tc_fence_after();
+#pragma unroll 1
+            for (int half = 0; half < OZ_N / 32; half++) {
+                double acc[32];
+#pragma unroll
+                for (int i = 0; i < 32; i++) acc[i] = 0.0;
+                if (!empty) {
+#pragma unroll 1
+                    for (int d = NS - 1; d >= 0; d--) {           // smallest contributions first
+                        uint32_t v[32];
+                        tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + d * OZ_N + half * 32, v);
+                        const double w = oz_pow2(-7 * d);
+#pragma unroll
+                        for (int i = 0; i < 32; i++) acc[i] = fma((double)(int32_t)v[i], w, acc[i]);
+                    }
+                }
+                if (half == OZ_N / 32 - 1) {                      // last TMEM read of this tile done: the next tile's MMAs may start
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty);
+                }
+                if (m < a.M) {
+#pragma unroll
+                    for (int i = 0; i < 32; i++) {
+                        const long n = (long)tn * OZ_N + half * 32 + i;
+                        if (n < a.N) {
+                            // alpha acc 2^(ea + eb - 12) as two exact scalings, the smaller exponent first (no spurious overflow)
+                            const int eb6 = s_eb[half * 32 + i] - 6;
+                            const double val = a.alpha * ((acc[i] * oz_pow2(min(eam, eb6))) * oz_pow2(max(eam, eb6)));
+                            double* cp = a.C + m + n * a.ldc;
+                            *cp = (a.beta == 0.0) ? val : fma(a.beta, *cp, val);
+                        }
+                    }
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");           // everybody is done with s_eb
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -606,7 +660,7 @@ int oz_launch(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, const OzAr
         configured = true;
     }
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
-    oz_gemm_kernel<NS><<<(unsigned)(a.ntiles < sms ? a.ntiles : sms), 128, smem, c.stream>>>(tmA, tmB, a);
+    oz_gemm_kernel<NS><<<(unsigned)(a.ntiles < sms ? a.ntiles : sms), OZ_THREADS, smem, c.stream>>>(tmA, tmB, a);
     SGP_CUDA(cudaGetLastError());
     count_launch();
     return ST_OK;

@@ -222,12 +222,14 @@ def test_spd_inverse_and_logdet_on_the_int8_route(api, ozaki_all, n, ns, leaf):
     assert abs(ld - ldr) < 1e-10 * max(1.0, abs(ldr)) and abs(ld0 - ldr) < 1e-10 * max(1.0, abs(ldr))
     e = np.abs(Ai - ref).max() / np.abs(ref).max()
     e0 = np.abs(Ai0 - ref).max() / np.abs(ref).max()
-    print(f"\nn={n} ns={ns} leaf={leaf}: max|Ainv - ref| / max|ref| = {e:.2e} (DMMA route {e0:.2e})")
-    assert e < max(20 * e0, 1e-9), (e, e0)
-    # the residual A Ainv - I does not depend on the comparison inverse
-    r = np.abs(A @ Ai - np.eye(n)).max()
+    r = np.abs(A @ Ai - np.eye(n)).max()             # the residual does not depend on the comparison inverse
     r0 = np.abs(A @ Ai0 - np.eye(n)).max()
-    assert r < max(20 * r0, 1e-9), (r, r0)
+    print(f"\nn={n} ns={ns} leaf={leaf}: max|Ainv - ref| / max|ref| = {e:.2e} (DMMA route {e0:.2e}); |A Ainv - I| = {r:.2e} ({r0:.2e})")
+    # 7 slices keep 49 bits of every row's scale against the 53 of FP64 (measured ~100x the DMMA route's error at this
+    # condition number); 8 slices keep 56 and must match it
+    slack = 400.0 if ns == 7 else 8.0
+    assert e < slack * e0, (e, e0)
+    assert r < slack * r0, (r, r0)
 
 
 @pytest.mark.parametrize("ns,leaf", [(7, 256), (8, 512)])

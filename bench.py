@@ -554,9 +554,26 @@ def leg_sweep(B, dgemm):
         st = B.stage_times()
         n = 2.0 * Ns
         t3 = st["potrf"] + st["trtri"] + st["lauum"]
-        out.append({"N": Ns, "n": 2 * Ns, "ms_per_eval": ms, "TFLOP/s": n ** 3 / ms / 1e9, "frac_of_dgemm": n ** 3 / ms / 1e9 / dgemm,
-                    "stages_ms": {k: round(v, 4) for k, v in st.items()}, "dmma_stage_TFLOP/s": n ** 3 / t3 / 1e9 if t3 > 0 else None,
-                    "nll": float(rs_d[0].item())})
+        row = {"N": Ns, "n": 2 * Ns, "ms_per_eval": ms, "TFLOP/s": n ** 3 / ms / 1e9, "frac_of_dgemm": n ** 3 / ms / 1e9 / dgemm,
+               "stages_ms": {k: round(v, 4) for k, v in st.items()}, "dmma_stage_TFLOP/s": n ** 3 / t3 / 1e9 if t3 > 0 else None,
+               "nll": float(rs_d[0].item())}
+        if 2 * Ns > 4096:
+            # the same evaluation on the opt-in INT8 route (7 slices, all three stages)
+            res_dmma = rs_d.cpu().numpy().copy()
+            B.ctx.set_ozaki_ex(7, 3, 4096)
+            try:
+                for _ in range(1 if big else 2):
+                    step_s()
+                ms8 = B.timed(step_s, 2 if big else 5)
+                r8 = rs_d.cpu().numpy()
+                row["int8_route"] = {"ms_per_eval": ms8, "fp64_equiv_TFLOP/s": n ** 3 / ms8 / 1e9, "speedup": ms / ms8,
+                                     "nll_rel_diff": abs(float(r8[0]) - float(res_dmma[0])) / abs(float(res_dmma[0])),
+                                     "grad_rel_diff": max(abs(float(r8[1 + k]) - float(res_dmma[1 + k])) / abs(float(res_dmma[1 + k])) for k in range(2))}
+            except (MemoryError, RuntimeError) as e:
+                row["int8_route"] = {"skipped": str(e)[:120]}
+            finally:
+                B.ctx.set_ozaki_ex(0, 1, 0)
+        out.append(row)
         del xs_d, zs_d
         B.free()
     return out

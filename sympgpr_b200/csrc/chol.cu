@@ -174,64 +174,74 @@ gemv_t_lower_kernel(const double* __restrict__ X, long ld, const double* __restr
     if (lane == 0) alpha[c] = s;
 }
 
-// w = X z for the explicit lower-triangular X = L^-1 (the forward substitution L w = z, once the inverse factor exists and
-// the factor itself was never kept: the INT8 route, ozaki_chol.cu).  Block (i, j) = 128 rows x 512 columns on or below the
-// diagonal, rows down the threads (coalesced), partial sums per column chunk written to `part` and added in chunk order by
-// the second kernel: fixed summation order.  4 n^2 bytes, HBM-read bound.
-constexpr int TRMV_CW = 512;
+// y = A x (mode 0) or y -= A x (mode 1) for a column-major block A (rows x cols, multiples of 128; tri != 0: square and lower
+// triangular, the entries above the diagonal are not read).  With X = L^-1 this is the forward substitution w = X z of the
+// INT8 route, which never holds L (ozaki_chol.cu); with A = L21 the update z2 -= L21 w1 of its factor-only variant.
+// Block (i, j) = 128 rows x 512 columns, rows down the threads (coalesced), partial sums per column chunk written to `part`
+// and added in chunk order by the second kernel: fixed summation order.  HBM-read bound.
+constexpr int GEMV_CW = 512;
 __global__ void __launch_bounds__(256)
-trmv_lower_part_kernel(const double* __restrict__ X, long ld, const double* __restrict__ z, double* __restrict__ part, long n)
+gemv_part_kernel(const double* __restrict__ A, long ld, const double* __restrict__ x, double* __restrict__ part, long rows, long cols, int tri)
 {
-    __shared__ double zs[TRMV_CW];
+    __shared__ double xs[GEMV_CW];
     __shared__ double hi[TILE];
     const int i = blockIdx.x, j = blockIdx.y, tid = threadIdx.x;
-    const long c0 = (long)j * TRMV_CW, rend = (long)(i + 1) * TILE;
-    if (c0 >= rend) return;
-    const long c1 = c0 + TRMV_CW < rend ? c0 + TRMV_CW : rend;
-    for (int k = tid; k < TRMV_CW; k += 256) zs[k] = (c0 + k < c1) ? z[c0 + k] : 0.0;
+    const long c0 = (long)j * GEMV_CW;
+    const long cend = tri ? (long)(i + 1) * TILE : cols;          // columns this row tile reads at all
+    if (c0 >= cend) return;
+    const long c1 = c0 + GEMV_CW < cend ? c0 + GEMV_CW : cend;
+    for (int k = tid; k < GEMV_CW; k += 256) xs[k] = (c0 + k < c1) ? x[c0 + k] : 0.0;
     __syncthreads();
     const int r = tid & (TILE - 1), half = tid >> 7;
     const long row = (long)i * TILE + r;
-    const long hb = c0 + half * (TRMV_CW / 2);
-    long he = hb + TRMV_CW / 2;
+    const long hb = c0 + half * (GEMV_CW / 2);
+    long he = hb + GEMV_CW / 2;
     if (he > c1) he = c1;
-    if (he > row + 1) he = row + 1;
-    const double* Xr = X + row;
+    if (tri && he > row + 1) he = row + 1;
+    const double* Ar = A + row;
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     long cc = hb;
     for (; cc + 3 < he; cc += 4) {
-        a0 = fma(Xr[cc * ld], zs[cc - c0], a0);
-        a1 = fma(Xr[(cc + 1) * ld], zs[cc + 1 - c0], a1);
-        a2 = fma(Xr[(cc + 2) * ld], zs[cc + 2 - c0], a2);
-        a3 = fma(Xr[(cc + 3) * ld], zs[cc + 3 - c0], a3);
+        a0 = fma(Ar[cc * ld], xs[cc - c0], a0);
+        a1 = fma(Ar[(cc + 1) * ld], xs[cc + 1 - c0], a1);
+        a2 = fma(Ar[(cc + 2) * ld], xs[cc + 2 - c0], a2);
+        a3 = fma(Ar[(cc + 3) * ld], xs[cc + 3 - c0], a3);
     }
-    for (; cc < he; cc++) a0 = fma(Xr[cc * ld], zs[cc - c0], a0);
+    for (; cc < he; cc++) a0 = fma(Ar[cc * ld], xs[cc - c0], a0);
     const double s = (a0 + a1) + (a2 + a3);
     if (half) hi[r] = s;
     __syncthreads();
-    if (!half) part[(long)j * n + row] = s + hi[r];
+    if (!half) part[(long)j * rows + row] = s + hi[r];
 }
 
-__global__ void trmv_lower_sum_kernel(const double* __restrict__ part, double* __restrict__ w, long n)
+__global__ void gemv_sum_kernel(const double* __restrict__ part, double* __restrict__ y, long rows, long cols, int tri, int mode)
 {
     const long row = (long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= n) return;
-    const long rend = (row / TILE + 1) * TILE;
+    if (row >= rows) return;
+    const long cend = tri ? (row / TILE + 1) * TILE : cols;
     double s = 0.0;
-    for (long j = 0; j * TRMV_CW < rend; j++) s += part[j * n + row];
-    w[row] = s;
+    for (long j = 0; j * GEMV_CW < cend; j++) s += part[j * rows + row];
+    y[row] = mode ? y[row] - s : s;
 }
 
-size_t trmv_lower_scratch_doubles(long n_pad) { return (size_t)((n_pad + TRMV_CW - 1) / TRMV_CW) * (size_t)n_pad; }
+size_t gemv_scratch_doubles(long rows, long cols) { return (size_t)((cols + GEMV_CW - 1) / GEMV_CW) * (size_t)rows; }
 
-int trmv_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* z, double* w, double* part)
+int gemv_blocked(Ctx& c, const double* A, long ld, long rows, long cols, int tri, const double* x, double* y, int mode, double* part)
 {
-    const dim3 grid((unsigned)(n_pad / TILE), (unsigned)((n_pad + TRMV_CW - 1) / TRMV_CW));
-    trmv_lower_part_kernel<<<grid, 256, 0, c.stream>>>(X, ldx, z, part, n_pad);
-    trmv_lower_sum_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, c.stream>>>(part, w, n_pad);
+    if (rows % TILE || cols % TILE || (tri && rows != cols)) { set_error("gemv_blocked: block %ld x %ld not tile aligned", rows, cols); return ST_BADARG; }
+    const dim3 grid((unsigned)(rows / TILE), (unsigned)((cols + GEMV_CW - 1) / GEMV_CW));
+    gemv_part_kernel<<<grid, 256, 0, c.stream>>>(A, ld, x, part, rows, cols, tri);
+    gemv_sum_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, c.stream>>>(part, y, rows, cols, tri, mode);
     SGP_CUDA(cudaGetLastError());
     count_launch(2);
     return ST_OK;
+}
+
+size_t trmv_lower_scratch_doubles(long n_pad) { return gemv_scratch_doubles(n_pad, n_pad); }
+
+int trmv_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* z, double* w, double* part)
+{
+    return gemv_blocked(c, X, ldx, n_pad, n_pad, 1, z, w, 0, part);
 }
 
 int gemv_t_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* w, double* alpha)

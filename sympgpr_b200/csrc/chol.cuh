@@ -19,6 +19,9 @@ int gemv_t_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* w,
 // w = X z for the explicit lower-triangular X; part: trmv_lower_scratch_doubles(n_pad) doubles of device scratch
 int trmv_lower(Ctx& c, const double* X, long n_pad, long ldx, const double* z, double* w, double* part);
 size_t trmv_lower_scratch_doubles(long n_pad);
+// y = A x (mode 0) / y -= A x (mode 1), A rows x cols column-major (tri: square lower triangular); part: gemv_scratch_doubles
+int gemv_blocked(Ctx& c, const double* A, long ld, long rows, long cols, int tri, const double* x, double* y, int mode, double* part);
+size_t gemv_scratch_doubles(long rows, long cols);
 // alpha = W y for the symmetric W given by its lower triangle (tiles on and below the diagonal complete)
 int symv_lower(Ctx& c, const double* W, long n_pad, long ldw, const double* y, double* alpha);
 int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T);

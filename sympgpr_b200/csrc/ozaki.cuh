@@ -56,4 +56,11 @@ size_t ozaki_factinv_workspace_bytes(long n_pad, int ns);
 int ozaki_factinv(Ctx& c, int ns, long leaf_n, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* T,
                   void* work, size_t work_bytes);
 
+// Factor-only variant for evaluations that need the value alone (0.38 n^3 flop): the diagonal blocks of the recursion hold
+// inverse factors, the off-diagonal blocks L itself, and the forward substitution L w = z rides along (z is updated in place;
+// leaves solve their part inside potrf_ll).  part: ozaki_factor_solve_scratch_doubles(n_pad) doubles; work as for ozaki_factinv.
+size_t ozaki_factor_solve_scratch_doubles(long n_pad);
+int ozaki_factor_solve(Ctx& c, int ns, long leaf_n, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* T,
+                       double* z, double* w, double* part, void* work, size_t work_bytes);
+
 }  // namespace sgp

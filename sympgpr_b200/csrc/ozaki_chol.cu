@@ -33,14 +33,20 @@ struct FactInv {
     double *Dinv, *logparts, *T;
     int* info;
     void *bufA, *bufB;
+    double *z, *w, *part;      // factor-only variant: right-hand side (updated in place), solution of L w = z, gemv scratch
 };
 
-int node(FactInv& f, int j0, int mt)
+// inverse = true: the block is replaced by X = L^-1.  inverse = false (factor-only variant, for evaluations that need the value
+// alone): X11 is still formed (step 2 needs it) but A21 keeps L21, steps 4 and 6 are skipped and the (2,2) block recurses in
+// the same form -- n^3/3 + n^3/24 + ... = 0.38 n^3 flop instead of 0.67 n^3; the forward substitution L w = z rides along:
+// w1 = X11 z1, z2 -= L21 w1 before the (2,2) block, and a leaf solves its own part inside potrf_ll.
+int node(FactInv& f, int j0, int mt, bool inverse)
 {
     double* A11 = AT(f.A, f.lda, j0, j0);
     if (mt <= f.leaf_t) {
         const long nb = (long)mt * TILE;
         double* Dinv = f.Dinv + (long)j0 * TILE * TILE;
+        if (!inverse) return potrf(f.c, A11, nb, f.lda, Dinv, f.logparts + j0, f.info, f.z + (long)j0 * TILE, f.w + (long)j0 * TILE);
         SGP_TRY(potrf(f.c, A11, nb, f.lda, Dinv, f.logparts + j0, f.info));
         return trtri(f.c, A11, nb, f.lda, Dinv, f.T);
     }
@@ -50,7 +56,7 @@ int node(FactInv& f, int j0, int mt)
     double* A22 = AT(f.A, f.lda, j0 + m1, j0 + m1);
     Ctx& c = f.c;
     const int ns = f.ns;
-    SGP_TRY(node(f, j0, m1));
+    SGP_TRY(node(f, j0, m1, true));
     // 2. L21 = A21 X11^T
     OzSliced SA = ozaki_carve(f.bufA, h2, h1, ns), SB = ozaki_carve(f.bufB, h1, h1, ns);
     SGP_TRY(ozaki_slice(c, ns, A21, f.lda, h2, h1, OZ_MN, 0, SA));
@@ -59,11 +65,18 @@ int node(FactInv& f, int j0, int mt)
     // 3. A22 -= L21 L21^T
     SGP_TRY(ozaki_slice(c, ns, A21, f.lda, h2, h1, OZ_MN, 0, SA));
     SGP_TRY(ozaki_gemm_sliced(c, ns, SA, SA, h2, h2, -1.0, 1.0, A22, f.lda, 0, 1));
+    if (!inverse) {
+        double* z1 = f.z + (long)j0 * TILE;
+        double* w1 = f.w + (long)j0 * TILE;
+        SGP_TRY(gemv_blocked(c, A11, f.lda, h1, h1, 1, z1, w1, 0, f.part));                      // w1 = X11 z1
+        SGP_TRY(gemv_blocked(c, A21, f.lda, h2, h1, 0, w1, z1 + h1, 1, f.part));                 // z2 -= L21 w1
+        return node(f, j0 + m1, m2, false);
+    }
     // 4. A21 = L21 X11
     SGP_TRY(ozaki_slice(c, ns, A11, f.lda, h1, h1, OZ_K, 2, SB));
     SGP_TRY(ozaki_gemm_sliced(c, ns, SA, SB, h2, h1, 1.0, 0.0, A21, f.lda, OZ_KLO_TN, 0));
     // 5.
-    SGP_TRY(node(f, j0 + m1, m2));
+    SGP_TRY(node(f, j0 + m1, m2, true));
     // 6. X21 = -X22 (L21 X11)
     SA = ozaki_carve(f.bufA, h2, h2, ns);
     SB = ozaki_carve(f.bufB, h1, h2, ns);
@@ -80,15 +93,37 @@ size_t ozaki_factinv_workspace_bytes(long n_pad, int ns)
     return 2 * (ozaki_sliced_bytes(hmax, hmax, ns) + 256);
 }
 
+static int oz_chol_check(const char* who, int ns, long leaf_n, long n_pad, long lda, size_t work_bytes)
+{
+    if (n_pad <= 0 || n_pad % TILE || (lda & 1) || leaf_n < TILE) { set_error("%s: bad arguments", who); return ST_BADARG; }
+    if (ns < 4 || ns > 8 || (long)ns * n_pad * 4096 >= 2147483647L) { set_error("%s: %d slices at order %ld: no exact INT32 accumulation", who, ns, n_pad); return ST_BADARG; }
+    if (work_bytes < ozaki_factinv_workspace_bytes(n_pad, ns)) { set_error("%s: workspace too small", who); return ST_BADARG; }
+    return ST_OK;
+}
+
 int ozaki_factinv(Ctx& c, int ns, long leaf_n, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* T,
                   void* work, size_t work_bytes)
 {
-    if (n_pad <= 0 || n_pad % TILE || (lda & 1) || leaf_n < TILE) { set_error("ozaki_factinv: bad arguments"); return ST_BADARG; }
-    if (ns < 4 || ns > 8 || (long)ns * n_pad * 4096 >= 2147483647L) { set_error("ozaki_factinv: %d slices at order %ld: no exact INT32 accumulation", ns, n_pad); return ST_BADARG; }
-    if (work_bytes < ozaki_factinv_workspace_bytes(n_pad, ns)) { set_error("ozaki_factinv: workspace too small"); return ST_BADARG; }
+    SGP_TRY(oz_chol_check("ozaki_factinv", ns, leaf_n, n_pad, lda, work_bytes));
     const size_t half = ozaki_factinv_workspace_bytes(n_pad, ns) / 2;
-    FactInv f{c, ns, (int)(leaf_n / TILE), A, lda, Dinv, logparts, T, info, work, (char*)work + half};
-    return node(f, 0, (int)(n_pad / TILE));
+    FactInv f{c, ns, (int)(leaf_n / TILE), A, lda, Dinv, logparts, T, info, work, (char*)work + half, nullptr, nullptr, nullptr};
+    return node(f, 0, (int)(n_pad / TILE), true);
+}
+
+size_t ozaki_factor_solve_scratch_doubles(long n_pad)
+{
+    const long nt = n_pad / TILE, h = (nt - nt / 2) * TILE;
+    return gemv_scratch_doubles(h, h) + 16;
+}
+
+int ozaki_factor_solve(Ctx& c, int ns, long leaf_n, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, double* T,
+                       double* z, double* w, double* part, void* work, size_t work_bytes)
+{
+    SGP_TRY(oz_chol_check("ozaki_factor_solve", ns, leaf_n, n_pad, lda, work_bytes));
+    if (!z || !w || !part) { set_error("ozaki_factor_solve: bad arguments"); return ST_BADARG; }
+    const size_t half = ozaki_factinv_workspace_bytes(n_pad, ns) / 2;
+    FactInv f{c, ns, (int)(leaf_n / TILE), A, lda, Dinv, logparts, T, info, work, (char*)work + half, z, w, part};
+    return node(f, 0, (int)(n_pad / TILE), false);
 }
 
 }  // namespace sgp

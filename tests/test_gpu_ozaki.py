@@ -247,6 +247,28 @@ def test_nll_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all, N, ns, le
     assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr)
 
 
+@pytest.mark.parametrize("ns,leaf", [(7, 128), (7, 256), (8, 384)])
+@pytest.mark.parametrize("N", [600, 1024, 1600])
+def test_nll_value_on_the_factor_only_int8_recursion(api, ozaki_all, N, ns, leaf):
+    """nll_chol (value only: the objective of the scripts' L-BFGS loops) through the factor-only variant of the INT8 recursion --
+    inverse factors on the diagonal blocks, L below them, forward substitution riding along -- against the oracle at 1e-9, and
+    the regression-kernel variant (nll_chol_reg) likewise."""
+    from oracle import oracle as O
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    vr = O.nll_chol(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    v0 = api.nll_chol(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    ozaki_all.set_ozaki_ex(ns, 3, leaf)
+    v = api.nll_chol(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    print(f"\nN={N} ns={ns} leaf={leaf}: nll {v!r} (DMMA {v0!r}, oracle {vr!r})")
+    assert np.isclose(v, vr, rtol=1e-9), (v, vr)
+    assert np.isclose(v, v0, rtol=1e-11), (v, v0)
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8)
+    vr = O.nll_chol_reg(hypp, d["xtrainp"], d["ztrainp"], N)
+    v = api.nll_chol_reg(hypp, d["xtrainp"], d["ztrainp"], N)
+    assert np.isclose(v, vr, rtol=1e-9), (v, vr)
+
+
 def test_int8_route_reports_a_matrix_that_is_not_positive_definite(api, ozaki_all):
     """The leaf factorisations carry the info word: a negative pivot in the SECOND half of the recursion (after sliced updates)
     still raises LinAlgError, as the reference's bare `except` around scipy.linalg.cholesky expects."""

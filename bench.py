@@ -443,7 +443,7 @@ def leg_ozaki(B, head_ms, head_res, dgemm, bf16_peak):
     a, torch, W = B.a, B.torch, B.W
     out = {"note": "opt-in (sgp_set_ozaki_ex); headline value/roofline above are the DMMA path north_star names"}
     g = {}
-    for ns in (7, 8):
+    for ns in (6, 7):
         ms = (ctypes.c_double * 2)()
         B._lib.check(B.L.sgp_ozaki_bench(B.ctx.handle, ns, 8192, 8192, 8192, 3, ms), "sgp_ozaki_bench")
         g[f"{ns}_slices"] = {"ms_slicing_plus_gemm": ms[0], "ms_gemm": ms[1], "fp64_equiv_TFLOP/s": 2 * 8192.0**3 / ms[0] / 1e9,
@@ -456,10 +456,10 @@ def leg_ozaki(B, head_ms, head_res, dgemm, bf16_peak):
     # INT8 has no entry in MEASURED_PEAKS.json; the dense INT8 rate of the tensor core is twice its bf16 rate (nominal 4.5 POP/s
     # against 2.25 PFLOP/s), so 2 x the MEASURED bf16 burst figure is the denominator
     if bf16_peak:
-        tops = g["7_slices"]["int8_TOP/s_gemm_only"]
-        g["roofline"] = {"kernel": "oz_gemm_kernel<7>", "bound": "tensor", "achieved": tops, "peak": 2.0 * bf16_peak, "unit": "INT8 TOP/s",
+        tops = g["6_slices"]["int8_TOP/s_gemm_only"]
+        g["roofline"] = {"kernel": "oz_gemm_kernel<6>", "bound": "tensor", "achieved": tops, "peak": 2.0 * bf16_peak, "unit": "INT8 TOP/s",
                          "frac": tops / (2.0 * bf16_peak),
-                         "note": "28 slice-pair products of 128 x 64 x K per output tile; peak = 2 x bf16_tflops of MEASURED_PEAKS.json "
+                         "note": "21 digit-pair products of 128 x 64 x K per output tile; peak = 2 x bf16_tflops of MEASURED_PEAKS.json "
                                  "(no INT8 entry there; burst figure, the kernel is timed alone)"}
     out["gemm_8192"] = g
     B.free()
@@ -475,45 +475,54 @@ def leg_ozaki(B, head_ms, head_res, dgemm, bf16_peak):
     def rel(res):
         return [abs(float(res[1 + k]) - float(head_res[1 + k])) / abs(float(head_res[1 + k])) for k in range(2)]
 
-    # (b) all stages
-    B.ctx.set_ozaki_ex(7, 3, 4096)
-    try:
-        step(); step(); step()
-        reps = max(3, a.steps)
-        t0 = time.time()
-        ms = B.timed(step, reps)
-        t1 = time.time()
-        st = B.stage_times()
-        res = res_d.cpu().numpy()
-        # end to end through the public API from pinned host buffers, as the headline's e2e
-        x_h = torch.from_numpy(d["xtrain"].copy()).pin_memory()
-        z_h = torch.from_numpy(d["ztrain"].copy()).pin_memory()
-        xn, zn = x_h.numpy(), z_h.numpy()
-        B.api.nll_grad(hyp, xn, zn, n)
-        te = time.perf_counter()
-        for _ in range(3):
-            ve, ge = B.api.nll_grad(hyp, xn, zn, n)
-        te = (time.perf_counter() - te) / 3
-    finally:
-        B.ctx.set_ozaki_ex(0, 1, 0)
-        B.free()
-    t3 = st["potrf"] + st["trtri"] + st["lauum"]
-    out["nll_grad_all_stages_int8"] = {
-        "slices": 7, "leaf_rows_on_dmma": 4096, "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "speedup_vs_dmma_path": head_ms / ms,
-        "e2e": {"value": 1.0 / te, "unit": "evals/s", "ms_per_eval": 1e3 * te, "h2d_bytes_per_step": int(x_h.numel() * 8 + z_h.numel() * 8),
-                "d2h_bytes_per_step": 16 * 8},
-        "stages_ms": {k: round(v, 3) for k, v in st.items()},
-        "stage_note": "potrf + trtri run as ONE recursion (ozaki_factinv) timed under 'trtri', with w = X z and alpha = X^T w",
-        "fp64_equiv_TFLOP/s": float(n)**3 / t3 / 1e9, "frac_of_dgemm": float(n)**3 / t3 / 1e9 / dgemm,
-        "lauum_fp64_equiv_TFLOP/s": float(n)**3 / 3.0 / st["lauum"] / 1e9,
-        "clocks": B.sampler.summary(t0, t1),
-        "nll": float(res[0]), "grad": [float(res[1]), float(res[2])],
-        "nll_rel_diff_vs_dmma_path": abs(float(res[0]) - float(head_res[0])) / abs(float(head_res[0])),
-        "grad_rel_diff_vs_dmma_path": rel(res),
-        "parity": "tests/test_gpu_ozaki.py::test_full_size_gradient_with_all_stages_on_the_int8_pipe: this route against the CPU golden "
-                  "(tests/golden/fullsize_nll_N16384.json) at 1e-9"}
-    # (c) lauum only (8 slices)
-    B.ctx.set_ozaki(8)
+    # (b) all stages: 6 digits (47 bits of every row's scale, 21 digit pairs) and 7 digits (55 bits, 28 pairs: FP64-grade)
+    for ns, key in ((6, "nll_grad_all_stages_int8"), (7, "nll_grad_all_stages_int8_7digits")):
+        B.ctx.set_ozaki_ex(ns, 3, 4096)
+        try:
+            step(); step(); step()
+            reps = max(3, a.steps)
+            t0 = time.time()
+            ms = B.timed(step, reps)
+            t1 = time.time()
+            st = B.stage_times()
+            res = res_d.cpu().numpy()
+            # end to end through the public API from pinned host buffers, as the headline's e2e; then the value-only evaluation
+            x_h = torch.from_numpy(d["xtrain"].copy()).pin_memory()
+            z_h = torch.from_numpy(d["ztrain"].copy()).pin_memory()
+            xn, zn = x_h.numpy(), z_h.numpy()
+            B.api.nll_grad(hyp, xn, zn, n)
+            te = time.perf_counter()
+            for _ in range(3):
+                ve, ge = B.api.nll_grad(hyp, xn, zn, n)
+            te = (time.perf_counter() - te) / 3
+            B.api.nll_chol(hyp, xn, zn, n)
+            tv = time.perf_counter()
+            for _ in range(3):
+                vv = B.api.nll_chol(hyp, xn, zn, n)
+            tv = (time.perf_counter() - tv) / 3
+        finally:
+            B.ctx.set_ozaki_ex(0, 1, 0)
+            B.free()
+        t3 = st["potrf"] + st["trtri"] + st["lauum"]
+        out[key] = {
+            "digits": ns, "bits_of_row_scale": 8 * ns - 1, "digit_pairs": ns * (ns + 1) // 2, "leaf_rows_on_dmma": 4096,
+            "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "speedup_vs_dmma_path": head_ms / ms,
+            "e2e": {"value": 1.0 / te, "unit": "evals/s", "ms_per_eval": 1e3 * te, "h2d_bytes_per_step": int(x_h.numel() * 8 + z_h.numel() * 8),
+                    "d2h_bytes_per_step": 16 * 8},
+            "value_only_e2e": {"ms_per_eval": 1e3 * tv, "nll": float(vv),
+                               "note": "api.nll_chol (the objective of the scripts' L-BFGS loops) through the factor-only recursion, 0.38 n^3 flop"},
+            "stages_ms": {k: round(v, 3) for k, v in st.items()},
+            "stage_note": "potrf + trtri run as ONE recursion (ozaki_factinv) timed under 'trtri', with w = X z and alpha = X^T w",
+            "fp64_equiv_TFLOP/s": float(n)**3 / t3 / 1e9, "frac_of_dgemm": float(n)**3 / t3 / 1e9 / dgemm,
+            "lauum_fp64_equiv_TFLOP/s": float(n)**3 / 3.0 / st["lauum"] / 1e9,
+            "clocks": B.sampler.summary(t0, t1),
+            "nll": float(res[0]), "grad": [float(res[1]), float(res[2])],
+            "nll_rel_diff_vs_dmma_path": abs(float(res[0]) - float(head_res[0])) / abs(float(head_res[0])),
+            "grad_rel_diff_vs_dmma_path": rel(res),
+            "parity": "tests/test_gpu_ozaki.py::test_full_size_gradient_with_all_stages_on_the_int8_pipe: this route against the CPU golden "
+                      "(tests/golden/fullsize_nll_N16384.json) at 1e-9"}
+    # (c) lauum only (7 digits)
+    B.ctx.set_ozaki(7)
     try:
         step(); step()
         ms = B.timed(step, 3)
@@ -522,7 +531,7 @@ def leg_ozaki(B, head_ms, head_res, dgemm, bf16_peak):
     finally:
         B.ctx.set_ozaki(0)
         B.free()
-    out["nll_grad_lauum_int8"] = {"slices": 8, "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "speedup_vs_dmma_path": head_ms / ms,
+    out["nll_grad_lauum_int8"] = {"digits": 7, "ms_per_eval": ms, "evals_per_s": 1e3 / ms, "speedup_vs_dmma_path": head_ms / ms,
                                   "stages_ms": {k: round(v, 3) for k, v in st.items()},
                                   "lauum_fp64_equiv_TFLOP/s": float(n)**3 / 3.0 / st["lauum"] / 1e9,
                                   "nll": float(res[0]), "grad": [float(res[1]), float(res[2])],
@@ -558,9 +567,9 @@ def leg_sweep(B, dgemm):
                "stages_ms": {k: round(v, 4) for k, v in st.items()}, "dmma_stage_TFLOP/s": n ** 3 / t3 / 1e9 if t3 > 0 else None,
                "nll": float(rs_d[0].item())}
         if 2 * Ns > 4096:
-            # the same evaluation on the opt-in INT8 route (7 slices, all three stages)
+            # the same evaluation on the opt-in INT8 route (6 digits, all three stages)
             res_dmma = rs_d.cpu().numpy().copy()
-            B.ctx.set_ozaki_ex(7, 3, 4096)
+            B.ctx.set_ozaki_ex(6, 3, 4096)
             try:
                 for _ in range(1 if big else 2):
                     step_s()

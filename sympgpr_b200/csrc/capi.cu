@@ -964,7 +964,7 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
     SGP_CUDA(cudaGetLastError());
     SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), c.stream));
     // opt-in INT8 route (sgp_set_ozaki_ex, stages bit 1): factor and inverse factor in one recursion; it never holds L
-    const bool oz_ok = c.ozaki_slices > 0 && (long)c.ozaki_slices * n_pad * 4096 < 2147483647L;
+    const bool oz_ok = c.ozaki_slices > 0;
     const bool oz_fact = oz_ok && (c.ozaki_stages & 2) && Ainv && !L && n_pad > c.ozaki_leaf;
     if (oz_fact) {
         const size_t wb = ozaki_factinv_workspace_bytes(n_pad, c.ozaki_slices);
@@ -1095,12 +1095,13 @@ int sgp_ozaki_gemm_host_ex(sgp_ctx* ctx, int ns, long M, long N, long K, double 
     Ctx& c = ctx->c;
     if (M <= 0 || N <= 0 || K <= 0 || !A || !B || !C || ldc < M) { set_error("ozaki_gemm_host_ex: bad arguments"); return ST_BADARG; }
     if (lda < (la == OZ_MN ? M : K) || ldb < (lb == OZ_MN ? N : K)) { set_error("ozaki_gemm_host_ex: leading dimension too small"); return ST_BADARG; }
+    if ((la == OZ_K && (lda & 1)) || (lb == OZ_K && (ldb & 1))) { set_error("ozaki_gemm_host_ex: the leading dimension of an operand in storage order 1 must be even"); return ST_BADARG; }
     const size_t szA = (size_t)lda * (la == OZ_MN ? K : M), szB = (size_t)ldb * (lb == OZ_MN ? K : N), szC = (size_t)ldc * N;
     const size_t bA = ozaki_sliced_bytes(M, K, ns) + 256, bB = ozaki_sliced_bytes(N, K, ns) + 256;
     SGP_TRY(c.Kmat.reserve((szA + szB + szC + 8) * sizeof(double)));
     SGP_TRY(c.Wmat.reserve(bA + bB));
     double* dA = c.Kmat.as<double>();
-    double* dB = dA + szA; double* dC = dB + szB;
+    double* dB = dA + ((szA + 1) & ~(size_t)1); double* dC = dB + ((szB + 1) & ~(size_t)1);       // 16-byte aligned operands
     SGP_TRY(upload(c, dA, A, szA)); SGP_TRY(upload(c, dB, B, szB)); SGP_TRY(upload(c, dC, C, szC));
     const OzSliced SA = ozaki_carve(c.Wmat.p, M, K, ns), SB = ozaki_carve((char*)c.Wmat.p + bA, N, K, ns);
     SGP_TRY(ozaki_slice(c, ns, dA, lda, M, K, la, ta, SA));

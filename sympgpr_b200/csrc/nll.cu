@@ -153,7 +153,7 @@ int nll_enqueue(Ctx& c, const NllJob& job)
 
     // opt-in (sgp_set_ozaki_ex): factor and inverse factor in one recursion whose products run on the INT8 tensor pipe
     // (ozaki_chol.cu).  It leaves X = L^-1 and never L, so it serves the evaluations that form the inverse and do not hand L out.
-    const bool oz_ok = c.ozaki_slices > 0 && (long)c.ozaki_slices * n_pad * 4096 < 2147483647L;
+    const bool oz_ok = c.ozaki_slices > 0;
     const bool oz_fact = oz_ok && (c.ozaki_stages & 2) && need_inv && !job.d_L && n_pad > c.ozaki_leaf;
     // ... and its factor-only variant for the evaluations that need the value alone (nll_chol, the objective of the scripts'
     // L-BFGS / CMA loops): 0.38 n^3 flop on the INT8 pipe instead of n^3 / 3 on DMMA

@@ -3,14 +3,16 @@
 // north_star asks for DMMA in the Cholesky (done: potrf_ll.cu / dmma_gemm_ws.cuh run at 91-97 % of the DMMA issue limit),
 // which makes that limit -- 37 TFLOP/s -- the ceiling of the NLL+gradient evaluation.  The only way past it on Blackwell is
 // the 5th-generation tensor core, which has no f64 kind: tcgen05.mma kind::i8 (INT8 x INT8 -> INT32, accumulators in tensor
-// memory).  An FP64 product is recovered EXACTLY up to the slices kept by splitting both operands into signed 7-bit slices
-// of their row-scaled mantissas (Ozaki scheme):
-//     A(m,:) = 2^(ea(m)-6) sum_s As(m,:) 2^(-7 s),   B(n,:) = 2^(eb(n)-6) sum_t Bt(n,:) 2^(-7 t),   |As|,|Bt| <= 64
-//     C(m,n) = 2^(ea(m)+eb(n)-12) sum_d 2^(-7 d) sum_{s+t=d} As(m,:) . Bt(n,:)          (d < NS: the pairs that matter)
-// Every slice product is an integer GEMM without rounding (K 64^2 NS < 2^31 for K <= 65536 / NS), pairs with equal
-// s + t share one INT32 accumulator in tensor memory, and the only floating-point roundings are the final NS-term sum per
-// output element.  tools/ozaki_study.py (round 1) shows 7 slices hold 1e-9 on the benchmark NLL and 9 are needed at
-// cond 1e10.
+// memory).  An FP64 product is recovered EXACTLY up to the slices kept by splitting both operands into signed 8-bit digits
+// of their row-scaled mantissas (Ozaki scheme, balanced radix 256):
+//     A(m,:) = 2^(ea(m)-7) sum_s As(m,:) 2^(-8 s),   B(n,:) = 2^(eb(n)-7) sum_t Bt(n,:) 2^(-8 t),   -128 <= As, Bt <= 127
+//     C(m,n) = 2^(ea(m)+eb(n)-14) sum_d 2^(-8 d) sum_{s+t=d} As(m,:) . Bt(n,:)          (d < NS: the pairs that matter)
+// Every slice product is an integer GEMM without rounding (NS K 128^2 < 2^31 per launch: deeper products are split along K
+// on the host side), pairs with equal s + t share one INT32 accumulator in tensor memory, and the only floating-point
+// roundings are the final NS-term sum per output element.  Balanced digits (every digit signed, taken from the bottom of the
+// two's-complement mantissa with a carry) keep the dropped pairs zero-mean, so their sum over k grows like sqrt(K), not K.
+// NS digits keep 8 NS - 1 bits of every ROW'S scale: 6 -> 47 (21 slice pairs), 7 -> 55 (28 pairs: FP64-grade), 8 -> 63.
+// (Round-2 states up to "i" used 7-bit digits from round-to-nearest of every stage: 49 bits for 28 pairs.)
 //
 // This file: (1) the tcgen05 plumbing (TMEM allocation, shared-memory matrix descriptors for the K-major 128-byte-swizzled
 // canonical layout, the kind::i8 instruction descriptor, tcgen05.commit -> mbarrier, tcgen05.ld) with a self test of one
@@ -195,9 +197,8 @@ __global__ void i32_diff_kernel(const int32_t* __restrict__ a, const int32_t* __
 // ---------------------------------------------------------------------------------------------------------
 // (2) slicing: FP64 operand X (R rows x K) -> row exponents e(r) with max_k |X(r,k)| < 2^e(r) and NS INT8 slices
 //     slices[s][r][k] (k contiguous, row pitch Kp, slice pitch Rp Kp) with
-//     X(r,k) = 2^(e-6) sum_s slices[s][r][k] 2^(-7 s) + O(2^(e - 6 - 7 NS)),  |slice| <= 64.
-// Every step is exact in FP64 (scaling by a power of two, round-to-nearest-integer by the 1.5 * 2^52 trick -- whose sum also
-// holds the integer in its low mantissa bits --, subtracting the integer just extracted).  Two storage orders of X:
+//     X(r,k) = 2^(e-7) sum_s slices[s][r][k] 2^(-8 s) + O(2^(e - 8 NS)),  -128 <= slice <= 127.
+// Every step is exact (scaling by a power of two, one rounding to a 64-bit integer, integer digit extraction).  Two storage orders of X:
 //     OZ_MN: element (r, k) at X[r + k ld]   (operand rows run down the columns of a column-major matrix)
 //     OZ_K:  element (r, k) at X[k + r ld]   (operand rows ARE the columns of a column-major matrix: the operand is X^T)
 // and triangular operands whose other half holds unrelated numbers (the Cholesky works in the lower triangle only):
@@ -205,27 +206,35 @@ __global__ void i32_diff_kernel(const int32_t* __restrict__ a, const int32_t* __
 // invalid entries become zeros, and k-chunks that no GEMM tile of a triangular product loads are not written at all.
 // Rows / columns beyond R / K are zero.
 // ---------------------------------------------------------------------------------------------------------
-constexpr double OZ_MAGIC = 6755399441055744.0;        // 1.5 * 2^52
+// 2^e as a double for -1022 <= e <= 1023
+__device__ __forceinline__ double oz_pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
 
-// y (|y| <= 64, or anything else -> treated as 0) -> NS signed slices through `put(s, byte)`
+// x (|x| < 0.995 * 2^e, e its row's exponent; anything else -> treated as 0) -> NS balanced radix-256 digits through
+// `put(s, digit)`: v = rint(x 2^(8 NS - 1 - e)) as a 64-bit integer (exact: a power-of-two scaling of a 53-bit mantissa, at most
+// 2 bits of left shift), digits from the bottom with the carry of the sign extension
 template <int NS, class Put>
-__device__ __forceinline__ void oz_split(double y, Put put)
+__device__ __forceinline__ void oz_split(double x, int e, Put put)
 {
-    if (!(fabs(y) <= 64.0)) y = 0.0;                   // NaN / Inf / out of range: not representable
+    const int k = 8 * NS - 1 - e, k1 = k > 1000 ? 1000 : k;       // -969 <= k <= 1063
+    const double y = (x * oz_pow2(k1)) * oz_pow2(k - k1);
+    long long v = (fabs(y) < 0.996 * oz_pow2(8 * NS - 1)) ? __double2ll_rn(y) : 0ll;       // NaN / Inf / out of range: not representable
 #pragma unroll
-    for (int s = 0; s < NS; s++) {
-        const double t = y + OZ_MAGIC;                 // low mantissa bits of t = rint(y) (two's complement)
-        put(s, (int8_t)__double2loint(t));
-        y = (y - (t - OZ_MAGIC)) * 128.0;
+    for (int s = NS - 1; s >= 0; s--) {
+        const int8_t d = (int8_t)(v & 0xff);
+        put(s, d);
+        v = (v - d) >> 8;
     }
 }
-// 2^(6 - e) for -1000 < e <= 1024 (oz_exp_kernel keeps e in that range)
-__device__ __forceinline__ double oz_scale(int e) { return __hiloint2double((1023 + 6 - e) << 20, 0); }
 
+// row exponent: max|x| = f 2^e with 0.5 <= f < 0.995 (one more when the mantissa is at the top of its binade, so that the leading
+// digit stays below 128); rows below 1e-290 count as zero rows
 __device__ __forceinline__ int oz_exp_of(double mx)
 {
     int e = 0;
-    if (mx >= 1e-290 && mx <= DBL_MAX) frexp(mx, &e);  // mx = f 2^e, 0.5 <= f < 1  =>  |x| 2^-e < 1; tiny rows count as zero rows
+    if (mx >= 1e-290 && mx <= DBL_MAX) {
+        const double f = frexp(mx, &e);
+        if (f >= 0.995) e++;
+    }
     return e;
 }
 
@@ -271,7 +280,7 @@ __global__ void __launch_bounds__(256) oz_slice_mn_kernel(const double* __restri
     if (tri == 1 && k0 >= (r0 / 128 + 1) * 128) return;             // beyond every k-range that reads these rows
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const long r = r0 + tx;
-    const double sc = oz_scale((r < R) ? exps[r] : 0);
+    const int e = (r < R) ? exps[r] : 0;
     double x[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
@@ -279,7 +288,7 @@ __global__ void __launch_bounds__(256) oz_slice_mn_kernel(const double* __restri
         x[j] = (r < R && k < K && (tri != 1 || k <= r)) ? X[r + k * ld] : 0.0;
     }
 #pragma unroll
-    for (int j = 0; j < 16; j++) oz_split<NS>(x[j] * sc, [&](int s, int8_t b) { tile[s][tx][ty + 8 * j] = b; });
+    for (int j = 0; j < 16; j++) oz_split<NS>(x[j], e, [&](int s, int8_t b) { tile[s][tx][ty + 8 * j] = b; });
     __syncthreads();
     const int row = threadIdx.x >> 3, kq = threadIdx.x & 7;
 #pragma unroll
@@ -311,12 +320,12 @@ template <int NS>
 __global__ void __launch_bounds__(256) oz_slice_k_kernel(const double* __restrict__ X, long ld, long R, long K, int tri,
                                                           const int* __restrict__ exps, int8_t* __restrict__ slices, long Rp, long Kp)
 {
-    const long kb = (long)blockIdx.x * blockDim.x + threadIdx.x;       // 16-element block index along k
-    const long r = blockIdx.y;
+    const long kb = (long)blockIdx.y * blockDim.x + threadIdx.x;       // 16-element block index along k
+    const long r = blockIdx.x;                                          // (rows in x: more than 65 535 of them at n = 65 536)
     if (kb * 16 >= Kp) return;
     const long k0 = kb * 16;
     if (tri == 2 && k0 + 16 <= (r / 128) * 128) return;                 // never loaded
-    const double sc = oz_scale((r < R) ? exps[r] : 0);
+    const int e = (r < R) ? exps[r] : 0;
     const double* row = X + r * ld;
     double x[16];
     if (r < R && k0 + 16 <= K && (tri != 2 || k0 >= r)) {
@@ -334,7 +343,7 @@ __global__ void __launch_bounds__(256) oz_slice_k_kernel(const double* __restric
     }
     union { int8_t b[NS][16]; uint4 v[NS]; } out;
 #pragma unroll
-    for (int i = 0; i < 16; i++) oz_split<NS>(x[i] * sc, [&](int s, int8_t b) { out.b[s][i] = b; });
+    for (int i = 0; i < 16; i++) oz_split<NS>(x[i], e, [&](int s, int8_t b) { out.b[s][i] = b; });
 #pragma unroll
     for (int s = 0; s < NS; s++) *reinterpret_cast<uint4*>(slices + (size_t)s * Rp * Kp + (size_t)r * Kp + k0) = out.v[s];
 }
@@ -379,14 +388,12 @@ struct OzArgs {
     double* C; long ldc;                // column-major output
     long M, N;                          // logical sizes (rows beyond them exist, zero, inside the slices)
     int nk;                             // k-chunks of OZ_KC in the sliced operands
+    int kc_lo, kc_hi;                   // this launch covers the chunks [kc_lo, kc_hi) (deep products are split along K)
     int kmode;                          // OZ_KLO_* / OZ_KHI_* bits: the k-range of a tile
     const int2* tiles; int ntiles;      // (tm, tn) of every tile in processing order (oz_tile_list)
     int* ticket;                        // zeroed before the launch
     double alpha, beta;
 };
-
-// 2^e as a double for -1022 <= e <= 1023
-__device__ __forceinline__ double oz_pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
 
 constexpr int OZ_THREADS = 192;     // warps 0-3: epilogue (TMEM lanes 32 w ..), warp 4: TMA producer, warp 5: MMA issuer
 
@@ -423,8 +430,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
     const uint32_t tmem = tmem_base_s;
     // k-chunk range of a tile
     auto krange = [&](int tm, int tn, int& kc0, int& kc1) {
-        kc0 = 0; kc1 = a.nk;
-        if (a.kmode & OZ_KLO_TM) kc0 = tm * (OZ_M / OZ_KC);
+        kc0 = a.kc_lo; kc1 = a.kc_hi;
+        if (a.kmode & OZ_KLO_TM) kc0 = max(kc0, tm * (OZ_M / OZ_KC));
         if (a.kmode & OZ_KLO_TN) kc0 = max(kc0, tn * (OZ_N / OZ_KC));
         if (a.kmode & OZ_KHI_TM) kc1 = min(kc1, (tm + 1) * (OZ_M / OZ_KC));
         if (a.kmode & OZ_KHI_TN) kc1 = min(kc1, (tn + 1) * (OZ_N / OZ_KC));
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                 s_eb[tid] = (n < a.N) ? a.eb[n] : 0;
             }
             const long m = (long)tm * OZ_M + 32 * warp + lane;
-            const int eam = ((m < a.M) ? a.ea[m] : 0) - 6;
+            const int eam = ((m < a.M) ? a.ea[m] : 0) - 7;
             asm volatile("bar.sync 1, 128;" ::: "memory");           // s_eb visible to the four epilogue warps
             mbar_wait(&tmem_full, nt & 1u);
             tc_fence_after();
@@ -538,7 +545,7 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                     for (int d = NS - 1; d >= 0; d--) {           // smallest contributions first
                         uint32_t v[32];
                         tmem_ld32(tmem + ((uint32_t)(32 * warp) << 16) + d * OZ_N + half * 32, v);
-                        const double w = oz_pow2(-7 * d);
+                        const double w = oz_pow2(-8 * d);
 #pragma unroll
                         for (int i = 0; i < 32; i++) acc[i] = fma((double)(int32_t)v[i], w, acc[i]);
                     }
@@ -547,13 +554,13 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                     tc_fence_before();
                     mbar_arrive(&tmem_empty);
                 }
-                if (m < a.M) {
+                if (m < a.M && !(empty && a.beta == 1.0)) {       // (a later k-block of a tile whose range ended earlier: nothing to add)
 #pragma unroll
                     for (int i = 0; i < 32; i++) {
                         const long n = (long)tn * OZ_N + half * 32 + i;
                         if (n < a.N) {
-                            // alpha acc 2^(ea + eb - 12) as two exact scalings, the smaller exponent first (no spurious overflow)
-                            const int eb6 = s_eb[half * 32 + i] - 6;
+                            // alpha acc 2^(ea + eb - 14) as two exact scalings, the smaller exponent first (no spurious overflow)
+                            const int eb6 = s_eb[half * 32 + i] - 7;
                             const double val = a.alpha * ((acc[i] * oz_pow2(min(eam, eb6))) * oz_pow2(max(eam, eb6)));
                             double* cp = a.C + m + n * a.ldc;
                             *cp = (a.beta == 0.0) ? val : fma(a.beta, *cp, val);
@@ -677,7 +684,7 @@ int oz_slice_t(Ctx& c, const double* X, long ld, long R, long K, int layout, int
         count_launch(3);
     } else {
         oz_rowexp_k_kernel<<<(unsigned)((o.Rp + 7) / 8), 256, 0, c.stream>>>(X, ld, R, o.Rp, K, tri, o.ex);
-        oz_slice_k_kernel<NS><<<dim3((unsigned)((o.Kp / 16 + 255) / 256), (unsigned)o.Rp), 256, 0, c.stream>>>(X, ld, R, K, tri, o.ex, o.sl, o.Rp, o.Kp);
+        oz_slice_k_kernel<NS><<<dim3((unsigned)o.Rp, (unsigned)((o.Kp / 16 + 255) / 256)), 256, 0, c.stream>>>(X, ld, R, K, tri, o.ex, o.sl, o.Rp, o.Kp);
         count_launch(2);
     }
     SGP_CUDA(cudaGetLastError());
@@ -705,17 +712,16 @@ OzSliced ozaki_carve(void* buf, long R, long K, int ns)
     return o;
 }
 
-static int oz_check_ns(int ns, long K)
+static int oz_check_ns(int ns)
 {
     if (ns < 4 || ns > 8) { set_error("ozaki: 4..8 slices per operand, got %d", ns); return ST_BADARG; }
-    if ((long)ns * K * 4096 >= 2147483647L) { set_error("ozaki: K = %ld too deep for exact INT32 accumulation with %d slices", K, ns); return ST_BADARG; }
     return ST_OK;
 }
 
 int ozaki_slice(Ctx& c, int ns, const double* X, long ld, long R, long K, int layout, int tri, const OzSliced& out)
 {
-    SGP_TRY(oz_check_ns(ns, K));
-    if (R <= 0 || K <= 0 || (layout != OZ_MN && layout != OZ_K) || (layout == OZ_MN && tri == 2) || (layout == OZ_K && tri == 1) || (ld & 1)) {
+    SGP_TRY(oz_check_ns(ns));
+    if (R <= 0 || K <= 0 || (layout != OZ_MN && layout != OZ_K) || (layout == OZ_MN && tri == 2) || (layout == OZ_K && tri == 1) || (layout == OZ_K && ((ld & 1) || ((uintptr_t)X & 15)))) {
         set_error("ozaki_slice: bad arguments"); return ST_BADARG;
     }
     switch (ns) {
@@ -730,25 +736,38 @@ int ozaki_slice(Ctx& c, int ns, const double* X, long ld, long R, long K, int la
 int ozaki_gemm_sliced(Ctx& c, int ns, const OzSliced& A, const OzSliced& B, long M, long N, double alpha, double beta, double* C, long ldc,
                       int kmode, int lower)
 {
-    SGP_TRY(oz_check_ns(ns, A.Kp));
+    SGP_TRY(oz_check_ns(ns));
     if (M <= 0 || N <= 0 || A.Kp != B.Kp || M > A.Rp || N > B.Rp) { set_error("ozaki_gemm_sliced: operand shapes do not match"); return ST_BADARG; }
     CUtensorMap tmA, tmB;
     SGP_TRY(make_slice_tmap(&tmA, A.sl, A.Rp, A.Kp, ns, OZ_M));
     SGP_TRY(make_slice_tmap(&tmB, B.sl, B.Rp, B.Kp, ns, OZ_N));
     OzArgs a;
     a.ea = A.ex; a.eb = B.ex; a.C = C; a.ldc = ldc; a.M = M; a.N = N;
-    a.nk = (int)(A.Kp / OZ_KC); a.kmode = kmode; a.alpha = alpha; a.beta = beta;
+    a.nk = (int)(A.Kp / OZ_KC); a.kmode = kmode; a.alpha = alpha;
     const int mt = (int)((M + OZ_M - 1) / OZ_M), nt = (int)((N + OZ_N - 1) / OZ_N);
     const int order = (kmode & OZ_KHI_TM) ? 1 : (kmode & OZ_KLO_TN) ? 2 : (kmode & OZ_KHI_TN) ? 3 : 0;
     SGP_TRY(oz_tile_list(c, mt, nt, lower, order, &a.tiles, &a.ntiles));
-    SGP_TRY(oz_ticket(c, &a.ticket));
-    switch (ns) {
-    case 4: return oz_launch<4>(c, tmA, tmB, a);
-    case 5: return oz_launch<5>(c, tmA, tmB, a);
-    case 6: return oz_launch<6>(c, tmA, tmB, a);
-    case 7: return oz_launch<7>(c, tmA, tmB, a);
-    default: return oz_launch<8>(c, tmA, tmB, a);
+    // exact INT32 accumulation: at most ns pairs of |digit products| <= 2^14 per k and accumulator -> k-blocks of
+    // <= (2^31 - 1) / (ns 2^14) per launch, the blocks added in FP64 (beta = 1 after the first)
+    const int kmax = (int)((2147483647L / ((long)ns * 16384L)) / OZ_KC);          // in chunks
+    // The limit is on the depth a TILE accumulates, so the blocks are counted from the side its k-range is anchored at: from
+    // the end for the k >= ... modes (lauum: only the long rows of the triangle take part in a second launch).
+    const int nblk = (a.nk + kmax - 1) / kmax, per = (a.nk + nblk - 1) / nblk;
+    const bool from_end = (kmode & (OZ_KLO_TM | OZ_KLO_TN)) && !(kmode & (OZ_KHI_TM | OZ_KHI_TN));
+    for (int b = 0; b < nblk; b++) {
+        if (from_end) { a.kc_hi = a.nk - b * per; a.kc_lo = a.nk - (b + 1) * per > 0 ? a.nk - (b + 1) * per : 0; }
+        else { a.kc_lo = b * per; a.kc_hi = (b + 1) * per < a.nk ? (b + 1) * per : a.nk; }
+        a.beta = b == 0 ? beta : 1.0;
+        SGP_TRY(oz_ticket(c, &a.ticket));
+        switch (ns) {
+        case 4: SGP_TRY(oz_launch<4>(c, tmA, tmB, a)); break;
+        case 5: SGP_TRY(oz_launch<5>(c, tmA, tmB, a)); break;
+        case 6: SGP_TRY(oz_launch<6>(c, tmA, tmB, a)); break;
+        case 7: SGP_TRY(oz_launch<7>(c, tmA, tmB, a)); break;
+        default: SGP_TRY(oz_launch<8>(c, tmA, tmB, a)); break;
+        }
     }
+    return ST_OK;
 }
 
 size_t ozaki_workspace_bytes(long M, long N, long K, int ns)
@@ -759,7 +778,7 @@ size_t ozaki_workspace_bytes(long M, long N, long K, int ns)
 static int oz_check(int ns, long M, long N, long K, size_t work_bytes)
 {
     if (M <= 0 || N <= 0 || K <= 0) { set_error("ozaki_gemm: bad arguments"); return ST_BADARG; }
-    SGP_TRY(oz_check_ns(ns, K));
+    SGP_TRY(oz_check_ns(ns));
     if (work_bytes < ozaki_workspace_bytes(M, N, K, ns)) { set_error("ozaki_gemm: workspace too small"); return ST_BADARG; }
     return ST_OK;
 }
@@ -791,7 +810,7 @@ size_t ozaki_lauum_workspace_bytes(long n_pad, int ns) { return ozaki_sliced_byt
 int ozaki_lauum(Ctx& c, int ns, const double* X, long n_pad, long ldx, double* W, long ldw, void* work, size_t work_bytes)
 {
     if (n_pad <= 0 || n_pad % OZ_M) { set_error("ozaki_lauum: bad arguments"); return ST_BADARG; }
-    SGP_TRY(oz_check_ns(ns, n_pad));
+    SGP_TRY(oz_check_ns(ns));
     if (work_bytes < ozaki_lauum_workspace_bytes(n_pad, ns)) { set_error("ozaki_lauum: workspace too small"); return ST_BADARG; }
     const OzSliced S = ozaki_carve(work, n_pad, n_pad, ns);
     SGP_TRY(ozaki_slice(c, ns, X, ldx, n_pad, n_pad, OZ_K, 2, S));
@@ -799,7 +818,7 @@ int ozaki_lauum(Ctx& c, int ns, const double* X, long n_pad, long ldx, double* W
 }
 
 // C (M x N, column-major, ldc) = alpha A B^T + beta C with A (M x K) and B (N x K) given as element (r, k) at ptr[r + k ld];
-// ns = 4..8 slices per operand (7: ~2^-49 of the row / column scales; 8: ~2^-56).  ns K 4096 < 2^31 (INT32 headroom).
+// ns = 4..8 digits per operand (6: 2^-47 of the row scales; 7: 2^-55).
 int ozaki_gemm(Ctx& c, int ns, long M, long N, long K, double alpha, const double* A, long lda, const double* B, long ldb, double beta,
                double* C, long ldc, void* work, size_t work_bytes)
 {

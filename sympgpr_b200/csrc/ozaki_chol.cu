@@ -96,7 +96,7 @@ size_t ozaki_factinv_workspace_bytes(long n_pad, int ns)
 static int oz_chol_check(const char* who, int ns, long leaf_n, long n_pad, long lda, size_t work_bytes)
 {
     if (n_pad <= 0 || n_pad % TILE || (lda & 1) || leaf_n < TILE) { set_error("%s: bad arguments", who); return ST_BADARG; }
-    if (ns < 4 || ns > 8 || (long)ns * n_pad * 4096 >= 2147483647L) { set_error("%s: %d slices at order %ld: no exact INT32 accumulation", who, ns, n_pad); return ST_BADARG; }
+    if (ns < 4 || ns > 8) { set_error("%s: 4..8 slices, got %d", who, ns); return ST_BADARG; }
     if (work_bytes < ozaki_factinv_workspace_bytes(n_pad, ns)) { set_error("%s: workspace too small", who); return ST_BADARG; }
     return ST_OK;
 }

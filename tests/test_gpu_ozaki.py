@@ -142,12 +142,12 @@ def _lower_with_garbage(rng, n, scale_rows=False):
 
 
 def _bound(A, B, ns):
-    """A-priori error bound of the sliced product, elementwise: the slice pairs with s + t >= ns are dropped, each at most
-    64 x 64 x 2^(-7 (s + t)) x 2^(ea + eb - 12) per k with 2^ea <= 2 max_k |a|, plus the final FP64 roundings of the ns-term
+    """A-priori error bound of the sliced product, elementwise: the digit pairs with s + t >= ns are dropped, each at most
+    128 x 128 x 2^(-8 (s + t)) x 2^(ea + eb - 14) per k with 2^ea <= 2.01 max_k |a|, plus the final FP64 roundings of the ns-term
     sum: it is relative to the ROW MAXIMA of the operands (the Ozaki scheme scales rows), not to sum |a||b|."""
     K = A.shape[1]
-    dropped = sum((2 * ns - 1 - d) * 2.0 ** (-7 * d) for d in range(ns, 2 * ns - 1))
-    return (4.0 * dropped * K) * np.outer(np.abs(A).max(axis=1), np.abs(B).max(axis=1)) + 5e-15 * (np.abs(A) @ np.abs(B).T)
+    dropped = sum((2 * ns - 1 - d) * 2.0 ** (-8 * d) for d in range(ns, 2 * ns - 1))
+    return (4.1 * dropped * K) * np.outer(np.abs(A).max(axis=1), np.abs(B).max(axis=1)) + 5e-15 * (np.abs(A) @ np.abs(B).T)
 
 
 def _check(C, A, B, sign=1.0, mask=None):
@@ -160,7 +160,7 @@ def _check(C, A, B, sign=1.0, mask=None):
     return float(r.max())
 
 
-@pytest.mark.parametrize("ns", [7, 8])
+@pytest.mark.parametrize("ns", [5, 6, 7, 8])
 @pytest.mark.parametrize("h1,h2", [(128, 128), (384, 256), (256, 640)])
 def test_sliced_products_of_the_recursion(api, ns, h1, h2):
     """Steps 2, 3, 4 and 6 of ozaki_chol.cu's node and the lauum product, with the k-ranges, storage orders and triangular
@@ -204,7 +204,7 @@ def ozaki_all():
     ctx.set_ozaki_ex(0, 1, 0)
 
 
-@pytest.mark.parametrize("ns,leaf", [(7, 128), (8, 256), (7, 512)])
+@pytest.mark.parametrize("ns,leaf", [(6, 128), (7, 256), (8, 512)])
 @pytest.mark.parametrize("n", [700, 1536])
 def test_spd_inverse_and_logdet_on_the_int8_route(api, ozaki_all, n, ns, leaf):
     """sgp_spd_factor with factor + triangular inverse + lauum all on the INT8 pipe (leaves of `leaf` rows on DMMA): inverse
@@ -225,14 +225,13 @@ def test_spd_inverse_and_logdet_on_the_int8_route(api, ozaki_all, n, ns, leaf):
     r = np.abs(A @ Ai - np.eye(n)).max()             # the residual does not depend on the comparison inverse
     r0 = np.abs(A @ Ai0 - np.eye(n)).max()
     print(f"\nn={n} ns={ns} leaf={leaf}: max|Ainv - ref| / max|ref| = {e:.2e} (DMMA route {e0:.2e}); |A Ainv - I| = {r:.2e} ({r0:.2e})")
-    # 7 slices keep 49 bits of every row's scale against the 53 of FP64 (measured ~100x the DMMA route's error at this
-    # condition number); 8 slices keep 56 and must match it
-    slack = 400.0 if ns == 7 else 8.0
+    # 6 digits keep 47 bits of every row's scale against the 53 of FP64; 7 and 8 keep 55 and 63 and must match the DMMA route
+    slack = 3000.0 if ns == 6 else 8.0
     assert e < slack * e0, (e, e0)
     assert r < slack * r0, (r, r0)
 
 
-@pytest.mark.parametrize("ns,leaf", [(7, 256), (8, 512)])
+@pytest.mark.parametrize("ns,leaf", [(6, 256), (7, 256), (8, 512)])
 @pytest.mark.parametrize("N", [600, 1024])
 def test_nll_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all, N, ns, leaf):
     """NLL + gradient with potrf, trtri and lauum replaced by the INT8 recursion + INT8 lauum, judged on the SAME oracle
@@ -247,7 +246,7 @@ def test_nll_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all, N, ns, le
     assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr)
 
 
-@pytest.mark.parametrize("ns,leaf", [(7, 128), (7, 256), (8, 384)])
+@pytest.mark.parametrize("ns,leaf", [(6, 128), (7, 256), (8, 384)])
 @pytest.mark.parametrize("N", [600, 1024, 1600])
 def test_nll_value_on_the_factor_only_int8_recursion(api, ozaki_all, N, ns, leaf):
     """nll_chol (value only: the objective of the scripts' L-BFGS loops) through the factor-only variant of the INT8 recursion --
@@ -280,9 +279,11 @@ def test_int8_route_reports_a_matrix_that_is_not_positive_definite(api, ozaki_al
         api.spd_factor(A, want_factor=False, want_inverse=True)
 
 
-def test_full_size_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all):
-    """BASELINE's headline size (N = 16 384, n = 32 768): all three stages on the INT8 pipe (7 slices, leaves of 4096) against
-    the CPU golden (tests/golden/fullsize_nll_N16384.json), 1e-9 as for the DMMA path."""
+@pytest.mark.parametrize("ns", [6, 7])
+def test_full_size_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all, ns):
+    """BASELINE's headline size (N = 16 384, n = 32 768): all three stages on the INT8 pipe (6 digits = what bench.py times, and 7;
+    leaves of 4096) against the CPU golden (tests/golden/fullsize_nll_N16384.json), 1e-9 as for the DMMA path; the value-only
+    evaluation (factor-only recursion) likewise."""
     import json
     import os
     from oracle import oracle as O
@@ -290,9 +291,35 @@ def test_full_size_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all):
     N = g["N"]
     d = O.standard_map_training(N)
     hyp = O.timing_hyp(N, d["sig"], 1e-8)
-    ozaki_all.set_ozaki_ex(7, 3, 4096)
+    ozaki_all.set_ozaki_ex(ns, 3, 4096)
     v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
-    print(f"\nfull size, INT8 route: nll rel err {abs(v - g['nll']) / abs(g['nll']):.2e}, grad rel err "
-          f"{np.max(np.abs(np.asarray(gr) - np.asarray(g['grad'])) / np.abs(g['grad'])):.2e}")
+    v1 = api.nll_chol(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    print(f"\nfull size, INT8 route, {ns} digits: nll rel err {abs(v - g['nll']) / abs(g['nll']):.2e} (value-only {abs(v1 - g['nll']) / abs(g['nll']):.2e}), "
+          f"grad rel err {np.max(np.abs(np.asarray(gr) - np.asarray(g['grad'])) / np.abs(g['grad'])):.2e}")
     assert abs(v - g["nll"]) <= 1e-9 * abs(g["nll"])
+    assert abs(v1 - g["nll"]) <= 1e-9 * abs(g["nll"])
     assert np.allclose(gr, g["grad"], rtol=1e-9, atol=1e-9 * np.abs(g["grad"]).max()), (gr, g["grad"])
+
+
+def test_ill_conditioned_map_model_on_the_int8_route(api, ozaki_all):
+    """The map models of scripts 03/04/05 are fitted with length scales twice those of the timing workload: cond(K) ~ 1e10, where
+    FP64 itself only holds ~1e-7 of the gradient.  8 digits (63 bits of every row's scale) must stay within a small factor of
+    the DMMA route's own distance to the oracle; the distances of 6 and 7 digits are printed for the record."""
+    from oracle import oracle as O
+    N = 768
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    hyp[:2] *= 2.0
+    vr, gr = O.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    v0, g0 = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    dist = lambda v, g: (abs(v - vr) / abs(vr), float(np.max(np.abs(np.asarray(g) - gr) / np.abs(gr))))
+    e0 = dist(v0, g0)
+    rows = {}
+    for ns in (6, 7, 8):
+        ozaki_all.set_ozaki_ex(ns, 3, 256)
+        v, g = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+        rows[ns] = dist(v, g)
+    print(f"\ncond 1e10 model, N={N}: distance to the oracle (nll, grad): DMMA {e0[0]:.1e} {e0[1]:.1e}; "
+          + "; ".join(f"{ns} digits {e[0]:.1e} {e[1]:.1e}" for ns, e in rows.items()))
+    assert rows[8][0] <= max(5.0 * e0[0], 1e-9) and rows[8][1] <= max(5.0 * e0[1], 1e-9), (rows, e0)
+    assert rows[7][0] <= max(50.0 * e0[0], 1e-9) and rows[7][1] <= max(50.0 * e0[1], 1e-9), (rows, e0)

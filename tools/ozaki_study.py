@@ -29,6 +29,35 @@ def split(M, s, bits, axis):
     return slices, e
 
 
+def split256(M, s):
+    """The scheme csrc/ozaki.cu runs since round-2 state "j": s balanced radix-256 digits of the row-scaled mantissa
+    (v = rint(x 2^(8 s - 1 - e)); signed bytes from the bottom with a carry); returned most significant first."""
+    mx = np.max(np.abs(M), axis=1, keepdims=True)
+    f, e = np.frexp(np.where(mx > 0, mx, 1.0))
+    e = e + (f >= 0.995)
+    v = np.rint(np.ldexp(M, (8 * s - 1 - e).astype(np.int64) if s <= 6 else (8 * s - 1 - e).astype(np.int64)))
+    v = v.astype(object) if s > 7 else v.astype(np.int64)      # 63 bits: beyond float64-exact int64 conversion only in the last bits
+    v = np.array(v, dtype=object)
+    digits = []
+    for _ in range(s):
+        dgt = np.vectorize(lambda t: ((int(t) + 128) % 256) - 128, otypes=[object])(v)
+        digits.append(np.array(dgt, dtype=np.int64))
+        v = (v - dgt) // 256
+    return digits[::-1], e
+
+
+def ozaki256_gemm_nt(A, B, s):
+    As, ea = split256(A, s)
+    Bs, eb = split256(B, s)
+    C = np.zeros((A.shape[0], B.shape[0]))
+    for dcls in range(s - 1, -1, -1):                # smallest contributions first
+        acc = np.zeros((A.shape[0], B.shape[0]), dtype=np.int64)
+        for p in range(dcls + 1):
+            acc += As[p] @ Bs[dcls - p].T
+        C += acc.astype(np.float64) * 2.0**(-8 * dcls)
+    return C * 2.0**(ea - 7) * 2.0**(eb - 7).T
+
+
 def ozaki_gemm_nt(A, B, s, bits):
     """A (m,k) @ B(n,k)^T with both operands cut into s slices."""
     As, ea = split(A, s, bits, 1)
@@ -82,3 +111,11 @@ if __name__ == "__main__":
             except np.linalg.LinAlgError:
                 errs.append(float("nan"))
         print(f"{name:26s} {cond:9.2e}   " + "  ".join(f"{e:8.1e}" for e in errs))
+        errs = []
+        for sdig in (5, 6, 7, 8):
+            try:
+                v = nll_of(blocked_cholesky(K, 128, lambda A, B: ozaki256_gemm_nt(A, B, sdig)), z)
+                errs.append(abs(v - ref) / abs(ref))
+            except np.linalg.LinAlgError:
+                errs.append(float("nan"))
+        print(f"{'  radix-256 digits 5,6,7,8':26s} {'':9s}   " + "  ".join(f"{e:8.1e}" for e in errs))

@@ -274,6 +274,9 @@ int sgp_ozaki_gemm_host(sgp_ctx* ctx, int ns, long M, long N, long K, double alp
                         long ldb, double beta, double* C, long ldc);
 /* timing on random device operands: ms2[0] = slicing + GEMM per call, ms2[1] = the tensor-pipe GEMM alone (operands sliced) */
 int sgp_ozaki_bench(sgp_ctx* ctx, int ns, long M, long N, long K, int reps, double* ms2);
+/* vector FP64 ceiling: a register-resident DFMA loop on every SM; *dp_instr_per_s = thread-level DFMA instructions per second
+ * (what the map kernels' FP64-pipe roofline is measured against) */
+int sgp_bench_dfma(sgp_ctx* ctx, int reps, double* dp_instr_per_s);
 /* DMMA GEMM timing: `reps` launches on random operands (alpha = -1, beta = 1), average ms per launch */
 int sgp_bench_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, int reps, double* ms_avg);
 /* timing hooks for bench.py (device pointers, async): the individual stages of one evaluation */

@@ -80,6 +80,7 @@ _PROTOS = {
     "sgp_spd_factor": (c_i, [c_vp, c_dp, c_l, c_dp, c_dp, c_dp]),
     "sgp_selftest_gemm": (c_i, [c_vp, c_i, c_i, c_i, c_i, c_i, c_i, c_dp]),
     "sgp_i8mma_selftest": (c_i, [c_vp, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
+    "sgp_bench_dfma": (c_i, [c_vp, c_i, c_dp]),
     "sgp_set_ozaki": (c_i, [c_vp, c_i]),
     "sgp_set_ozaki_ex": (c_i, [c_vp, c_i, c_i, c_l]),
     "sgp_ozaki_gemm_host_ex": (c_i, [c_vp, c_i, c_l, c_l, c_l, c_d, c_dp, c_l, c_i, c_i, c_dp, c_l, c_i, c_i, c_d, c_dp, c_l, c_i, c_i]),

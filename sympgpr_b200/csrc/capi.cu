@@ -1173,6 +1173,47 @@ int sgp_ozaki_bench(sgp_ctx* ctx, int ns, long M, long N, long K, int reps, doub
     return ST_OK;
 }
 
+// Register-resident DFMA loop: the vector FP64 ceiling the map kernels are judged against ("a register-resident
+// DFMA loop (vector ceiling)", measured in the same run as the result).  8 independent chains per thread, 2048 threads per SM.
+__global__ void __launch_bounds__(256) dfma_probe_kernel(double* __restrict__ out, int iters, double a, double b)
+{
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    const double s = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (s == 123.456) out[blockIdx.x] = s;          // never true for the arguments used: keeps the chains alive
+}
+
+int sgp_bench_dfma(sgp_ctx* ctx, int reps, double* dp_instr_per_s)
+{
+    SGP_TRY(check_ctx(ctx));
+    Ctx& c = ctx->c;
+    if (reps <= 0 || !dp_instr_per_s) { set_error("bench_dfma: bad arguments"); return ST_BADARG; }
+    SGP_TRY(c.io.reserve(1 << 20));
+    const int sms = c.sm_count > 0 ? c.sm_count : 148;
+    const int blocks = sms * 8, iters = 4096;
+    dfma_probe_kernel<<<blocks, 256, 0, c.stream>>>(c.io.as<double>(), 64, 0.999999, 1e-9);        // warm-up
+    cudaEvent_t e0, e1;
+    SGP_CUDA(cudaEventCreate(&e0));
+    SGP_CUDA(cudaEventCreate(&e1));
+    SGP_CUDA(cudaEventRecord(e0, c.stream));
+    for (int r = 0; r < reps; r++) dfma_probe_kernel<<<blocks, 256, 0, c.stream>>>(c.io.as<double>(), iters, 0.999999, 1e-9);
+    SGP_CUDA(cudaEventRecord(e1, c.stream));
+    SGP_CUDA(cudaEventSynchronize(e1));
+    SGP_CUDA(cudaGetLastError());
+    count_launch((unsigned long long)reps + 1);
+    float ms = 0.f;
+    SGP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *dp_instr_per_s = (double)reps * blocks * 256.0 * iters * 64.0 / (ms * 1e-3);
+    return ST_OK;
+}
+
 int sgp_bench_gemm(sgp_ctx* ctx, int al, int bl, int mode, int Mt, int Nt, int K, int reps, double* ms_avg)
 {
     SGP_TRY(check_ctx(ctx));

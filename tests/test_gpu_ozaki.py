@@ -244,6 +244,14 @@ def test_nll_gradient_with_all_stages_on_the_int8_pipe(api, ozaki_all, N, ns, le
     v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
     assert np.isclose(v, vr, rtol=1e-9), (v, vr)
     assert np.allclose(gr, grr, rtol=1e-9, atol=1e-9 * np.abs(grr).max()), (gr, grr)
+    if N == 600:
+        # model finalisation (sgp_fit: alpha and Kyinv) on the same route against the DMMA route
+        f = api.fit(hyp, d["xtrain"], d["ztrain"], 2 * N, want_inverse=True)
+        ozaki_all.set_ozaki_ex(0, 1, 0)
+        f0 = api.fit(hyp, d["xtrain"], d["ztrain"], 2 * N, want_inverse=True)
+        tol = 1e-6 if ns == 6 else 1e-9
+        assert np.allclose(f["alpha"], f0["alpha"], rtol=tol, atol=tol * np.abs(f0["alpha"]).max())
+        assert np.allclose(f["Kyinv"], f0["Kyinv"], rtol=tol, atol=tol * np.abs(f0["Kyinv"]).max())
 
 
 @pytest.mark.parametrize("ns,leaf", [(6, 128), (7, 256), (8, 384)])

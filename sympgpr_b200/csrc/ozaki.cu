@@ -60,6 +60,24 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
         : "memory");
 }
+// the same with the A operand kept in the tensor core's collector buffer for the next MMA (KEEP = 1: fill and keep) or taken
+// from it (KEEP = 2: last use): two MMAs that share A read it from shared memory once (SASS UTCIMMA .A_KEEP / .A_REUSE)
+template <int KEEP>
+__device__ __forceinline__ void umma_i8_a(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    if (KEEP == 1)
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8.collector::a::fill [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+            : "memory");
+    else
+        asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8.collector::a::lastuse [%0], %1, %2, %3, {%5, %6, %7, %8}, p;\n}\n" ::"r"(tmem_d),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u), "r"(0u), "r"(0u), "r"(0u)
+            : "memory");
+}
 // all MMAs issued so far by this thread -> one arrival on the mbarrier when they have completed
 __device__ __forceinline__ void umma_commit(unsigned long long* bar)
 {
@@ -497,13 +515,18 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
                         mbar_wait(&fullA[st * NS + s], ph);
                         tc_fence_after();
 #pragma unroll
-                        for (int c0 = 0; c0 < (NS - s) * OZ_N; c0 += 256) {
-                            const int nn = ((NS - s) * OZ_N - c0 < 256) ? (NS - s) * OZ_N - c0 : 256;
-                            const uint32_t idesc = umma_idesc_i8(OZ_M, nn);
-#pragma unroll
-                            for (int ks = 0; ks < OZ_KC / 32; ks++)
-                                umma_i8(tmem + s * OZ_N + c0, umma_desc_k64(sA + s * A_BYTES + ks * 32),
-                                        umma_desc_k64(sB + (c0 / OZ_N) * B_BYTES + ks * 32), idesc, (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u);
+                        for (int ks = 0; ks < OZ_KC / 32; ks++) {
+                            const uint64_t adesc = umma_desc_k64(sA + s * A_BYTES + ks * 32);
+                            const uint32_t accf = (kc > kc0 || ks > 0 || s > 0) ? 1u : 0u;
+                            const int ncols = (NS - s) * OZ_N;
+                            if (ncols > 256) {
+                                // two MMAs share A_s: the first keeps it in the collector buffer, the second takes it from there
+                                umma_i8_a<1>(tmem + s * OZ_N, adesc, umma_desc_k64(sB + ks * 32), umma_idesc_i8(OZ_M, 256), accf);
+                                umma_i8_a<2>(tmem + s * OZ_N + 256, adesc, umma_desc_k64(sB + 4 * B_BYTES + ks * 32),
+                                             umma_idesc_i8(OZ_M, ncols - 256), accf);
+                            } else {
+                                umma_i8(tmem + s * OZ_N, adesc, umma_desc_k64(sB + ks * 32), umma_idesc_i8(OZ_M, ncols), accf);
+                            }
                         }
                         umma_commit(&emptyA[st * NS + s]);   // this A slot is free once the MMAs issued so far have read it
                     }

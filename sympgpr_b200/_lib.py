@@ -197,8 +197,8 @@ def context(device=None):
         oz = os.environ.get("SYMPGPR_B200_OZAKI")
         if oz:
             # "slices[:stages[:leaf_rows]]", e.g. 7:3 -- the opt-in INT8 route for scripts that run unchanged
-            f = [int(v) for v in oz.split(":")] + [3, 0]
-            ctx.set_ozaki_ex(f[0], f[1], f[2])
+            f = [int(v) for v in oz.split(":")]
+            ctx.set_ozaki_ex(f[0], f[1] if len(f) > 1 else 3, f[2] if len(f) > 2 else 0)
         with _lock:
             _ctx.setdefault(dev, ctx)
             ctx = _ctx[dev]

@@ -331,3 +331,35 @@ def test_ill_conditioned_map_model_on_the_int8_route(api, ozaki_all):
           + "; ".join(f"{ns} digits {e[0]:.1e} {e[1]:.1e}" for ns, e in rows.items()))
     assert rows[8][0] <= max(5.0 * e0[0], 1e-9) and rows[8][1] <= max(5.0 * e0[1], 1e-9), (rows, e0)
     assert rows[7][0] <= max(50.0 * e0[0], 1e-9) and rows[7][1] <= max(50.0 * e0[1], 1e-9), (rows, e0)
+
+
+def test_env_switch_selects_the_int8_route_for_unchanged_scripts(api):
+    """SYMPGPR_B200_OZAKI=digits:stages:leaf in the environment of a process that never mentions the route (what a reference script
+    run through sympgpr_b200.runner is): the default context takes the INT8 route -- the potrf stage disappears from the stage
+    times (factor and inverse run as one recursion) -- and the results agree with the DMMA route of this process."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from oracle import oracle as O
+    N = 600
+    code = (
+        "import ctypes, json, sys\n"
+        "sys.path.insert(0, '.')\n"
+        "from oracle import oracle as O\n"
+        "from sympgpr_b200 import _lib, api\n"
+        f"d = O.standard_map_training({N}); hyp = O.timing_hyp({N}, d['sig'], 1e-8)\n"
+        "ctx = _lib.context(); _lib.check(_lib.lib().sgp_set_profiling(ctx.handle, 1), 'prof')\n"
+        f"v, g = api.nll_grad(hyp, d['xtrain'], d['ztrain'], {2 * N})\n"
+        "st = (ctypes.c_double * 7)(); _lib.check(_lib.lib().sgp_stage_times(ctx.handle, st), 'st')\n"
+        "print(json.dumps({'v': v, 'g': [float(g[0]), float(g[1])], 'potrf_ms': st[1], 'trtri_ms': st[3]}))\n")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SYMPGPR_B200_OZAKI="7:3:256")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    r = json.loads(out.stdout.strip().splitlines()[-1])
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    v0, g0 = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    assert r["potrf_ms"] < 0.02 < r["trtri_ms"], r                      # potrf + trtri ran as one recursion, timed under trtri
+    assert np.isclose(r["v"], v0, rtol=1e-11) and np.allclose(r["g"], g0, rtol=1e-9)

@@ -363,3 +363,24 @@ def test_env_switch_selects_the_int8_route_for_unchanged_scripts(api):
     v0, g0 = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
     assert r["potrf_ms"] < 0.02 < r["trtri_ms"], r                      # potrf + trtri ran as one recursion, timed under trtri
     assert np.isclose(r["v"], v0, rtol=1e-11) and np.allclose(r["g"], g0, rtol=1e-9)
+
+
+def test_other_kernel_variants_on_the_int8_route(api, ozaki_all):
+    """The regression-kernel gradient (nll_grad_reg) and the 2-DOF 4 x 4-block kernel (reg = 4, BASELINE config 3) take the same
+    recursion: against the oracle at the tolerances of their DMMA tests."""
+    from oracle import oracle as O
+    N = 1024
+    d = O.standard_map_training(N)
+    hypp = O.timing_hyp(N, d["sigp"], 1e-8)
+    vr, gr = O.nll_grad_reg(hypp, d["xtrainp"], d["ztrainp"], N)
+    ozaki_all.set_ozaki_ex(7, 3, 256)
+    v, g = api.nll_grad_reg(hypp, d["xtrainp"], d["ztrainp"], N)
+    assert np.isclose(v, vr, rtol=1e-9), (v, vr)
+    assert np.allclose(g, gr, rtol=1e-9, atol=1e-9 * np.abs(gr).max()), (g, gr)
+    N2 = 200
+    x, z = O.henon_like_training(N2)
+    hyp = np.array([0.35, 0.4, 2 * np.max(np.abs(z))**2, 1e-4])          # cond(Ky) ~ 4e5
+    vr, gr = O.nll_grad4(hyp, x, z, 4 * N2, with_sig=True)
+    v, g = api.nll_grad4(hyp, x, z, 4 * N2, with_sig=True)
+    assert np.isclose(v, vr, rtol=1e-9), (v, vr)
+    assert np.allclose(g, gr, rtol=1e-8, atol=1e-8 * np.abs(gr).max()), (g, gr)

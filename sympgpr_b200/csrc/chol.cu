@@ -11,6 +11,7 @@
 // unchanged).  Only the lower triangle is referenced.
 #include "chol.cuh"
 
+#include <mutex>
 #include <utility>
 #include <vector>
 
@@ -349,6 +350,8 @@ int trtri(Ctx& c, double* A, long n_pad, long lda, const double* Dinv, double* T
     static TrtriPlan plans[NPLAN];
     static int plan_dev[NPLAN];
     static int next_plan = 0;
+    static std::mutex mu;                                 // contexts of several host threads share the cache
+    std::lock_guard<std::mutex> lock(mu);
     TrtriPlan* found = nullptr;
     for (int i = 0; i < NPLAN && !found; i++)
         if (plans[i].A == A && plans[i].lda == lda && plans[i].nt == nt && plans[i].T == T && plan_dev[i] == c.device) found = &plans[i];

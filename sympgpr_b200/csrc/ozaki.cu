@@ -24,6 +24,7 @@
 #include <float.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <vector>
 
 #include "mbar.cuh"
@@ -611,6 +612,8 @@ int oz_tile_list(Ctx& c, int mt, int nt, int lower, int order, const int2** d_ti
     constexpr int NLIST = 64;
     static OzTileList lists[NLIST];
     static int next = 0;
+    static std::mutex mu;                                 // contexts of several host threads share the cache
+    std::lock_guard<std::mutex> lock(mu);
     for (int i = 0; i < NLIST; i++) {
         OzTileList& L = lists[i];
         if (L.device == c.device && L.mt == mt && L.nt == nt && L.lower == lower && L.order == order && L.buf.p) {
@@ -648,10 +651,17 @@ int oz_tile_list(Ctx& c, int mt, int nt, int lower, int order, const int2** d_ti
 
 int oz_ticket(Ctx& c, int** ticket)
 {
+    // one ticket word per (device, stream slot): launches on ONE stream are ordered, so they may share a word; contexts on
+    // different streams of a device get different words (8 slots, hashed by the stream handle)
     static DBuf tickets[64];
+    static std::mutex mu;
     if (c.device < 0 || c.device >= 64) { set_error("ozaki: device index out of range"); return ST_BADARG; }
-    SGP_TRY(tickets[c.device].reserve(256));
-    *ticket = tickets[c.device].as<int>();
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        SGP_TRY(tickets[c.device].reserve(8 * 256));
+    }
+    const size_t slot = ((uintptr_t)c.stream >> 4) % 8;
+    *ticket = tickets[c.device].as<int>() + slot * 64;
     SGP_CUDA(cudaMemsetAsync(*ticket, 0, sizeof(int), c.stream));
     return ST_OK;
 }

@@ -1,6 +1,7 @@
 // extern "C" surface of libsympgpr_b200 (include/sympgpr_b200.h).
 #include "../../include/sympgpr_b200.h"
 
+#include <float.h>
 #include <new>
 #include <vector>
 
@@ -49,6 +50,63 @@ __global__ void embed_spd_kernel(const double* __restrict__ A, long n, double* _
         if (r < n && c < n) v = A[r + c * n];
         else if (r == c) v = 1.0;
         K[idx] = v;
+    }
+}
+
+// Symmetric equilibration by powers of two for the INT8 route of sgp_spd_factor (its digits are relative to the row maxima of
+// the operands, so a spread of scales along the diagonal would eat them): k_i = -round(log2(A_ii) / 2),
+// A^ = S A S with S = diag(2^k) -- exact scalings, undone exactly in the outputs (Ainv = S A^inv S, L = S^-1 L^,
+// log det L = log det L^ - ln 2 sum k).
+__global__ void equil_exponents_kernel(const double* __restrict__ A, long n, long n_pad, int* __restrict__ kexp)
+{
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    int k = 0;
+    if (i < n) {
+        const double d = A[i + i * n];
+        if (d > 0.0 && d <= DBL_MAX) {
+            int e;
+            frexp(d, &e);                                 // d = f 2^e, 0.5 <= f < 1
+            k = -(e / 2);
+        }
+    }
+    kexp[i] = k;
+}
+
+__global__ void embed_spd_scaled_kernel(const double* __restrict__ A, long n, double* __restrict__ K, long n_pad, const int* __restrict__ kexp)
+{
+    const long tot = n_pad * n_pad;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx % n_pad, c = idx / n_pad;
+        double v = 0.0;
+        if (r < n && c < n) v = scalbn(A[r + c * n], kexp[r] + kexp[c]);
+        else if (r == c) v = 1.0;
+        K[idx] = v;
+    }
+}
+
+// dst (n x n) from the lower triangle of src, entry (r, c) scaled by 2^(sr k_r + sc k_c); sym: symmetric completion
+__global__ void extract_scaled_kernel(const double* __restrict__ src, long lds, double* __restrict__ dst, long n, int sym,
+                                      const int* __restrict__ kexp, int sr, int sc)
+{
+    const long tot = n * n;
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < tot; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx % n, c = idx / n;
+        const double v = (r >= c) ? src[r + c * lds] : (sym ? src[c + r * lds] : 0.0);
+        dst[idx] = scalbn(v, sr * kexp[r] + sc * kexp[c]);
+    }
+}
+
+__global__ void sum_logs_scaled_kernel(const double* __restrict__ logparts, int nt, const int* __restrict__ info, const int* __restrict__ kexp,
+                                       long n, double* __restrict__ res)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double s = 0.0;
+        for (int k = 0; k < nt; k++) s += logparts[k];
+        long ks = 0;
+        for (long i = 0; i < n; i++) ks += kexp[i];
+        res[SGP_RES_LOGD] = s - 0.6931471805599453 * (double)ks;
+        res[SGP_RES_INFO] = (double)(*info);
     }
 }
 
@@ -960,12 +1018,21 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
     int* info = (int*)(logparts + nt);
     double* dres = logparts + nt + 2;
     SGP_TRY(upload(c, dA, A, (size_t)n * n));
-    embed_spd_kernel<<<1024, 256, 0, c.stream>>>(dA, n, K, n_pad);
+    // opt-in INT8 route (sgp_set_ozaki_ex, stages bit 1): factor and inverse factor in one recursion; it never holds L
+    const bool oz_ok = c.ozaki_slices > 0 && Ainv;
+    const bool oz_fact = oz_ok && (c.ozaki_stages & 2) && !L && n_pad > c.ozaki_leaf;
+    int* kexp = nullptr;
+    if (oz_ok) {
+        // an arbitrary SPD matrix may be badly scaled: equilibrate by powers of two (exact) before the digits are taken
+        SGP_TRY(c.vecs.reserve((size_t)4 * n_pad * sizeof(double)));
+        kexp = c.vecs.as<int>();
+        equil_exponents_kernel<<<(unsigned)((n_pad + 255) / 256), 256, 0, c.stream>>>(dA, n, n_pad, kexp);
+        embed_spd_scaled_kernel<<<1024, 256, 0, c.stream>>>(dA, n, K, n_pad, kexp);
+    } else {
+        embed_spd_kernel<<<1024, 256, 0, c.stream>>>(dA, n, K, n_pad);
+    }
     SGP_CUDA(cudaGetLastError());
     SGP_CUDA(cudaMemsetAsync(info, 0, sizeof(double), c.stream));
-    // opt-in INT8 route (sgp_set_ozaki_ex, stages bit 1): factor and inverse factor in one recursion; it never holds L
-    const bool oz_ok = c.ozaki_slices > 0;
-    const bool oz_fact = oz_ok && (c.ozaki_stages & 2) && Ainv && !L && n_pad > c.ozaki_leaf;
     if (oz_fact) {
         const size_t wb = ozaki_factinv_workspace_bytes(n_pad, c.ozaki_slices);
         SGP_TRY(c.ozbuf.reserve(wb));
@@ -974,10 +1041,12 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
     } else {
         SGP_TRY(potrf(c, K, n_pad, n_pad, c.Dinv.as<double>(), logparts, info));
     }
-    sum_logs_kernel<<<1, 32, 0, c.stream>>>(logparts, nt, info, dres);
+    if (kexp) sum_logs_scaled_kernel<<<1, 32, 0, c.stream>>>(logparts, nt, info, kexp, n, dres);
+    else sum_logs_kernel<<<1, 32, 0, c.stream>>>(logparts, nt, info, dres);
     SGP_CUDA(cudaGetLastError());
     if (L) {
-        extract_sym_kernel<<<1024, 256, 0, c.stream>>>(K, n_pad, dA, n, 0);
+        if (kexp) extract_scaled_kernel<<<1024, 256, 0, c.stream>>>(K, n_pad, dA, n, 0, kexp, -1, 0);        // L = S^-1 L^
+        else extract_sym_kernel<<<1024, 256, 0, c.stream>>>(K, n_pad, dA, n, 0);
         SGP_CUDA(cudaGetLastError());
         SGP_TRY(download(c, L, dA, (size_t)n * n));
     }
@@ -992,7 +1061,8 @@ int sgp_spd_factor(sgp_ctx* ctx, const double* A, long n, double* L, double* Ain
         } else {
             SGP_TRY(lauum(c, K, n_pad, n_pad, c.Wmat.as<double>(), n_pad));
         }
-        extract_sym_kernel<<<1024, 256, 0, c.stream>>>(c.Wmat.as<double>(), n_pad, dA, n, 1);
+        if (kexp) extract_scaled_kernel<<<1024, 256, 0, c.stream>>>(c.Wmat.as<double>(), n_pad, dA, n, 1, kexp, 1, 1);   // Ainv = S A^inv S
+        else extract_sym_kernel<<<1024, 256, 0, c.stream>>>(c.Wmat.as<double>(), n_pad, dA, n, 1);
         SGP_CUDA(cudaGetLastError());
         SGP_TRY(download(c, Ainv, dA, (size_t)n * n));
     }

@@ -384,3 +384,34 @@ def test_other_kernel_variants_on_the_int8_route(api, ozaki_all):
     v, g = api.nll_grad4(hyp, x, z, 4 * N2, with_sig=True)
     assert np.isclose(v, vr, rtol=1e-9), (v, vr)
     assert np.allclose(g, gr, rtol=1e-8, atol=1e-8 * np.abs(gr).max()), (g, gr)
+
+
+def test_int8_route_on_a_diagonally_scaled_matrix(api, ozaki_all):
+    """A = D B D with B well conditioned and d spanning 16 orders of magnitude.  The digits of the INT8 route are fixed-point numbers
+    relative to the maximum of each operand ROW: a spread of scales ALONG k (the columns of A21, the columns of X = L^-1) would eat
+    them, so sgp_spd_factor equilibrates an arbitrary matrix by powers of two first (exact, undone exactly in the outputs):
+    D Ainv D = B^-1 and the log-determinant as accurately as on the scale-invariant DMMA route."""
+    import scipy.linalg
+    rng = np.random.default_rng(11)
+    n = 1280
+    Q, _ = np.linalg.qr(rng.standard_normal((n, n)))
+    B = (Q * np.linspace(1.0, 50.0, n)) @ Q.T
+    B = 0.5 * (B + B.T)
+    Bi = scipy.linalg.inv(B)
+    dscale = 10.0 ** rng.uniform(-8, 8, n)
+    A = B * dscale[:, None] * dscale[None, :]
+    A = 0.5 * (A + A.T)
+    ldr = 0.5 * np.linalg.slogdet(B)[1] + np.sum(np.log(dscale))
+    out = {}
+    for name, ns in (("dmma", 0), ("int8", 7)):
+        ozaki_all.set_ozaki_ex(ns, 3 if ns else 1, 256)
+        _, Ai, ld = api.spd_factor(A, want_factor=False, want_inverse=True)
+        out[name] = (np.abs(Ai * dscale[:, None] * dscale[None, :] - Bi).max() / np.abs(Bi).max(), abs(ld - ldr) / abs(ldr))
+    print(f"\nD B D, 16 decades: DMMA {out['dmma'][0]:.1e} (logdet {out['dmma'][1]:.1e}), INT8 {out['int8'][0]:.1e} ({out['int8'][1]:.1e})")
+    assert out["dmma"][0] < 1e-11 and out["dmma"][1] < 1e-12, out
+    assert out["int8"][0] < 1e-11 and out["int8"][1] < 1e-12, out
+    # the factor comes back unscaled as well (lauum-only mode keeps L): L L^T = A
+    ozaki_all.set_ozaki_ex(7, 1, 256)
+    L, Ai, _ = api.spd_factor(A, want_factor=True, want_inverse=True)
+    assert np.abs((L @ L.T) / A - 1.0).max() < 1e-9
+    assert np.abs(Ai * dscale[:, None] * dscale[None, :] - Bi).max() / np.abs(Bi).max() < 1e-11

@@ -557,7 +557,8 @@ __global__ void __launch_bounds__(OZ_THREADS, 1) oz_gemm_kernel(const __grid_con
             const long m = (long)tm * OZ_M + 32 * warp + lane;
             const int eam = ((m < a.M) ? a.ea[m] : 0) - 7;
             asm volatile("bar.sync 1, 128;" ::: "memory");           // s_eb visible to the four epilogue warps
-            mbar_wait(&tmem_full, nt & 1u);
+            // the accumulators take the whole main loop of the tile (~10^5 clocks): wait with a back-off instead of polling
+            while (!mbar_try_wait(&tmem_full, nt & 1u)) __nanosleep(256);
             tc_fence_after();
 #pragma unroll 1
             for (int half = 0; half < OZ_N / 32; half++) {

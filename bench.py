@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--orbits", type=int, default=100000, help="orbits per GPU in the map leg")
     ap.add_argument("--map-steps", type=int, default=1000, help="map steps per launch in the map leg (config 04: 1000)")
     ap.add_argument("--cpu-budget", type=float, default=150.0, help="seconds the timed region of the CPU arm may take")
+    ap.add_argument("--route", default="dmma", choices=["dmma", "int8"],
+                    help="dmma (default, what north_star names): FP64 tensor-core DMMA everywhere; int8: the opt-in route of "
+                         "DESIGN.md 4.1 (factor + inverse + lauum from INT8 digit products on tcgen05) as the HEADLINE measurement")
+    ap.add_argument("--int8-digits", type=int, default=6, help="digits per operand of --route int8 (6: 47 bits, 7: 55 bits)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-map", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the config 01 / 03 / 05 legs")
@@ -404,6 +408,8 @@ def leg_headline(B):
     z_h = torch.from_numpy(d["ztrain"].copy()).pin_memory()
     x_d, z_d = x_h.to(B.dev), z_h.to(B.dev)
     step_dev, res_d = B.nll_dev_fn(hyp, x_d, z_d, n)
+    if a.route == "int8":
+        B.ctx.set_ozaki_ex(a.int8_digits, 3, 4096)
     for _ in range(max(a.warmup, 1)):
         step_dev()
     B.sync_all()
@@ -431,6 +437,8 @@ def leg_headline(B):
         B.api.nll_grad(hyp, xh_np, zh_np, n)
     torch.cuda.synchronize()
     t_e2e = B.max_over_ranks(time.perf_counter() - t0)
+    if a.route == "int8":
+        B.ctx.set_ozaki_ex(0, 1, 0)
     # full (2N x 2N) Hessian-block fill: the HBM-write roofline case (8 n^2 bytes)
     Kbuf = torch.empty(n * n, dtype=torch.float64, device=B.dev)
     hyp3 = (ctypes.c_double * 3)(*hyp[:3])
@@ -1002,7 +1010,7 @@ def main():
     n = head["n"]
     single = world == 1
     ozaki = None
-    if single and not a.no_configs:
+    if single and not a.no_configs and a.route == "dmma":
         try:
             ozaki = leg_ozaki(B, head["ms_per_step"], head["res"], dgemm_tflops, read_bf16_peak())
         except Exception as e:                           # noqa: BLE001 -- the opt-in leg must not take the headline line with it
@@ -1078,6 +1086,21 @@ def main():
                           "dfma_dp_instr_per_s": FP64_PEAK_MEASURED},
                 "result": {"nll": float(head["res"][0]), "grad": [float(head["res"][1]), float(head["res"][2])]},
                 }
+        if a.route == "int8":
+            # the opt-in route as the headline: the products are INT8 digit-pair GEMMs, so the roofline is the INT8 tensor rate
+            nd = a.int8_digits
+            pairs = nd * (nd + 1) // 2
+            t3 = (stages["potrf"] + stages["trtri"] + stages["lauum"]) * 1e-3
+            tops = pairs * float(n) ** 3 / t3 / 1e12
+            peak = 2.0 * read_bf16_peak(sustained=True)
+            line["dtype"] = f"f64 from {nd} int8 digits per operand ({8 * nd - 1} bits of every row's scale)"
+            line["config"]["route"] = f"int8 (opt-in, sgp_set_ozaki_ex({nd}, 3, 4096)); the default route is dmma"
+            line["roofline"] = {"kernel": f"oz_gemm_kernel<{nd}> (all sliced products of one evaluation; leaf blocks on DMMA included in the time)",
+                                "bound": "tensor", "achieved": tops, "peak": peak, "unit": "INT8 TOP/s", "frac": tops / peak, "traffic": None,
+                                "fp64_equiv_TFLOP/s": float(n) ** 3 / t3 / 1e12, "frac_of_dgemm": float(n) ** 3 / t3 / 1e12 / dgemm_tflops,
+                                "note": f"achieved = {pairs} digit-pair products x n^3 algorithmic operations / (factor + inverse + lauum stage "
+                                        "time); peak = 2 x bf16_tflops_sustained of MEASURED_PEAKS.json (no INT8 entry there; nominal INT8 = "
+                                        "2 x bf16; the sustained figure because the kernels run inside a 0.3 s step under the power cap)"}
         if ozaki:
             line["ozaki_opt_in"] = ozaki
         if sweep:
@@ -1129,13 +1152,13 @@ def read_traffic(n):
     return None, "no capture committed for this order"
 
 
-def read_bf16_peak():
-    """Measured cuBLAS bf16 burst rate (TFLOP/s) of this pool's B200s, else the fallback B200_PROFILING.md states."""
+def read_bf16_peak(sustained=False):
+    """Measured cuBLAS bf16 rate (TFLOP/s; burst or sustained) of this pool's B200s, else the fallback B200_PROFILING.md states."""
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["bf16_tflops"])
+            return float(json.load(f)["bf16_tflops_sustained" if sustained else "bf16_tflops"])
     except Exception:
-        return 1590.0
+        return 1400.0 if sustained else 1590.0
 
 
 def read_hbm_peak():

@@ -322,3 +322,41 @@ def test_sobol_of_the_learned_map_on_device(api, O):
     assert r["n_used"] == rh["n_used"]
     assert np.allclose(r["S1"], rh["S1"], atol=1e-10) and np.allclose(r["ST"], rh["ST"], atol=1e-10)
     assert r["ST"][1] > 0.5                                              # the final action is mostly the initial action
+
+
+def test_tokamak_map_at_baseline_training_size(api, C):
+    """BASELINE config 5's model size: the tokamak map kind with Nt = 16 384 training pairs (n = 32 768 kernel matrix, fitted on
+    the GPU exactly as bench.py's leg does), 96 orbits x 6 steps with the benchmarked solver against the C oracle started at the
+    same point and given the SAME model (alpha from the GPU fit): same loss pattern, 1e-8 on every orbit whose roots are roots."""
+    from sympgpr_b200 import workloads as W
+    Nt = 16384
+    d = W.tokamak_training(Nt)
+    hyp = hypp = f = fp = None
+    for factor in (1.0, 0.8, 0.65, 0.5):
+        h = W.aniso_hyp(Nt, d["sig"], 2 * np.pi, 9.4, factor, 1e-8)
+        hp = W.aniso_hyp(Nt, d["sigp"], 2 * np.pi, 9.4, factor, 1e-8)
+        try:
+            f = api.fit(h, d["xtrain"], d["ztrain"], 2 * Nt)
+            fp = api.fit(hp, d["xtrainp"], d["ztrainp"], Nt, reg=True)
+            hyp, hypp = h, hp
+            break
+        except np.linalg.LinAlgError:
+            continue
+    assert hyp is not None
+    xt, xtp = d["xtrain"], d["xtrainp"]
+    E, nm = 96, 7
+    q0 = W.halton(E, 5) * 2 * np.pi
+    p0 = 0.2 + 10.3 * W.halton(E, 7)                          # the ensemble of the bench leg: some orbits leave r < 0.5
+    out = C.applymap_alpha(3, nm, q0, p0, hyp[:3], hypp[:3], xtp[:Nt], xtp[Nt:], fp["alpha"], xt[:Nt], xt[Nt:], f["alpha"],
+                           want_notconv=True, start_delta=True)
+    qr, pr, maxres = out[0], out[1], out[-1]
+    good = maxres < 1e-10
+    q, p, st = api.applymap_tok(nm, E, hyp[:3], hypp[:3], q0, p0, xtp, None, None, xt, None, None, solver="newton_delta",
+                                alphap=fp["alpha"], alpha=f["alpha"], return_stats=True)
+    assert good.sum() >= 0.7 * E, good.sum()
+    assert np.array_equal(np.isnan(p[:, good]), np.isnan(pr[:, good]))
+    fin = ~np.isnan(pr)
+    dist = np.where(fin, np.maximum(_wrapdist(np.nan_to_num(q), np.nan_to_num(qr)), np.abs(np.nan_to_num(p) - np.nan_to_num(pr))), 0.0)
+    print(f"\ntokamak kind at Nt = {Nt}: {int(good.sum())} of {E} orbits comparable, {int(np.isnan(pr[-1]).sum())} lost, "
+          f"max distance over {nm - 1} steps {dist[:, good].max():.1e}")
+    assert dist[:, good].max() < 1e-8, dist[:, good].max()

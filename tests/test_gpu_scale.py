@@ -360,3 +360,33 @@ def test_tokamak_map_at_baseline_training_size(api, C):
     print(f"\ntokamak kind at Nt = {Nt}: {int(good.sum())} of {E} orbits comparable, {int(np.isnan(pr[-1]).sum())} lost, "
           f"max distance over {nm - 1} steps {dist[:, good].max():.1e}")
     assert dist[:, good].max() < 1e-8, dist[:, good].max()
+
+
+def test_dof2_map_at_baseline_training_size(api):
+    """BASELINE config 3's model size: the 2-DOF 4 x 4-block kernel with N = 8192 training pairs (n = 32 768, fitted on the GPU
+    with the length scale the bench leg finds), 24 orbits x 3 steps of map4_kernel against the oracle twin (oracle.applymap4:
+    grad F from build_k4 times the SAME alpha, Jacobian by differences): 1e-9.  Parity stays "unpinned" for this row (no
+    reference code); this checks the kernel against its twin at full size."""
+    from oracle import oracle as O
+    from sympgpr_b200 import workloads as W
+    N = 8192
+    x, z = W.henon_like_training(N)
+    f = hyp = None
+    for shrink in (1.0, 0.8, 0.65, 0.5):
+        h = W.dof2_hyp(N, z, shrink)
+        try:
+            f = api.fit(h, x, z, 4 * N, reg=4)
+            hyp = h
+            break
+        except np.linalg.LinAlgError:
+            continue
+    assert hyp is not None
+    E, nm = 24, 4
+    q0 = np.vstack((-0.3 + 0.6 * W.halton(E, 2, 7), -0.3 + 0.6 * W.halton(E, 3, 7)))
+    p0 = np.vstack((-0.3 + 0.6 * W.halton(E, 5, 7), -0.3 + 0.6 * W.halton(E, 7, 7)))
+    qr, pr = O.applymap4(nm, q0, p0, hyp[:3], x, f["alpha"])
+    q, p, st = api.applymap4(nm, E, hyp[:3], q0, p0, x, f["alpha"], return_stats=True)
+    dq, dp = np.abs(q - qr).max(), np.abs(p - pr).max()
+    print(f"\n2-DOF map at N = {N}: max |dq| {dq:.1e}, |dp| {dp:.1e} over {nm - 1} steps, unconverged {st['unconverged']}")
+    assert dq < 1e-9 and dp < 1e-9, (dq, dp)
+    assert st["unconverged"] == 0

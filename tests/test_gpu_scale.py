@@ -390,3 +390,40 @@ def test_dof2_map_at_baseline_training_size(api):
     print(f"\n2-DOF map at N = {N}: max |dq| {dq:.1e}, |dp| {dp:.1e} over {nm - 1} steps, unconverged {st['unconverged']}")
     assert dq < 1e-9 and dp < 1e-9, (dq, dp)
     assert st["unconverged"] == 0
+
+
+def test_config1_pendulum_100_orbits_1000_steps(api, C):
+    """BASELINE config 1 exactly as bench.py runs it: pendulum kick-drift map, product kernel, N = 200 training pairs fitted on the
+    GPU, 100 orbits x 1000 steps with the reference's solver (hybrd1 at the guess; the pendulum guess GP is trained on P).  Against
+    the C oracle on the same model: 1e-8 after 100 and after 1000 steps on the regular orbits (the oracle's own trajectories from p0
+    and p0 + 1e-12 differ by < 1e-9 after 1000 steps: everything outside the chaotic layer of the separatrix), and within 1e4 x
+    the oracle's own 1e-12 sensitivity elsewhere (a rounding difference of 1e-16 per step and a 1e-12 offset grow alike)."""
+    from sympgpr_b200 import workloads as W
+    N = 200
+    d = W.pendulum_training(N)
+    hyp = W.aniso_hyp(N, d["sig"], 2 * np.pi, 5.0, 1.0, 1e-8)
+    hypp = W.aniso_hyp(N, d["sigp"], 2 * np.pi, 5.0, 1.0, 1e-8)
+    f = api.fit(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    fp = api.fit(hypp, d["xtrainp"], d["ztrainp"], N, reg=True)
+    xt, xtp = d["xtrain"], d["xtrainp"]
+    E, nm = 100, 1001
+    q0 = W.halton(E, 5) * 2 * np.pi
+    p0 = -2.0 + 4.0 * W.halton(E, 7)
+    oa = C.applymap_alpha(0, nm, q0, p0, hyp[:3], hypp[:3], xtp[:N], xtp[N:], fp["alpha"], xt[:N], xt[N:], f["alpha"], want_notconv=True)
+    ob = C.applymap_alpha(0, nm, q0, p0 + 1e-12, hyp[:3], hypp[:3], xtp[:N], xtp[N:], fp["alpha"], xt[:N], xt[N:], f["alpha"])
+    qa, pa, good = oa[0], oa[1], oa[-1] < 1e-10
+    sens = np.maximum(_wrapdist(qa[-1], ob[0][-1]), np.abs(pa[-1] - ob[1][-1]))
+    sens100 = np.maximum(_wrapdist(qa[100], ob[0][100]), np.abs(pa[100] - ob[1][100]))
+    q, p = api.applymap(nm, E, hyp[:3], hypp[:3], q0, p0, xtp, None, None, xt, None, None, solver="hybrd", alphap=fp["alpha"],
+                        alpha=f["alpha"], out_every=100)
+    d100 = np.maximum(_wrapdist(q[1], qa[100]), np.abs(p[1] - pa[100]))
+    d1000 = np.maximum(_wrapdist(q[-1], qa[-1]), np.abs(p[-1] - pa[-1]))
+    regular = good & (sens < 1e-9)                     # the orbits outside the chaotic layer of the separatrix (SURVEY 8d)
+    print(f"\nconfig 1: {int(good.sum())} of {E} orbits comparable, {int(regular.sum())} regular; after 100 steps max {d100[good].max():.1e} "
+          f"(regular {d100[regular].max():.1e}); after 1000 steps regular median {np.median(d1000[regular]):.1e}, max {d1000[regular].max():.1e} "
+          f"(oracle's own 1e-12 sensitivity on them: median {np.median(sens[regular]):.1e})")
+    assert good.sum() >= 0.6 * E and regular.sum() >= 0.4 * E, (good.sum(), regular.sum())
+    assert d100[regular].max() < 1e-8 and d1000[regular].max() < 1e-8, (d100[regular].max(), d1000[regular].max())
+    # the chaotic layer: no closer than the oracle is to itself
+    assert np.all(d100[good] <= np.maximum(1e-8, 1e4 * sens100[good])), (d100[good].max(), sens100[good].max())
+    assert np.all(d1000[good] <= np.maximum(1e-8, 1e4 * sens[good]) + (sens[good] > 1e-5)), (d1000[good].max(), sens[good].max())

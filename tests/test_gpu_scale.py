@@ -427,3 +427,30 @@ def test_config1_pendulum_100_orbits_1000_steps(api, C):
     # the chaotic layer: no closer than the oracle is to itself
     assert np.all(d100[good] <= np.maximum(1e-8, 1e4 * sens100[good])), (d100[good].max(), sens100[good].max())
     assert np.all(d1000[good] <= np.maximum(1e-8, 1e4 * sens[good]) + (sens[good] > 1e-5)), (d1000[good].max(), sens[good].max())
+
+
+def test_largest_sweep_size_properties(api):
+    """The largest size of BASELINE's sweep, N = 32 768 training pairs (n = 65 536: 34 GB per matrix, no CPU golden is feasible):
+    size-independent properties.  (1) The gradient agrees with central differences of the NLL itself; (2) the opt-in INT8 route
+    (7 digits: 55 bits) reproduces value and gradient of the DMMA route -- two independent factorisations of the same matrix."""
+    from sympgpr_b200 import _lib, workloads as W
+    N = 32768
+    d = W.standard_map_training(N)
+    hyp = W.timing_hyp(N, d["sig"], 1e-8)
+    ctx = _lib.context()
+    try:
+        v, gr = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+        h = 1e-5 * hyp[0]
+        hp, hm = hyp.copy(), hyp.copy()
+        hp[0] += h
+        hm[0] -= h
+        fd = (api.nll_chol(hp, d["xtrain"], d["ztrain"], 2 * N) - api.nll_chol(hm, d["xtrain"], d["ztrain"], 2 * N)) / (2 * h)
+        ctx.set_ozaki_ex(7, 3, 4096)
+        v8, g8 = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    finally:
+        ctx.set_ozaki_ex(0, 1, 0)
+        ctx.release_workspace()
+    print(f"\nn = {2 * N}: nll {v!r}; d/dlx {gr[0]:.10e} against central differences {fd:.10e}; INT8 route (7 digits): nll rel "
+          f"{abs(v8 - v) / abs(v):.1e}, grad rel {np.max(np.abs(g8 - gr) / np.abs(gr)):.1e}")
+    assert abs(fd - gr[0]) <= 2e-5 * abs(gr[0]), (fd, gr[0])
+    assert abs(v8 - v) <= 1e-9 * abs(v) and np.allclose(g8, gr, rtol=1e-9), (v8, v, g8, gr)

@@ -454,3 +454,35 @@ def test_largest_sweep_size_properties(api):
           f"{abs(v8 - v) / abs(v):.1e}, grad rel {np.max(np.abs(g8 - gr) / np.abs(gr)):.1e}")
     assert abs(fd - gr[0]) <= 2e-5 * abs(gr[0]), (fd, gr[0])
     assert abs(v8 - v) <= 1e-9 * abs(v) and np.allclose(g8, gr, rtol=1e-9), (v8, v, g8, gr)
+
+
+def test_fill_at_the_headline_size(api):
+    """build_K at BASELINE's headline size (N = 16 384: a 32 768 x 32 768 matrix, 8.6 GB, through the f2py-signature entry point with
+    a host array): 1e-12 on blocks spread over all four quadrants against the oracle's closed forms, and the symmetry of the whole
+    matrix sampled on 10^6 entry pairs."""
+    from oracle import oracle as O
+    from sympgpr_b200 import workloads as W
+    N = 16384
+    d = W.standard_map_training(N)
+    hyp = W.timing_hyp(N, d["sig"], 1e-8)
+    xt = d["xtrain"]
+    K = np.empty((2 * N, 2 * N), order="F")
+    api.build_K(xt, xt, hyp[:3], K)
+    rng = np.random.default_rng(7)
+    B = 384
+    worst = 0.0
+    for (r0, c0) in ((0, 0), (N - B, 3000), (5000, N - B), (N - B, N - B), (123, 9000), (16000, 200)):
+        for (qr, qc) in ((0, 0), (1, 0), (0, 1), (1, 1)):                   # the xx, yx, xy, yy quadrants of the Hessian-block matrix
+            ref = O.build_k_vec(xt[r0:r0 + B], xt[N + r0:N + r0 + B], xt[c0:c0 + B], xt[N + c0:N + c0 + B], hyp[:3])
+            got = K[qr * N + r0:qr * N + r0 + B, qc * N + c0:qc * N + c0 + B]
+            refq = ref[qr * B:(qr + 1) * B, qc * B:(qc + 1) * B]
+            err = np.abs(got - refq).max() / max(np.abs(refq).max(), 1e-300)
+            worst = max(worst, err)
+            assert np.allclose(got, refq, rtol=1e-12, atol=1e-12 * hyp[2]), (r0, c0, qr, qc, err)
+    i = rng.integers(0, 2 * N, 1_000_000)
+    j = rng.integers(0, 2 * N, 1_000_000)
+    # (a, b) and (b, a) are evaluated independently (the fused multiply-adds of the addition theorem are not symmetric in their
+    # operands), so the symmetry holds to rounding, as in the reference's element-wise Fortran loop
+    asym = np.abs(K[i, j] - K[j, i]).max()
+    assert np.allclose(K[i, j], K[j, i], rtol=1e-12, atol=1e-13 * hyp[2]), asym
+    print(f"\nfill at n = {2 * N}: worst block error {worst:.1e} (relative to the block maximum), max |K_ij - K_ji| {asym:.1e} on 1e6 sampled pairs")

@@ -187,8 +187,12 @@ constexpr int DB = 32;
 //            d = row_j[0]; l = row[0] / sqrt(d); row[c-1] = row[c] - l * L(j+c, j)
 //   inverse: lane r accumulates row r of X = L^-1 in x[0..31] (x = e_r at the start);
 //            step k: lane k scales its finished row by 1/l_kk; lanes r > k: x[c] -= L(r,k) X(k,c)
-__device__ __noinline__ void warp_factor32(double* S, int k0, double* xd, int* info, int col0)
+__device__ __noinline__ void warp_factor32(double* S, int k0, double* xd, int* info, int col0, double* lbuf)
 {
+    // Column j of the block travels through shared memory instead of 31 double shuffles (62 SHFL per column bound the old
+    // version at ~480 clocks per column): every lane stores its L(r, j) into a 32-double line (two lines, alternating), one
+    // __syncwarp, then the line is read back as broadcast 16-byte loads.  Fully unrolled (about 1500 instructions), the row
+    // stays in registers with fixed indices, same operations and order as before: bit-identical results.
     const int lane = threadIdx.x & 31;
     const unsigned FULL = 0xffffffffu;
     double* Sr = S + (k0 + lane) * LL_LD + k0;
@@ -197,26 +201,31 @@ __device__ __noinline__ void warp_factor32(double* S, int k0, double* xd, int* i
     for (int c = 0; c < DB; c++) row[c] = (c <= lane) ? Sr[c] : 0.0;
     double myinv = 1.0;
     int bad = 0;
-    // two halves: after 16 shifts only 15 live columns remain, so the second half moves half the data
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const int NC = half == 0 ? DB : DB / 2;              // live register slots in this half
-        LL_UNROLL
-        for (int j = half * (DB / 2); j < (half + 1) * (DB / 2); j++) {
-            double d = __shfl_sync(FULL, row[0], j);
-            const bool neg = !(d > 0.0);                     // also NaN
-            bad = (neg && bad == 0) ? j + 1 : bad;
-            d = neg ? 1.0 : d;
-            const double inv = rsqrt(d);
-            const double lj = (lane == j) ? d * inv : row[0] * inv;
-            myinv = (lane == j) ? inv : myinv;
-            Sr[j] = (lane >= j) ? lj : Sr[j];                // (plain select + store: no divergent branch)
-#pragma unroll
-            for (int c = 1; c < NC; c++) {
-                const double lc = __shfl_sync(FULL, lj, (j + c) & 31);   // L(j + c, j); wrapped lanes give garbage in dead slots
-                row[c - 1] = fma(-lj, lc, row[c]);
+    for (int j = 0; j < DB; j++) {
+        double d = __shfl_sync(FULL, row[j], j);
+        const bool neg = !(d > 0.0);                     // also NaN
+        bad = (neg && bad == 0) ? j + 1 : bad;
+        d = neg ? 1.0 : d;
+        const double inv = rsqrt(d);
+        const double lj = (lane == j) ? d * inv : row[j] * inv;
+        myinv = (lane == j) ? inv : myinv;
+        Sr[j] = (lane >= j) ? lj : Sr[j];                // (plain select + store: no divergent branch)
+        if (j < DB - 1) {
+            double* line = lbuf + (j & 1) * DB;
+            line[lane] = lj;
+            __syncwarp();
+            int c = j + 1;
+            if (c & 1) {
+                row[c] = fma(-lj, line[c], row[c]);
+                c++;
             }
-            row[NC - 1] = 0.0;
+#pragma unroll
+            for (; c < DB; c += 2) {
+                const double2 l2 = *reinterpret_cast<const double2*>(line + c);         // L(c, j), L(c + 1, j)
+                row[c] = fma(-lj, l2.x, row[c]);
+                row[c + 1] = fma(-lj, l2.y, row[c + 1]);
+            }
         }
     }
     if (bad != 0 && lane == 0) atomicCAS(info, 0, col0 + k0 + bad);
@@ -372,7 +381,7 @@ __device__ __noinline__ void diag_tile_factor_invert(double* S, double* xd, doub
         unsigned long long tw0 = 0ull;
         if (stamp && tid == 0) tw0 = globaltimer();
         __syncwarp();                                        // (trace only diverges lane 0: re-converge, or the shuffles take their slow path)
-        if (warp == 0) warp_factor32(S, k0, xd, info, col0);
+        if (warp == 0) warp_factor32(S, k0, xd, info, col0, scratch);
         else if (warp == 1 && kb > 0) warp_invert32(S, k0 - DB, xd);
         if (stamp && tid == 0) stamp[3] += globaltimer() - tw0;      // trace: time in the warp-level block factorisations
         consumer_bar();

@@ -233,40 +233,33 @@ __device__ __noinline__ void warp_factor32(double* S, int k0, double* xd, int* i
     __syncwarp();
 }
 
-// warp 0 only, after warp_factor32: inverse of the factored diagonal block (reads L and xd from shared memory, writes
-// X^T into the block's strict upper triangle).  Runs while the other consumer warps do the panel and the trailing update.
+// One warp, after warp_factor32: inverse of the factored diagonal block (reads L and xd from shared memory, writes X^T into the
+// block's strict upper triangle).  Runs while another warp factors the next block / the other warps form the off-diagonal part
+// of the tile inverse.  Lane c solves L x = e_c for column c of X by forward substitution, on its own: no shuffles, no
+// synchronisation -- every L(r, k) is a broadcast load (all lanes read the same address), the column lives in 32 registers,
+// rows above the diagonal come out as exact zeros by themselves.  496 FMAs per lane on four partial sums per row, fully
+// unrolled (the shuffle version that accumulated ROWS of X took 7.8 us per block and set the pace of the factorisation phases).
 __device__ __noinline__ void warp_invert32(double* S, int k0, const double* xd)
 {
     const int lane = threadIdx.x & 31;
-    const unsigned FULL = 0xffffffffu;
-    double* Sr = S + (k0 + lane) * LL_LD + k0;
-    const double myinv = xd[k0 + lane];
-    double row[DB];
+    const double* L0 = S + k0 * LL_LD + k0;                  // L(r, k) = L0[r * LL_LD + k]
+    double x[DB];
 #pragma unroll
-    for (int c = 0; c < DB; c++) row[c] = (c == lane) ? 1.0 : 0.0;
-    double lk = Sr[0];
-    // two halves: rows k < 16 of X have no entries beyond column 15
+    for (int r = 0; r < DB; r++) {
+        const double* Lr = L0 + r * LL_LD;
+        double s[4] = {(r == lane) ? 1.0 : 0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const int NC = half == 0 ? DB / 2 : DB;
-        LL_UNROLL
-        for (int k = half * (DB / 2); k < (half + 1) * (DB / 2); k++) {
-            const double lnext = Sr[(k + 1) & 31];           // L(r, k+1): off the dependent chain
-            const double sc = (lane == k) ? myinv : 1.0;
-            const double ml = (lane > k) ? -lk : 0.0;
-#pragma unroll
-            for (int c = 0; c < NC; c++) {
-                const double xs = row[c] * sc;
-                const double xkc = __shfl_sync(FULL, xs, k); // X(k, c), final
-                row[c] = fma(ml, xkc, xs);
-            }
-            lk = lnext;
+        for (int k = 0; k < r; k++) {
+            const int slot = (k == r - 1) ? 0 : 1 + (k % 3);     // the newest x joins the chain that ends the row
+            s[slot] = fma(-Lr[k], x[k], s[slot]);
         }
+        x[r] = ((s[1] + s[2]) + s[3] + s[0]) * xd[k0 + r];
     }
-    // X(r, c), r > c, transposed into the strict upper triangle of the block
+    // X(r, c), r > c, transposed into the strict upper triangle of the block: lane c owns row k0 + c of S
+    double* Sc = S + (k0 + lane) * LL_LD + k0;
 #pragma unroll
-    for (int c = 0; c < DB; c++)
-        if (c < lane) S[(k0 + c) * LL_LD + k0 + lane] = row[c];
+    for (int r = 1; r < DB; r++)
+        if (r > lane) Sc[r] = x[r];
     __syncwarp();
 }
 

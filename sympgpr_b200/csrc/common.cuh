@@ -58,6 +58,17 @@ struct DBuf {
     template <class T> T* as() const { return (T*)p; }
 };
 
+// cudaFuncSetAttribute applies to the CURRENT device: a process that drives several devices (one context each) must opt every
+// kernel into its large dynamic shared memory once per device.  Returns true the first time it is called for (flags, device).
+inline bool first_use_on_current_device(bool (&flags)[64])
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;        // unknown: configure again (harmless)
+    if (flags[dev]) return false;
+    flags[dev] = true;
+    return true;
+}
+
 constexpr int TILE = 128;
 inline long round_up(long v, long m) { return (v + m - 1) / m * m; }
 

@@ -255,11 +255,10 @@ inline int ws_sm_count()
 template <int AL, int BL>
 inline cudaError_t gemm_ws_launch_t(const GemmArgs& a, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_current_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_f64_ws_kernel<AL, BL, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     const long nt = gemm_num_tiles(a);
     if (nt <= 0 || a.K <= 0) return cudaSuccess;
@@ -273,11 +272,10 @@ inline cudaError_t gemm_ws_launch_t(const GemmArgs& a, cudaStream_t st)
 template <int AL, int BL>
 inline cudaError_t gemm_ws_launch_grouped_t(const GemmGroupEntry* d_grp, int nprob, long ntiles, cudaStream_t st)
 {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_current_device(configured)) {
         cudaError_t e = cudaFuncSetAttribute(gemm_f64_ws_kernel<AL, BL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WS_SMEM);
         if (e != cudaSuccess) return e;
-        configured = true;
     }
     if (nprob <= 0 || ntiles <= 0) return cudaSuccess;
     const int sms = ws_sm_count();

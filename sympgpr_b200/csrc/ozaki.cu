@@ -695,11 +695,9 @@ template <int NS>
 int oz_launch(Ctx& c, const CUtensorMap& tmA, const CUtensorMap& tmB, const OzArgs& a)
 {
     const size_t smem = (size_t)OZ_STAGES * NS * (OZ_M + OZ_N) * OZ_KC + 1024;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_current_device(configured))
         SGP_CUDA(cudaFuncSetAttribute(oz_gemm_kernel<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
-    }
     const int sms = c.sm_count > 0 ? c.sm_count : 148;
     oz_gemm_kernel<NS><<<(unsigned)(a.ntiles < sms ? a.ntiles : sms), OZ_THREADS, smem, c.stream>>>(tmA, tmB, a);
     SGP_CUDA(cudaGetLastError());

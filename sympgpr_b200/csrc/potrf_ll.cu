@@ -684,11 +684,10 @@ size_t potrf_ll_flag_bytes(long n_pad)
 int potrf_ll(Ctx& c, double* A, long n_pad, long lda, double* Dinv, double* logparts, int* info, int* flags, const double* y,
              double* w)
 {
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {};
+    if (first_use_on_current_device(configured)) {
         SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
         SGP_CUDA(cudaFuncSetAttribute(potrf_ll_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)LL_SMEM));
-        configured = true;
     }
     static_assert((size_t)TILE * LL_LD * sizeof(double) + (4 * TILE + 32 * 96) * sizeof(double) <= (size_t)WS_STAGES * 2 * STAGE_DOUBLES * sizeof(double),
                   "diagonal tile scratch must fit in the operand ring");

@@ -486,3 +486,31 @@ def test_fill_at_the_headline_size(api):
     asym = np.abs(K[i, j] - K[j, i]).max()
     assert np.allclose(K[i, j], K[j, i], rtol=1e-12, atol=1e-13 * hyp[2]), asym
     print(f"\nfill at n = {2 * N}: worst block error {worst:.1e} (relative to the block maximum), max |K_ij - K_ji| {asym:.1e} on 1e6 sampled pairs")
+
+
+def test_two_devices_in_one_process(api):
+    """One host process driving two GPUs (a context per device): the kernels' opt-in to large dynamic shared memory is a per-device
+    attribute, so the second device must be configured as well.  NLL + gradient through the C ABI on device 1 (DMMA route and
+    INT8 route) against the default context on device 0.  Skipped on a one-GPU box."""
+    import ctypes
+    from oracle import oracle as O
+    from sympgpr_b200 import _lib
+    if _lib.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    N = 700
+    d = O.standard_map_training(N)
+    hyp = O.timing_hyp(N, d["sig"], 1e-8)
+    v0, g0 = api.nll_grad(hyp, d["xtrain"], d["ztrain"], 2 * N)
+    ctx1 = _lib.Context(1)
+    try:
+        L = _lib.lib()
+        res = np.zeros(16)
+        x = np.ascontiguousarray(d["xtrain"]); z = np.ascontiguousarray(d["ztrain"])
+        for ns in (0, 7):
+            ctx1.set_ozaki_ex(ns, 3 if ns else 1, 256)
+            st = L.sgp_nll(ctx1.handle, 0, 0.5, 0, _lib.dptr(np.ascontiguousarray(hyp)), _lib.dptr(x), _lib.dptr(z), 2 * N, 2, _lib.dptr(res))
+            _lib.check(st, "sgp_nll on device 1")
+            assert np.isclose(res[0], v0, rtol=1e-11), (ns, res[0], v0)
+            assert np.allclose(res[1:3], g0, rtol=1e-9), (ns, res[1:3], g0)
+    finally:
+        ctx1.close()

@@ -1,6 +1,6 @@
 """Run a reference example script unchanged against libsympgpr_b200.
 
-    python -m sympgpr_b200.runner /path/to/python/02_pert_pendulum/main.py [--family sq] [--solver newton_delta]
+    python -m sympgpr_b200.runner /path/to/python/02_pert_pendulum/main.py [--family sq] [--solver newton_delta] [--int8-digits 7]
 
 Registers the shim modules under the names the reference imports (`sympgpr`, `fortran.sympgpr`,
 `kernels`, `kernels_sq`, `kernels_sum`, `fieldlines`), puts the reference's `python/` directory on
@@ -33,10 +33,14 @@ def family_of(script_dir):
     return "product"
 
 
-def run(script, family="auto", per=0.5, solver="hybrd", run_name="__main__"):
+def run(script, family="auto", per=0.5, solver="hybrd", run_name="__main__", int8_digits=0):
     import sympgpr_b200
     if solver not in SOLVER_CHOICES:
         raise ValueError(f"solver must be one of {SOLVER_CHOICES}")
+    if int8_digits:
+        # opt-in INT8 route for the script's NLL / fit calls: factor + inverse + lauum from INT8 digit products
+        from sympgpr_b200 import _lib
+        _lib.context().set_ozaki_ex(int(int8_digits), 3, 0)
     script = os.path.abspath(script)
     ex_dir = os.path.dirname(script)
     if family == "auto":
@@ -74,8 +78,10 @@ def main():
     ap.add_argument("--family", default="auto", choices=FAMILY_CHOICES)
     ap.add_argument("--per", type=float, default=0.5)
     ap.add_argument("--solver", default="hybrd", choices=SOLVER_CHOICES)
+    ap.add_argument("--int8-digits", type=int, default=0, choices=[0, 4, 5, 6, 7, 8],
+                    help="opt-in INT8 route for the training stages (0 = off, the default DMMA route; 6: 47 bits, 7: 55 bits)")
     a = ap.parse_args()
-    run(a.script, a.family, a.per, a.solver)
+    run(a.script, a.family, a.per, a.solver, int8_digits=a.int8_digits)
 
 
 if __name__ == "__main__":
